@@ -1,0 +1,407 @@
+// Drop-in command-line driver: same argv / rspecifier / wspecifier / exit-code
+// contract as upstream Kaldi's nnet3-xvector-compute, as invoked by
+//   egs/sre/v5/sid/nnet3/xvector/extract_xvectors_new.sh:84-93
+//     nnet3-xvector-compute --use-gpu=no --min-chunk-size=$min --chunk-size=$chunk "$nnet" "$feat" ark,scp:A,B
+// and the two-stream variant invoked by
+//   egs/sre/v5/sid/nnet3_cvector/cvector/extract_cvectors_with_am.sh:99-110
+//     nnet3-cvector-compute-multiple-input ... --name="$input_name" 2 "$nnet" "$feat" "$feat_am" ark,scp:A,B
+// (that binary is referenced but not shipped by the reference; semantics = the
+// single-input program with N named inputs read in lock-step).
+//
+// Chunking / averaging follows nnet3-xvector-compute.cc main();
+// the forward pass itself goes through the C ABI (include/cvx.h) to the CUDA side.
+// Utterances are packed into row batches; a worker thread runs cvx_extract on one
+// batch while the main thread keeps reading the feature pipe(s) into the other.
+#include "extract_main.h"
+
+#include <chrono>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <memory>
+#include <thread>
+
+#include "../../../include/cvx.h"
+#include "../kaldi_io.h"
+
+namespace cvx {
+namespace {
+
+struct HostBatch {
+  std::vector<float*> feats;        // pinned, per stream
+  std::vector<size_t> cap_rows;     // per stream capacity in rows
+  std::vector<int32_t> dims;
+  int64_t rows = 0;
+  std::vector<std::string> keys;
+  std::vector<int64_t> chunk_start;
+  std::vector<int32_t> chunk_len, chunk_utt;
+  std::vector<float> chunk_weight;
+  std::vector<float> out;
+  int64_t frames = 0;  // un-padded input frames of the successful utterances
+
+  void Reset() {
+    rows = 0;
+    frames = 0;
+    keys.clear();
+    chunk_start.clear();
+    chunk_len.clear();
+    chunk_utt.clear();
+    chunk_weight.clear();
+  }
+  void Reserve(int64_t need_rows) {
+    for (size_t s = 0; s < feats.size(); ++s) {
+      if (static_cast<size_t>(need_rows) <= cap_rows[s]) continue;
+      size_t ncap = std::max<size_t>(static_cast<size_t>(need_rows) * 5 / 4, 1 << 16);
+      void* p = nullptr;
+      if (cvx_host_alloc(&p, ncap * dims[s] * sizeof(float)) != CVX_OK) throw KaldiError(cvx_last_error());
+      if (rows) std::memcpy(p, feats[s], static_cast<size_t>(rows) * dims[s] * sizeof(float));
+      cvx_host_free(feats[s]);
+      feats[s] = static_cast<float*>(p);
+      cap_rows[s] = ncap;
+    }
+  }
+  void AppendRow(const std::vector<const float*>& src_rows) {
+    for (size_t s = 0; s < feats.size(); ++s)
+      std::memcpy(feats[s] + static_cast<size_t>(rows) * dims[s], src_rows[s], dims[s] * sizeof(float));
+    ++rows;
+  }
+  ~HostBatch() {
+    for (float* p : feats) cvx_host_free(p);
+  }
+};
+
+std::string ReadOutputNodeFromConfig(const std::string& path) {
+  // accepts the one-line extract.config written by run_xvector_new.sh:123 /
+  // extract_xvectors_new.sh:58: "output-node name=output input=<descriptor>"
+  std::ifstream f(path);
+  if (!f) throw KaldiError("cannot open --nnet-config file " + path);
+  std::string line;
+  while (std::getline(f, line)) {
+    size_t h = line.find('#');
+    if (h != std::string::npos) line = line.substr(0, h);
+    if (line.find("output-node") == std::string::npos) continue;
+    if (line.find("name=output ") == std::string::npos && line.find("name=output\t") == std::string::npos) continue;
+    size_t p = line.find("input=");
+    if (p == std::string::npos) continue;
+    std::string v = line.substr(p + 6);
+    size_t q = v.find(" objective=");
+    if (q != std::string::npos) v = v.substr(0, q);
+    while (!v.empty() && std::isspace(static_cast<unsigned char>(v.back()))) v.pop_back();
+    return v;
+  }
+  throw KaldiError("no 'output-node name=output input=...' line in " + path);
+}
+
+}  // namespace
+
+int ExtractMain(int argc, const char* const* argv, bool multiple_input) {
+  try {
+    const char* usage_single =
+        "Computes one embedding (x-vector / c-vector) per utterance: runs the frame-level\n"
+        "TDNN layers, the statistics pooling and the segment-level layers of an nnet3 raw\n"
+        "model up to output-node 'output' on the GPU.  With --chunk-size, long utterances\n"
+        "are cut into chunks, one embedding is computed per chunk and the chunk embeddings\n"
+        "are averaged weighted by their frame counts.\n"
+        "\n"
+        "Usage: nnet3-xvector-compute [options] <raw-nnet-in> "
+        "<features-rspecifier> <vector-wspecifier>\n"
+        "e.g.: nnet3-xvector-compute final.raw scp:feats.scp "
+        "ark:nnet_prediction.ark\n"
+        "See also: nnet3-compute\n";
+    const char* usage_multi =
+        "Like nnet3-xvector-compute, for networks with several input nodes\n"
+        "(e.g. speaker features + phonetic/AM features).  The i-th name in --name\n"
+        "is the input-node fed by the i-th feature rspecifier; all streams are read\n"
+        "in lock-step and must have the same keys and row counts.\n"
+        "\n"
+        "Usage: nnet3-cvector-compute-multiple-input [options] --name=n1,n2 <num-inputs> "
+        "<raw-nnet-in> <features-rspecifier-1> ... <features-rspecifier-n> <vector-wspecifier>\n";
+    ParseOptions po(multiple_input ? usage_multi : usage_single);
+
+    std::string use_gpu = "yes", output_node, nnet_config, precision = "fp16", names;
+    int32_t chunk_size = -1, min_chunk_size = 100, gpu_id = -1;
+    int64_t batch_rows = 1 << 20, max_batch_rows = 0;
+    bool pad_input = false, profile = false;
+    // accepted for command-line compatibility with nnet3 programs; no effect here
+    int32_t ign_i[4] = {0, 0, 0, 0};
+    float ign_f = 1.0f;
+    bool ign_b[2] = {false, false};
+    std::string ign_s;
+
+    po.Register("use-gpu", &use_gpu, "yes|no|optional|wait, accepted for compatibility; this program always runs on a GPU");
+    po.Register("chunk-size", &chunk_size,
+                "Frames per chunk; embeddings of the chunks are averaged. -1 = one chunk per utterance.");
+    po.Register("min-chunk-size", &min_chunk_size, "Shortest chunk (in frames) an embedding is computed from.");
+    po.Register("pad-input", &pad_input,
+                "If true, duplicate the first and last frames of the input features as required to equal min-chunk-size "
+                "(newer Kaldi default); if false, chunks shorter than min-chunk-size are skipped (older Kaldi).");
+    po.Register("output-node", &output_node,
+                "Descriptor to use as output-node 'output' (same effect as piping the model through "
+                "nnet3-copy --nnet-config=extract.config)");
+    po.Register("nnet-config", &nnet_config, "File with an 'output-node name=output input=...' line (extract.config)");
+    po.Register("precision", &precision, "TDNN operand type: fp16 | bf16 | fp32 (fp32 = slow validation kernels)");
+    po.Register("gpu-id", &gpu_id, "CUDA device ordinal (-1: $CVX_DEVICE or 0)");
+    po.Register("batch-rows", &batch_rows, "Frames read from the feature pipe(s) per cvx_extract call");
+    po.Register("max-batch-rows", &max_batch_rows, "Frames per packed device batch (0 = engine default)");
+    po.Register("profile", &profile, "Print per-kernel CUDA-event times at the end");
+    if (multiple_input) po.Register("name", &names, "Comma-separated input-node names, one per feature stream");
+    po.Register("frame-subsampling-factor", &ign_i[0], "ignored");
+    po.Register("extra-left-context", &ign_i[1], "ignored");
+    po.Register("extra-right-context", &ign_i[2], "ignored");
+    po.Register("frames-per-chunk", &ign_i[3], "ignored");
+    po.Register("acoustic-scale", &ign_f, "ignored");
+    po.Register("debug-computation", &ign_b[0], "ignored");
+    po.Register("optimization.optimize", &ign_b[1], "ignored");
+    po.Register("cache-capacity", &ign_i[0], "ignored");
+
+    po.Read(argc, argv);
+    int num_inputs = 1;
+    int arg = 1;
+    if (multiple_input) {
+      if (po.NumArgs() < 4) {
+        po.PrintUsage();
+        return 1;
+      }
+      num_inputs = std::atoi(po.GetArg(arg++).c_str());
+      if (num_inputs < 1 || po.NumArgs() != num_inputs + 3) {
+        po.PrintUsage();
+        return 1;
+      }
+    } else if (po.NumArgs() != 3) {
+      po.PrintUsage();
+      return 1;
+    }
+    const std::string nnet_rxfilename = po.GetArg(arg++);
+    std::vector<std::string> feat_rspecifiers;
+    for (int i = 0; i < num_inputs; ++i) feat_rspecifiers.push_back(po.GetArg(arg++));
+    const std::string vector_wspecifier = po.GetArg(arg++);
+
+    if (use_gpu != "yes" && use_gpu != "no" && use_gpu != "optional" && use_gpu != "wait")
+      throw KaldiError("invalid value for --use-gpu: " + use_gpu);
+    if (use_gpu == "no") CVX_LOG("--use-gpu=no requested; this implementation has no CPU path and runs on the GPU");
+    if (!nnet_config.empty()) output_node = ReadOutputNodeFromConfig(nnet_config);
+    int32_t prec;
+    if (precision == "fp16") prec = CVX_PRECISION_FP16;
+    else if (precision == "bf16") prec = CVX_PRECISION_BF16;
+    else if (precision == "fp32") prec = CVX_PRECISION_FP32;
+    else throw KaldiError("invalid --precision " + precision);
+    if (gpu_id < 0) {
+      const char* e = std::getenv("CVX_DEVICE");
+      gpu_id = e ? std::atoi(e) : 0;
+    }
+
+    cvx_model* model = nullptr;
+    if (cvx_model_load(nnet_rxfilename.c_str(), output_node.empty() ? nullptr : output_node.c_str(), &model) != CVX_OK)
+      throw KaldiError(std::string("reading ") + nnet_rxfilename + ": " + cvx_last_error());
+    cvx_model_info info;
+    cvx_model_get_info(model, &info);
+    if (po.verbose >= 1) CVX_LOG("extraction plan:\n" << cvx_model_describe(model));
+    if (info.num_inputs != num_inputs)
+      throw KaldiError("the network reads " + std::to_string(info.num_inputs) + " input node(s) but " +
+                       std::to_string(num_inputs) + " feature stream(s) were given");
+    // stream order: --name maps rspecifier i to input node name[i]
+    std::vector<int> stream_of_arg(num_inputs);
+    for (int i = 0; i < num_inputs; ++i) stream_of_arg[i] = i;
+    if (multiple_input && !names.empty()) {
+      std::vector<std::string> nm;
+      size_t p = 0;
+      while (p <= names.size()) {
+        size_t q = names.find(',', p);
+        if (q == std::string::npos) q = names.size();
+        nm.push_back(names.substr(p, q - p));
+        p = q + 1;
+      }
+      if (static_cast<int>(nm.size()) != num_inputs) throw KaldiError("--name must list " + std::to_string(num_inputs) + " names");
+      for (int i = 0; i < num_inputs; ++i) {
+        int found = -1;
+        for (int s = 0; s < info.num_inputs; ++s)
+          if (nm[i] == cvx_model_input_name(model, s)) found = s;
+        if (found < 0) throw KaldiError("the network has no input-node named '" + nm[i] + "'");
+        stream_of_arg[i] = found;
+      }
+    }
+
+    cvx_engine_options eo;
+    cvx_engine_options_default(&eo);
+    eo.device = gpu_id;
+    eo.precision = prec;
+    eo.max_batch_rows = max_batch_rows;
+    eo.profile = profile ? 1 : 0;
+    cvx_engine* engine = nullptr;
+    if (cvx_engine_create(model, &eo, &engine) != CVX_OK) throw KaldiError(std::string("creating the GPU engine: ") + cvx_last_error());
+
+    std::vector<std::unique_ptr<SequentialMatrixReader>> readers;
+    for (int i = 0; i < num_inputs; ++i) readers.emplace_back(new SequentialMatrixReader(feat_rspecifiers[i]));
+    VectorWriter writer(vector_wspecifier);
+
+    HostBatch hb[2];
+    for (HostBatch& b : hb) {
+      b.feats.assign(num_inputs, nullptr);
+      b.cap_rows.assign(num_inputs, 0);
+      b.dims.resize(num_inputs);
+      for (int s = 0; s < num_inputs; ++s) b.dims[s] = cvx_model_input_dim(model, s);
+    }
+    const int32_t E = info.embedding_dim;
+    const int32_t ctx = info.left_context + info.right_context + 1;
+    int64_t num_success = 0, num_fail = 0, frame_count = 0;
+    auto t_start = std::chrono::steady_clock::now();
+
+    std::thread worker;
+    struct Joiner {
+      std::thread& t;
+      ~Joiner() {
+        if (t.joinable()) t.join();
+      }
+    } joiner{worker};
+    int worker_status = CVX_OK;
+    std::string worker_error;
+    int inflight = -1;
+    auto finish_inflight = [&]() {
+      if (inflight < 0) return;
+      worker.join();
+      if (worker_status != CVX_OK) throw KaldiError("cvx_extract failed: " + worker_error);
+      HostBatch& b = hb[inflight];
+      for (size_t u = 0; u < b.keys.size(); ++u) writer.Write(b.keys[u], b.out.data() + u * E, E);
+      num_success += static_cast<int64_t>(b.keys.size());
+      frame_count += b.frames;
+      b.Reset();
+      inflight = -1;
+    };
+    auto launch = [&](int which) {
+      HostBatch& b = hb[which];
+      if (b.keys.empty()) return;
+      finish_inflight();
+      b.out.assign(b.keys.size() * static_cast<size_t>(E), 0.f);
+      inflight = which;
+      worker = std::thread([&, which]() {
+        HostBatch& w = hb[which];
+        std::vector<const float*> f(w.feats.begin(), w.feats.end());
+        worker_status = cvx_extract(engine, f.data(), num_inputs, w.rows, w.chunk_start.data(), w.chunk_len.data(),
+                                    w.chunk_utt.data(), w.chunk_weight.data(), static_cast<int64_t>(w.chunk_start.size()),
+                                    static_cast<int32_t>(w.keys.size()), w.out.data(), 0);
+        if (worker_status != CVX_OK) worker_error = cvx_last_error();
+      });
+    };
+
+    int cur = 0;
+    std::vector<const Matrix*> mats(num_inputs);
+    std::vector<const float*> row_ptrs(num_inputs);
+    for (; !readers[0]->Done(); ) {
+      const std::string utt = readers[0]->Key();
+      bool ok = true;
+      for (int i = 0; i < num_inputs; ++i) {
+        if (readers[i]->Done() || readers[i]->Key() != utt)
+          throw KaldiError("feature streams are not in lock-step at utterance " + utt);
+        mats[stream_of_arg[i]] = &readers[i]->Value();
+      }
+      const int32_t T = mats[0]->rows;
+      for (int s = 0; s < num_inputs; ++s) {
+        if (mats[s]->rows != T) {
+          CVX_WARN("Feature streams of " << utt << " have different numbers of rows (" << T << " vs " << mats[s]->rows << ")");
+          ok = false;
+        }
+        if (T > 0 && mats[s]->cols != hb[cur].dims[s])
+          throw KaldiError("feature dimension " + std::to_string(mats[s]->cols) + " of " + utt + " does not match the network's input dim " +
+                           std::to_string(hb[cur].dims[s]));
+      }
+      if (ok && T == 0) {
+        CVX_WARN("Zero-length utterance: " << utt);
+        ok = false;
+      }
+      if (ok && !pad_input && T < min_chunk_size) {
+        CVX_WARN("Minimum chunk size of " << min_chunk_size << " is greater than the number of rows in utterance: " << utt);
+        ok = false;
+      }
+      if (ok) {
+        // nnet3-xvector-compute.cc main(): this_chunk_size, num_chunks, per-chunk offset
+        int32_t this_chunk = chunk_size;
+        if (chunk_size == -1 || T < chunk_size) this_chunk = T;
+        const int32_t num_chunks = (T + this_chunk - 1) / this_chunk;
+        HostBatch& b = hb[cur];
+        b.Reserve(b.rows + T + std::max(min_chunk_size, 0));
+        const int32_t utt_index = static_cast<int32_t>(b.keys.size());
+        const size_t chunks_before = b.chunk_start.size();
+        const int64_t rows_before = b.rows;
+        for (int32_t ci = 0; ci < num_chunks; ++ci) {
+          const int32_t begin = ci * this_chunk;
+          const int32_t offset = std::min(this_chunk, T - begin);
+          int32_t left_pad = 0, right_pad = 0;
+          bool use = true;
+          if (offset < min_chunk_size) {
+            if (!pad_input) use = false;
+            else {
+              left_pad = (min_chunk_size - offset) / 2;
+              right_pad = min_chunk_size - offset - left_pad;
+            }
+          }
+          const int32_t rows_here = left_pad + offset + right_pad;
+          if (use && rows_here < ctx) {
+            CVX_WARN("Chunk of " << rows_here << " frames of utterance " << utt << " is shorter than the network's context ("
+                                 << ctx << " frames); skipping it");
+            use = false;
+          }
+          const int64_t start = b.rows;
+          auto put = [&](int32_t r) {
+            for (int s = 0; s < num_inputs; ++s) row_ptrs[s] = mats[s]->Row(r);
+            b.AppendRow(row_ptrs);
+          };
+          for (int32_t k = 0; k < left_pad; ++k) put(begin);
+          for (int32_t r = begin; r < begin + offset; ++r) put(r);
+          for (int32_t k = 0; k < right_pad; ++k) put(begin + offset - 1);
+          if (use) {
+            b.chunk_start.push_back(start);
+            b.chunk_len.push_back(rows_here);
+            b.chunk_utt.push_back(utt_index);
+            b.chunk_weight.push_back(static_cast<float>(offset));
+          }
+        }
+        if (b.chunk_start.size() == chunks_before) {
+          CVX_WARN("No usable chunk in utterance " << utt);
+          b.rows = rows_before;
+          ok = false;
+        } else {
+          b.keys.push_back(utt);
+          b.frames += T;
+        }
+      }
+      if (!ok) ++num_fail;
+      for (int i = 0; i < num_inputs; ++i) readers[i]->Next();
+      if (hb[cur].rows >= batch_rows) {
+        launch(cur);
+        cur ^= 1;
+        if (inflight == cur) finish_inflight();
+      }
+    }
+    for (int i = 1; i < num_inputs; ++i)
+      if (!readers[i]->Done()) CVX_WARN("feature stream " << (i + 1) << " has extra utterances after the first stream ended");
+    launch(cur);
+    finish_inflight();
+    for (auto& r : readers) {
+      int st = r->Close();
+      if (st != 0) CVX_WARN("a feature input pipe exited with status " << st);
+    }
+    writer.Close();
+
+    double elapsed = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
+    CVX_LOG("Time taken " << elapsed << "s: real-time factor assuming 100 frames/sec is "
+                          << (frame_count > 0 ? elapsed * 100.0 / static_cast<double>(frame_count) : 0.0));
+    CVX_LOG("Done " << num_success << " utterances, failed for " << num_fail);
+    if (profile) {
+      cvx_kernel_profile recs[16];
+      int32_t n = 0;
+      cvx_engine_get_profile(engine, recs, 16, &n);
+      for (int32_t i = 0; i < n; ++i)
+        CVX_LOG("profile " << recs[i].name << ": launches=" << recs[i].launches << " ms=" << recs[i].total_ms
+                           << (recs[i].flops > 0 ? " TFLOP/s=" + std::to_string(recs[i].flops / recs[i].total_ms * 1e-9) : "")
+                           << (recs[i].bytes > 0 ? " GB/s=" + std::to_string(recs[i].bytes / recs[i].total_ms * 1e-6) : ""));
+    }
+    cvx_engine_destroy(engine);
+    cvx_model_free(model);
+    return num_success != 0 ? 0 : 1;
+  } catch (const std::exception& e) {
+    LogMessage("ERROR", "main", __FILE__, __LINE__, e.what());
+    return -1 & 0xff;
+  }
+}
+
+}  // namespace cvx

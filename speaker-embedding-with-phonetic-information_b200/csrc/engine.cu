@@ -1,0 +1,711 @@
+// Engine: lowers a Plan to device resources and runs the hot path.
+//
+// HBM layout (all row-major, one packed ragged batch of chunks at a time):
+//   features     fp32 [rows, D_s] per input stream (device copy of the caller's rows)
+//   staging      elem [rows_cap, roundup(sum tap dims, 64)]  spliced first-layer operand
+//   activations  elem [rows_cap, roundup(N_l, 64)] per frame layer; pad columns are zero
+//   weights      elem [roundup(N_l,64), K_pad] per layer, tap-major, each tap padded to the
+//                source buffer's row pitch; BatchNorm scale folded into rows
+//   stats        fp32 [chunks_in_batch, 2*D]   pooled mean | stddev
+//   chunk_emb    fp32 [num_chunks, E]          per-chunk embeddings of the whole call
+// Row r of every frame-level buffer is the same time step of the same chunk: edge
+// rows of a chunk read their neighbours' rows and hold garbage that pooling never
+// reads (a layer's valid rows are [start+left, start+len-right)).
+#include "engine.h"
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace cvx {
+
+namespace {
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn GetEncodeTiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  CVX_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+  if (q != cudaDriverEntryPointSuccess || !p) throw CudaError("cuTensorMapEncodeTiled is not available in this driver");
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+// 2-D map over a row-major [rows, ld] matrix of 2-byte elements, box = box_cols x box_rows,
+// 128-byte swizzle (box_cols * 2 bytes == 128), out-of-bounds reads give zeros.
+void Encode2D(CUtensorMap* map, int32_t elem, void* base, int64_t rows, int64_t ld, uint32_t box_cols,
+              uint32_t box_rows) {
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(ld), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = GetEncodeTiled()(map, elem == kBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                                base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw CudaError("cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r)));
+}
+
+inline int32_t RoundUp(int32_t v, int32_t m) { return (v + m - 1) / m * m; }
+
+void ConvertToElem(const float* src, size_t n, int32_t elem, void* dst) {
+  if (elem == kF32) {
+    std::memcpy(dst, src, n * 4);
+  } else if (elem == kF16) {
+    __half* d = static_cast<__half*>(dst);
+    for (size_t i = 0; i < n; ++i) d[i] = __float2half_rn(std::min(std::max(src[i], -65504.f), 65504.f));
+  } else {
+    __nv_bfloat16* d = static_cast<__nv_bfloat16*>(dst);
+    for (size_t i = 0; i < n; ++i) d[i] = __float2bfloat16_rn(src[i]);
+  }
+}
+
+float ElemToFloat(const void* p, size_t i, int32_t elem) {
+  if (elem == kF32) return static_cast<const float*>(p)[i];
+  if (elem == kF16) return __half2float(static_cast<const __half*>(p)[i]);
+  return __bfloat162float(static_cast<const __nv_bfloat16*>(p)[i]);
+}
+
+const char* kProfNames[] = {"stage_input", "tdnn_gemm", "stats_pool_partial", "stats_pool_finalize",
+                            "segment_affine", "utt_average"};
+
+}  // namespace
+
+template <typename T>
+T* Engine::DevAlloc(size_t n) {
+  void* p = nullptr;
+  CVX_CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+  return static_cast<T*>(p);
+}
+
+void Engine::Grow(void** p, size_t* cap, size_t bytes) {
+  if (bytes <= *cap) return;
+  CVX_CUDA_CHECK(cudaStreamSynchronize(compute_));
+  CVX_CUDA_CHECK(cudaStreamSynchronize(copy_));
+  if (*p) CVX_CUDA_CHECK(cudaFree(*p));
+  *p = nullptr;
+  size_t want = bytes + bytes / 8;
+  CVX_CUDA_CHECK(cudaMalloc(p, want));
+  *cap = want;
+}
+
+Engine::Engine(const Plan& plan, const cvx_engine_options& opts) : plan_(plan), opts_(opts) {
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    throw CudaError(std::string("no usable CUDA device (") + cudaGetErrorString(e) + "); this path has no CPU fallback");
+  if (opts.device < 0 || opts.device >= ndev) throw InvalidArgument("device ordinal out of range");
+  CVX_CUDA_CHECK(cudaSetDevice(opts.device));
+  cudaDeviceProp prop;
+  CVX_CUDA_CHECK(cudaGetDeviceProperties(&prop, opts.device));
+  num_sms_ = prop.multiProcessorCount;
+  if (opts.precision == CVX_PRECISION_FP16) elem_ = kF16;
+  else if (opts.precision == CVX_PRECISION_BF16) elem_ = kBF16;
+  else if (opts.precision == CVX_PRECISION_FP32) elem_ = kF32;
+  else throw InvalidArgument("unknown precision");
+  if (elem_ != kF32 && prop.major != 10)
+    throw CudaError("the tcgen05 path needs an sm_100a device (Blackwell B200); found sm_" + std::to_string(prop.major) +
+                    std::to_string(prop.minor));
+  debug_ = static_cast<uint32_t>(opts.reserved[0]);
+  profile_ = opts.profile != 0;
+  max_batch_rows_ = opts.max_batch_rows > 0 ? opts.max_batch_rows : (int64_t{1} << 19);
+  max_batch_rows_ = (max_batch_rows_ + kGemmBlockM - 1) / kGemmBlockM * kGemmBlockM;
+
+  CVX_CUDA_CHECK(cudaStreamCreateWithFlags(&compute_, cudaStreamNonBlocking));
+  CVX_CUDA_CHECK(cudaStreamCreateWithFlags(&copy_, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    CVX_CUDA_CHECK(cudaEventCreateWithFlags(&feat_ready_[i], cudaEventDisableTiming));
+    CVX_CUDA_CHECK(cudaEventCreateWithFlags(&feat_free_[i], cudaEventDisableTiming));
+  }
+  if (plan_.input_dims.size() > kMaxASources) throw InvalidArgument("too many input streams");
+
+  // ---- lower frame layers ----
+  layer_buffer_.assign(plan_.frame.size(), -1);
+  for (size_t li = 0; li < plan_.frame.size(); ++li) {
+    const Layer& L = plan_.frame[li];
+    FrameOp op;
+    op.layer = static_cast<int32_t>(li);
+    op.n_pad = RoundUp(L.out_dim, 64);
+    bool all_inputs = true;
+    for (const Tap& t : L.taps) all_inputs = all_inputs && t.src < 0;
+    std::vector<std::pair<int32_t, int32_t>> col_map;  // (logical k begin, padded k begin) per tap; dims via plan
+    std::vector<int32_t> tap_dims;
+    if (all_inputs && !(debug_ & kDebugForceTapPath)) {
+      // compact splice: one staging buffer holds Append(...) exactly as W's columns expect
+      int32_t b = StagingFor(L.taps);
+      op.srcs.push_back(b);
+      op.k_pad = buffers_[b].ld;
+      for (int32_t j = 0; j < op.k_pad / kGemmBlockK; ++j) op.kb.push_back({0, j * kGemmBlockK, 0});
+      col_map.push_back({0, 0});
+      tap_dims.push_back(L.in_dim);
+    } else {
+      int32_t klog = 0, kpad = 0;
+      for (const Tap& t : L.taps) {
+        int32_t b;
+        if (t.src < 0) b = StagingFor({Tap{t.src, 0}});  // plain converted copy of the stream
+        else b = layer_buffer_[t.src];
+        int32_t si = -1;
+        for (size_t s = 0; s < op.srcs.size(); ++s)
+          if (op.srcs[s] == b) si = static_cast<int32_t>(s);
+        if (si < 0) {
+          if (op.srcs.size() >= kMaxASources) throw InvalidArgument("layer " + L.name + " appends more than 4 distinct sources");
+          si = static_cast<int32_t>(op.srcs.size());
+          op.srcs.push_back(b);
+        }
+        const int32_t d = buffers_[b].dim, dp = buffers_[b].ld;
+        for (int32_t j = 0; j < dp / kGemmBlockK; ++j) op.kb.push_back({si, j * kGemmBlockK, t.offset});
+        col_map.push_back({klog, kpad});
+        tap_dims.push_back(d);
+        klog += d;
+        kpad += dp;
+      }
+      op.k_pad = kpad;
+    }
+    if (op.kb.size() > kMaxKBlocks)
+      throw InvalidArgument("layer " + L.name + ": padded K " + std::to_string(op.k_pad) + " exceeds " +
+                            std::to_string(kMaxKBlocks * kGemmBlockK));
+
+    // weights: fold BatchNorm scale into rows, re-pack columns, convert
+    std::vector<float> wp(static_cast<size_t>(op.n_pad) * op.k_pad, 0.f);
+    std::vector<float2> post(op.n_pad, make_float2(0.f, 0.f));
+    for (int32_t n = 0; n < L.out_dim; ++n) {
+      float s = L.scale.empty() ? 1.f : L.scale[n];
+      if (L.relu && !(s > 0.f))
+        throw InvalidArgument("layer " + L.name + ": BatchNorm scale <= 0 after ReLU cannot be folded");
+      for (size_t t = 0; t < col_map.size(); ++t)
+        for (int32_t c = 0; c < tap_dims[t]; ++c)
+          wp[static_cast<size_t>(n) * op.k_pad + col_map[t].second + c] =
+              L.weight[static_cast<size_t>(n) * L.in_dim + col_map[t].first + c] * s;
+      post[n] = make_float2((L.bias.empty() ? 0.f : L.bias[n]) * s, L.offset.empty() ? 0.f : L.offset[n]);
+    }
+    std::vector<uint8_t> wconv(wp.size() * ElemSize(elem_));
+    ConvertToElem(wp.data(), wp.size(), elem_, wconv.data());
+    CVX_CUDA_CHECK(cudaMalloc(&op.d_w, wconv.size()));
+    CVX_CUDA_CHECK(cudaMemcpy(op.d_w, wconv.data(), wconv.size(), cudaMemcpyHostToDevice));
+    op.d_post = DevAlloc<float2>(post.size());
+    CVX_CUDA_CHECK(cudaMemcpy(op.d_post, post.data(), post.size() * sizeof(float2), cudaMemcpyHostToDevice));
+
+    Buffer ob;
+    ob.ld = op.n_pad;
+    ob.dim = L.out_dim;
+    op.out_buffer = static_cast<int32_t>(buffers_.size());
+    buffers_.push_back(ob);
+    layer_buffer_[li] = op.out_buffer;
+    std::memset(&op.targs, 0, sizeof(op.targs));
+    frame_ops_.push_back(std::move(op));
+  }
+
+  // ---- segment layers (fp32) ----
+  for (const Layer& L : plan_.segment) {
+    SegOp s;
+    s.in_dim = L.in_dim;
+    s.out_dim = L.out_dim;
+    s.relu = L.relu;
+    s.d_w = DevAlloc<float>(L.weight.size());
+    CVX_CUDA_CHECK(cudaMemcpy(s.d_w, L.weight.data(), L.weight.size() * 4, cudaMemcpyHostToDevice));
+    if (!L.bias.empty()) {
+      s.d_b = DevAlloc<float>(L.bias.size());
+      CVX_CUDA_CHECK(cudaMemcpy(s.d_b, L.bias.data(), L.bias.size() * 4, cudaMemcpyHostToDevice));
+    }
+    if (!L.scale.empty()) {
+      s.d_scale = DevAlloc<float>(L.scale.size());
+      s.d_offset = DevAlloc<float>(L.offset.size());
+      CVX_CUDA_CHECK(cudaMemcpy(s.d_scale, L.scale.data(), L.scale.size() * 4, cudaMemcpyHostToDevice));
+      CVX_CUDA_CHECK(cudaMemcpy(s.d_offset, L.offset.data(), L.offset.size() * 4, cudaMemcpyHostToDevice));
+    }
+    seg_ops_.push_back(s);
+  }
+}
+
+Engine::~Engine() {
+  cudaSetDevice(opts_.device);
+  cudaDeviceSynchronize();
+  for (Buffer& b : buffers_)
+    if (b.ptr) cudaFree(b.ptr);
+  for (FrameOp& op : frame_ops_) {
+    cudaFree(op.d_w);
+    cudaFree(op.d_post);
+  }
+  for (SegOp& s : seg_ops_) {
+    cudaFree(s.d_w);
+    cudaFree(s.d_b);
+    cudaFree(s.d_scale);
+    cudaFree(s.d_offset);
+  }
+  for (int i = 0; i < 2; ++i)
+    for (int s = 0; s < kMaxASources; ++s) cudaFree(d_feat_[i][s]);
+  void* scratch[] = {d_slabs_, d_chunk_slab_off_, d_weights_, d_utt_off_, d_partials_, d_stats_,
+                     d_seg_[0], d_seg_[1], d_chunk_emb_, d_out_};
+  for (void* p : scratch) cudaFree(p);
+  for (cudaEvent_t ev : event_pool_) cudaEventDestroy(ev);
+  for (PendingEvent& pe : pending_) {
+    cudaEventDestroy(pe.a);
+    cudaEventDestroy(pe.b);
+  }
+  for (int i = 0; i < 2; ++i) {
+    if (feat_ready_[i]) cudaEventDestroy(feat_ready_[i]);
+    if (feat_free_[i]) cudaEventDestroy(feat_free_[i]);
+  }
+  if (compute_) cudaStreamDestroy(compute_);
+  if (copy_) cudaStreamDestroy(copy_);
+}
+
+int32_t Engine::StagingFor(const std::vector<Tap>& taps) {
+  for (const Staging& s : stagings_) {
+    if (s.taps.size() != taps.size()) continue;
+    bool same = true;
+    for (size_t i = 0; i < taps.size(); ++i)
+      same = same && s.taps[i].stream == -1 - taps[i].src && s.taps[i].offset == taps[i].offset;
+    if (same) return s.buffer;
+  }
+  if (taps.size() > kMaxStageTaps) throw InvalidArgument("first-layer splice has more than 16 taps");
+  Staging s;
+  int32_t col = 0;
+  for (const Tap& t : taps) {
+    StageTap st;
+    st.stream = -1 - t.src;
+    st.offset = t.offset;
+    st.dim = plan_.input_dims[st.stream];
+    st.col0 = col;
+    col += st.dim;
+    s.taps.push_back(st);
+  }
+  Buffer b;
+  b.dim = col;
+  b.ld = RoundUp(col, 64);
+  s.buffer = static_cast<int32_t>(buffers_.size());
+  buffers_.push_back(b);
+  stagings_.push_back(s);
+  return s.buffer;
+}
+
+void Engine::EnsureRows(int64_t rows) {
+  int64_t need = (rows + kGemmBlockM - 1) / kGemmBlockM * kGemmBlockM;
+  if (need <= rows_cap_) return;
+  CVX_CUDA_CHECK(cudaStreamSynchronize(compute_));
+  CVX_CUDA_CHECK(cudaStreamSynchronize(copy_));
+  for (Buffer& b : buffers_) {
+    if (b.ptr) CVX_CUDA_CHECK(cudaFree(b.ptr));
+    b.ptr = nullptr;
+  }
+  rows_cap_ = need;
+  for (Buffer& b : buffers_) {
+    size_t bytes = static_cast<size_t>(rows_cap_) * b.ld * ElemSize(elem_);
+    CVX_CUDA_CHECK(cudaMalloc(&b.ptr, bytes));
+    CVX_CUDA_CHECK(cudaMemsetAsync(b.ptr, 0, bytes, compute_));
+  }
+  EncodeMaps();
+}
+
+void Engine::EncodeMaps() {
+  if (elem_ == kF32) return;
+  for (FrameOp& op : frame_ops_) {
+    TdnnGemmArgs& a = op.targs;
+    std::memset(&a, 0, sizeof(a));
+    for (size_t s = 0; s < op.srcs.size(); ++s) {
+      const Buffer& b = buffers_[op.srcs[s]];
+      Encode2D(&a.a_maps[s], elem_, b.ptr, rows_cap_, b.ld, kGemmBlockK, kGemmBlockM);
+    }
+    for (size_t s = op.srcs.size(); s < kMaxASources; ++s) a.a_maps[s] = a.a_maps[0];
+    Encode2D(&a.b_map, elem_, op.d_w, op.n_pad, op.k_pad, kGemmBlockK, kGemmBlockN);
+    const Buffer& ob = buffers_[op.out_buffer];
+    Encode2D(&a.c_map, elem_, ob.ptr, rows_cap_, ob.ld, 64, 32);
+    a.num_kb = static_cast<int32_t>(op.kb.size());
+    for (size_t i = 0; i < op.kb.size(); ++i) a.kb[i] = op.kb[i];
+    a.n_pad = op.n_pad;
+    a.num_n_tiles = (op.n_pad + kGemmBlockN - 1) / kGemmBlockN;
+    a.post = op.d_post;
+    a.relu = plan_.frame[op.layer].relu ? 1 : 0;
+    a.ab_format = elem_ == kBF16 ? 1 : 0;
+  }
+}
+
+// ------------------------------------------------------------- profile ----
+void Engine::ProfBegin(int cls, double flops, double bytes) {
+  ++launches_;
+  if (!profile_) return;
+  PendingEvent pe;
+  pe.cls = cls;
+  pe.flops = flops;
+  pe.bytes = bytes;
+  for (cudaEvent_t* ev : {&pe.a, &pe.b}) {
+    if (!event_pool_.empty()) {
+      *ev = event_pool_.back();
+      event_pool_.pop_back();
+    } else {
+      CVX_CUDA_CHECK(cudaEventCreate(ev));
+    }
+  }
+  CVX_CUDA_CHECK(cudaEventRecord(pe.a, compute_));
+  pending_.push_back(pe);
+}
+
+void Engine::ProfEnd() {
+  if (!profile_) return;
+  CVX_CUDA_CHECK(cudaEventRecord(pending_.back().b, compute_));
+}
+
+void Engine::ProfResolve() {
+  if (!profile_) return;
+  for (PendingEvent& pe : pending_) {
+    float ms = 0.f;
+    CVX_CUDA_CHECK(cudaEventElapsedTime(&ms, pe.a, pe.b));
+    prof_ms_[pe.cls] += ms;
+    prof_flops_[pe.cls] += pe.flops;
+    prof_bytes_[pe.cls] += pe.bytes;
+    prof_launches_[pe.cls] += 1;
+    event_pool_.push_back(pe.a);
+    event_pool_.push_back(pe.b);
+  }
+  pending_.clear();
+}
+
+int Engine::GetProfile(cvx_kernel_profile* recs, int32_t max_recs) {
+  int n = 0;
+  for (int c = 0; c < kNumProf && n < max_recs; ++c) {
+    std::memset(&recs[n], 0, sizeof(recs[n]));
+    std::strncpy(recs[n].name, kProfNames[c], sizeof(recs[n].name) - 1);
+    recs[n].launches = prof_launches_[c];
+    recs[n].total_ms = prof_ms_[c];
+    recs[n].flops = prof_flops_[c];
+    recs[n].bytes = prof_bytes_[c];
+    ++n;
+  }
+  return n;
+}
+
+void Engine::ResetProfile() {
+  for (int c = 0; c < kNumProf; ++c) prof_ms_[c] = prof_flops_[c] = prof_bytes_[c] = 0, prof_launches_[c] = 0;
+}
+
+// ---------------------------------------------------------- frame pass ----
+void Engine::RunFrames(const float* const* dev_feats, int64_t rows, int64_t src_row_min, int64_t src_row_max) {
+  for (const Staging& s : stagings_) {
+    StageArgs a;
+    std::memset(&a, 0, sizeof(a));
+    for (size_t i = 0; i < plan_.input_dims.size(); ++i) {
+      a.feats[i] = dev_feats[i];
+      a.feat_dim[i] = plan_.input_dims[i];
+    }
+    a.num_taps = static_cast<int32_t>(s.taps.size());
+    for (size_t i = 0; i < s.taps.size(); ++i) a.taps[i] = s.taps[i];
+    a.out = buffers_[s.buffer].ptr;
+    a.ld_out = buffers_[s.buffer].ld;
+    a.elem = elem_;
+    a.rows = rows;
+    a.src_row_min = src_row_min;
+    a.src_row_max = src_row_max;
+    ProfBegin(kProfStage, 0, static_cast<double>(rows) * (buffers_[s.buffer].dim * 4.0 + a.ld_out * ElemSize(elem_)));
+    CVX_CUDA_CHECK(LaunchStageInput(a, compute_));
+    ProfEnd();
+  }
+  for (FrameOp& op : frame_ops_) {
+    const Layer& L = plan_.frame[op.layer];
+    const double flops = 2.0 * static_cast<double>(rows) * L.in_dim * L.out_dim;
+    ProfBegin(kProfGemm, flops, 0);
+    if (elem_ == kF32) {
+      TdnnGemmSimtArgs a;
+      std::memset(&a, 0, sizeof(a));
+      for (size_t s = 0; s < op.srcs.size(); ++s) {
+        a.a_src[s] = static_cast<const float*>(buffers_[op.srcs[s]].ptr);
+        a.a_ld[s] = buffers_[op.srcs[s]].ld;
+      }
+      a.num_kb = static_cast<int32_t>(op.kb.size());
+      for (size_t i = 0; i < op.kb.size(); ++i) a.kb[i] = op.kb[i];
+      a.w = static_cast<const float*>(op.d_w);
+      a.k_pad = op.k_pad;
+      a.n_pad = op.n_pad;
+      a.post = op.d_post;
+      a.relu = L.relu ? 1 : 0;
+      a.out = static_cast<float*>(buffers_[op.out_buffer].ptr);
+      a.ld_out = buffers_[op.out_buffer].ld;
+      a.rows = rows;
+      a.rows_cap = rows_cap_;
+      CVX_CUDA_CHECK(LaunchTdnnGemmSimt(a, compute_));
+    } else {
+      op.targs.num_m_tiles = static_cast<int32_t>((rows + kGemmBlockM - 1) / kGemmBlockM);
+      CVX_CUDA_CHECK(LaunchTdnnGemm(op.targs, num_sms_, compute_));
+    }
+    ProfEnd();
+  }
+}
+
+void Engine::DebugForwardFrames(const float* const* feats, int64_t rows, float* out) {
+  CVX_CUDA_CHECK(cudaSetDevice(opts_.device));
+  if (rows <= 0) throw InvalidArgument("rows must be positive");
+  EnsureRows(rows);
+  const float* dev[kMaxASources] = {};
+  for (size_t s = 0; s < plan_.input_dims.size(); ++s) {
+    size_t bytes = static_cast<size_t>(rows) * plan_.input_dims[s] * 4;
+    Grow(&d_feat_[0][s], &d_feat_cap_[0][s], bytes);
+    CVX_CUDA_CHECK(cudaMemcpyAsync(d_feat_[0][s], feats[s], bytes, cudaMemcpyHostToDevice, compute_));
+    dev[s] = static_cast<const float*>(d_feat_[0][s]);
+  }
+  RunFrames(dev, rows, 0, rows);
+  const Buffer& b = buffers_[frame_ops_.back().out_buffer];
+  std::vector<uint8_t> host(static_cast<size_t>(rows) * b.ld * ElemSize(elem_));
+  CVX_CUDA_CHECK(cudaMemcpyAsync(host.data(), b.ptr, host.size(), cudaMemcpyDeviceToHost, compute_));
+  CVX_CUDA_CHECK(cudaStreamSynchronize(compute_));
+  ProfResolve();
+  for (int64_t r = 0; r < rows; ++r)
+    for (int32_t c = 0; c < b.dim; ++c) out[r * b.dim + c] = ElemToFloat(host.data(), static_cast<size_t>(r) * b.ld + c, elem_);
+}
+
+// -------------------------------------------------------------- extract ----
+void Engine::Extract(const float* const* feats, int32_t num_streams, int64_t total_rows, const int64_t* chunk_start,
+                     const int32_t* chunk_len, const int32_t* chunk_utt, const float* chunk_weight,
+                     int64_t num_chunks, int32_t num_utts, float* out, uint32_t flags) {
+  CVX_CUDA_CHECK(cudaSetDevice(opts_.device));
+  if (num_streams != static_cast<int32_t>(plan_.input_dims.size()))
+    throw InvalidArgument("model has " + std::to_string(plan_.input_dims.size()) + " input stream(s), got " +
+                          std::to_string(num_streams));
+  if (num_utts < 0 || num_chunks < 0 || total_rows < 0) throw InvalidArgument("negative size");
+  if (!out && num_utts > 0) throw InvalidArgument("out is NULL");
+  const int32_t E = plan_.EmbeddingDim();
+  const bool dev_in = (flags & CVX_FLAG_DEVICE_INPUT) != 0, dev_out = (flags & CVX_FLAG_DEVICE_OUTPUT) != 0;
+  if (num_utts == 0) return;
+  if (num_chunks == 0) {
+    if (dev_out) CVX_CUDA_CHECK(cudaMemset(out, 0, static_cast<size_t>(num_utts) * E * 4));
+    else std::memset(out, 0, static_cast<size_t>(num_utts) * E * 4);
+    return;
+  }
+  for (int32_t s = 0; s < num_streams; ++s)
+    if (!feats || !feats[s]) throw InvalidArgument("feats[" + std::to_string(s) + "] is NULL");
+
+  const Layer& PL = plan_.frame[plan_.pool_src];
+  const int32_t L = PL.left, R = PL.right;
+  const int32_t lc = plan_.pool_left_context, rc = plan_.pool_right_context;
+  (void)lc;  // left >= 0 >= -lc: the window's left edge never binds
+
+  // ---- validate chunks, cut batches, build pooling slabs ----
+  struct Batch {
+    int64_t c0, c1, row0, row1;
+    int64_t slab0, slab1;
+  };
+  std::vector<Batch> batches;
+  std::vector<PoolSlab> slabs;
+  std::vector<int32_t> chunk_slab_off(num_chunks + 1, 0);
+  std::vector<int64_t> utt_off(static_cast<size_t>(num_utts) + 1, 0);
+  std::vector<float> weights(num_chunks);
+  int64_t prev_end = 0;
+  int32_t prev_utt = 0;
+  int64_t max_chunk_rows = 0;
+  for (int64_t c = 0; c < num_chunks; ++c) {
+    const int64_t st = chunk_start[c];
+    const int32_t len = chunk_len[c];
+    if (st < prev_end || len <= 0 || st + len > total_rows)
+      throw InvalidArgument("chunk " + std::to_string(c) + " is out of order, overlapping or out of range");
+    if (chunk_utt[c] < prev_utt || chunk_utt[c] >= num_utts)
+      throw InvalidArgument("chunk_utt must be non-decreasing and < num_utts");
+    if (std::min<int64_t>(len - 1 - R, rc) < L)
+      throw InvalidArgument("chunk " + std::to_string(c) + " has " + std::to_string(len) + " rows but the network needs " +
+                            std::to_string(L + R + 1) + " (left " + std::to_string(L) + ", right " + std::to_string(R) + ")");
+    prev_end = st + len;
+    prev_utt = chunk_utt[c];
+    utt_off[chunk_utt[c] + 1] += 1;
+    weights[c] = chunk_weight ? chunk_weight[c] : static_cast<float>(len);
+    max_chunk_rows = std::max<int64_t>(max_chunk_rows, len);
+  }
+  for (int32_t u = 0; u < num_utts; ++u) utt_off[u + 1] += utt_off[u];
+  const int64_t cap = std::max(max_batch_rows_, (max_chunk_rows + kGemmBlockM - 1) / kGemmBlockM * kGemmBlockM);
+  {
+    int64_t c = 0;
+    while (c < num_chunks) {
+      Batch b;
+      b.c0 = c;
+      b.row0 = chunk_start[c];
+      b.slab0 = static_cast<int64_t>(slabs.size());
+      while (c < num_chunks && chunk_start[c] + chunk_len[c] - b.row0 <= cap) {
+        const int64_t lo = chunk_start[c] - b.row0 + L;
+        const int64_t hi = chunk_start[c] - b.row0 + std::min<int64_t>(chunk_len[c] - 1 - R, rc);  // inclusive
+        chunk_slab_off[c] = static_cast<int32_t>(slabs.size() - b.slab0);
+        for (int64_t r = lo; r <= hi; r += kPoolSlabRows) {
+          PoolSlab s;
+          s.row_begin = r;
+          s.nrows = static_cast<int32_t>(std::min<int64_t>(kPoolSlabRows, hi - r + 1));
+          s.chunk = static_cast<int32_t>(c - b.c0);
+          slabs.push_back(s);
+        }
+        ++c;
+      }
+      b.c1 = c;
+      b.row1 = chunk_start[c - 1] + chunk_len[c - 1];
+      b.slab1 = static_cast<int64_t>(slabs.size());
+      batches.push_back(b);
+    }
+  }
+  // chunk_slab_off is stored per batch as [c1-c0+1] entries relative to the batch's first slab
+  std::vector<int32_t> slab_off_packed;
+  std::vector<int64_t> slab_off_pos(batches.size());
+  for (size_t bi = 0; bi < batches.size(); ++bi) {
+    const Batch& b = batches[bi];
+    slab_off_pos[bi] = static_cast<int64_t>(slab_off_packed.size());
+    for (int64_t c = b.c0; c < b.c1; ++c) slab_off_packed.push_back(chunk_slab_off[c]);
+    slab_off_packed.push_back(static_cast<int32_t>(b.slab1 - b.slab0));
+  }
+
+  // ---- device scratch ----
+  int64_t max_rows = 0, max_chunks = 0, max_slabs = 0;
+  for (const Batch& b : batches) {
+    max_rows = std::max(max_rows, b.row1 - b.row0);
+    max_chunks = std::max(max_chunks, b.c1 - b.c0);
+    max_slabs = std::max(max_slabs, b.slab1 - b.slab0);
+  }
+  EnsureRows(max_rows);
+  const Buffer& pool_buf = buffers_[layer_buffer_[plan_.pool_src]];
+  const int32_t D = PL.out_dim, pooled = plan_.PooledDim();
+  Grow(&d_slabs_, &slabs_cap_, slabs.size() * sizeof(PoolSlab));
+  Grow(&d_chunk_slab_off_, &chunk_slab_off_cap_, slab_off_packed.size() * 4);
+  Grow(&d_weights_, &weights_cap_, weights.size() * 4);
+  Grow(&d_utt_off_, &utt_off_cap_, utt_off.size() * 8);
+  Grow(&d_partials_, &partials_cap_, static_cast<size_t>(max_slabs) * 2 * pool_buf.ld * 4);
+  Grow(&d_stats_, &stats_cap_, static_cast<size_t>(max_chunks) * pooled * 4);
+  int32_t max_seg = 0;
+  for (size_t i = 0; i + 1 < seg_ops_.size(); ++i) max_seg = std::max(max_seg, seg_ops_[i].out_dim);
+  for (int i = 0; i < 2; ++i) Grow(&d_seg_[i], &seg_cap_[i], static_cast<size_t>(max_chunks) * std::max(max_seg, 1) * 4);
+  Grow(&d_chunk_emb_, &chunk_emb_cap_, static_cast<size_t>(num_chunks) * E * 4);
+  Grow(&d_out_, &out_cap_, static_cast<size_t>(num_utts) * E * 4);
+  if (!dev_in)
+    for (int i = 0; i < 2; ++i)
+      for (int32_t s = 0; s < num_streams; ++s)
+        Grow(&d_feat_[i][s], &d_feat_cap_[i][s], static_cast<size_t>(max_rows) * plan_.input_dims[s] * 4);
+
+  CVX_CUDA_CHECK(cudaMemcpyAsync(d_slabs_, slabs.data(), slabs.size() * sizeof(PoolSlab), cudaMemcpyHostToDevice, compute_));
+  CVX_CUDA_CHECK(cudaMemcpyAsync(d_chunk_slab_off_, slab_off_packed.data(), slab_off_packed.size() * 4,
+                                 cudaMemcpyHostToDevice, compute_));
+  CVX_CUDA_CHECK(cudaMemcpyAsync(d_weights_, weights.data(), weights.size() * 4, cudaMemcpyHostToDevice, compute_));
+  CVX_CUDA_CHECK(cudaMemcpyAsync(d_utt_off_, utt_off.data(), utt_off.size() * 8, cudaMemcpyHostToDevice, compute_));
+  // the pageable host vectors above must stay alive until these copies ran
+  CVX_CUDA_CHECK(cudaStreamSynchronize(compute_));
+
+  // ---- batches ----
+  for (size_t bi = 0; bi < batches.size(); ++bi) {
+    const Batch& b = batches[bi];
+    const int64_t rows = b.row1 - b.row0;
+    const int fb = static_cast<int>(bi & 1);
+    const float* dev[kMaxASources] = {};
+    int64_t src_min, src_max;
+    if (dev_in) {
+      for (int32_t s = 0; s < num_streams; ++s) dev[s] = feats[s] + b.row0 * plan_.input_dims[s];
+      src_min = -b.row0;
+      src_max = total_rows - b.row0;
+    } else {
+      // H2D of this batch on the copy stream, overlapping the previous batch's compute
+      if (bi >= 2) CVX_CUDA_CHECK(cudaStreamWaitEvent(copy_, feat_free_[fb], 0));
+      for (int32_t s = 0; s < num_streams; ++s) {
+        CVX_CUDA_CHECK(cudaMemcpyAsync(d_feat_[fb][s], feats[s] + b.row0 * plan_.input_dims[s],
+                                       static_cast<size_t>(rows) * plan_.input_dims[s] * 4, cudaMemcpyHostToDevice, copy_));
+        dev[s] = static_cast<const float*>(d_feat_[fb][s]);
+      }
+      CVX_CUDA_CHECK(cudaEventRecord(feat_ready_[fb], copy_));
+      CVX_CUDA_CHECK(cudaStreamWaitEvent(compute_, feat_ready_[fb], 0));
+      src_min = 0;
+      src_max = rows;
+    }
+    RunFrames(dev, rows, src_min, src_max);
+    if (!dev_in) CVX_CUDA_CHECK(cudaEventRecord(feat_free_[fb], compute_));
+
+    const int32_t nslabs = static_cast<int32_t>(b.slab1 - b.slab0);
+    const int32_t nchunks = static_cast<int32_t>(b.c1 - b.c0);
+    const PoolSlab* dsl = static_cast<const PoolSlab*>(d_slabs_) + b.slab0;
+    double pooled_rows = 0;
+    for (int64_t s = b.slab0; s < b.slab1; ++s) pooled_rows += slabs[s].nrows;
+    ProfBegin(kProfPool, 0, pooled_rows * D * ElemSize(elem_));
+    CVX_CUDA_CHECK(LaunchStatsPoolPartial(pool_buf.ptr, elem_, pool_buf.ld, dsl, nslabs,
+                                          static_cast<float*>(d_partials_), compute_));
+    ProfEnd();
+    ProfBegin(kProfPoolFin, 0, static_cast<double>(nslabs) * 2 * D * 4 + static_cast<double>(nchunks) * pooled * 4);
+    CVX_CUDA_CHECK(LaunchStatsPoolFinalize(static_cast<const float*>(d_partials_), pool_buf.ld, dsl,
+                                           static_cast<const int32_t*>(d_chunk_slab_off_) + slab_off_pos[bi], nchunks, D,
+                                           plan_.pool_output_stddevs ? 1 : 0, plan_.pool_variance_floor,
+                                           static_cast<float*>(d_stats_), pooled, compute_));
+    ProfEnd();
+
+    const float* cur = static_cast<const float*>(d_stats_);
+    int32_t cur_ld = pooled;
+    float* emb = static_cast<float*>(d_chunk_emb_) + b.c0 * E;
+    if (seg_ops_.empty()) {
+      CVX_CUDA_CHECK(cudaMemcpyAsync(emb, cur, static_cast<size_t>(nchunks) * E * 4, cudaMemcpyDeviceToDevice, compute_));
+    }
+    for (size_t si = 0; si < seg_ops_.size(); ++si) {
+      const SegOp& s = seg_ops_[si];
+      const bool last = si + 1 == seg_ops_.size();
+      float* dst = last ? emb : static_cast<float*>(d_seg_[si & 1]);
+      const int32_t dst_ld = s.out_dim;
+      ProfBegin(kProfSegment, 2.0 * nchunks * s.in_dim * s.out_dim, 0);
+      CVX_CUDA_CHECK(LaunchSegmentAffine(cur, cur_ld, nchunks, s.in_dim, s.d_w, s.d_b, s.relu ? 1 : 0, s.d_scale,
+                                         s.d_offset, s.out_dim, dst, dst_ld, compute_));
+      ProfEnd();
+      cur = dst;
+      cur_ld = dst_ld;
+    }
+  }
+  ProfBegin(kProfAverage, 0, static_cast<double>(num_chunks + num_utts) * E * 4);
+  CVX_CUDA_CHECK(LaunchUttAverage(static_cast<const float*>(d_chunk_emb_), E, static_cast<const int64_t*>(d_utt_off_),
+                                  static_cast<const float*>(d_weights_), num_utts,
+                                  dev_out ? out : static_cast<float*>(d_out_), compute_));
+  ProfEnd();
+  if (!dev_out)
+    CVX_CUDA_CHECK(cudaMemcpyAsync(out, d_out_, static_cast<size_t>(num_utts) * E * 4, cudaMemcpyDeviceToHost, compute_));
+  CVX_CUDA_CHECK(cudaStreamSynchronize(compute_));
+  ProfResolve();
+  last_num_chunks_ = num_chunks;
+}
+
+void Engine::LastChunkEmbeddings(float* out, int64_t num_chunks) {
+  CVX_CUDA_CHECK(cudaSetDevice(opts_.device));
+  if (num_chunks != last_num_chunks_) throw InvalidArgument("num_chunks does not match the last cvx_extract call");
+  CVX_CUDA_CHECK(cudaMemcpy(out, d_chunk_emb_, static_cast<size_t>(num_chunks) * plan_.EmbeddingDim() * 4,
+                            cudaMemcpyDeviceToHost));
+}
+
+// ------------------------------------------------------------ test hook ----
+void TestStatsPool(int32_t device, int32_t precision, const float* in, int64_t rows, int32_t dim, const int64_t* begin,
+                   const int64_t* end, int64_t num_chunks, float variance_floor, float* out) {
+  CVX_CUDA_CHECK(cudaSetDevice(device));
+  const int32_t elem = precision == CVX_PRECISION_FP16 ? kF16 : precision == CVX_PRECISION_BF16 ? kBF16 : kF32;
+  const int32_t ld = RoundUp(dim, 64);
+  std::vector<float> padded(static_cast<size_t>(rows) * ld, 0.f);
+  for (int64_t r = 0; r < rows; ++r) std::memcpy(&padded[r * ld], in + r * dim, static_cast<size_t>(dim) * 4);
+  std::vector<uint8_t> conv(padded.size() * ElemSize(elem));
+  ConvertToElem(padded.data(), padded.size(), elem, conv.data());
+  std::vector<PoolSlab> slabs;
+  std::vector<int32_t> off(num_chunks + 1, 0);
+  for (int64_t c = 0; c < num_chunks; ++c) {
+    if (begin[c] < 0 || end[c] > rows || end[c] <= begin[c]) throw InvalidArgument("bad pooling range");
+    off[c] = static_cast<int32_t>(slabs.size());
+    for (int64_t r = begin[c]; r < end[c]; r += kPoolSlabRows)
+      slabs.push_back({r, static_cast<int32_t>(std::min<int64_t>(kPoolSlabRows, end[c] - r)), static_cast<int32_t>(c)});
+  }
+  off[num_chunks] = static_cast<int32_t>(slabs.size());
+  void *d_act = nullptr, *d_slabs = nullptr, *d_off = nullptr, *d_part = nullptr, *d_stats = nullptr;
+  CVX_CUDA_CHECK(cudaMalloc(&d_act, std::max<size_t>(conv.size(), 16)));
+  CVX_CUDA_CHECK(cudaMalloc(&d_slabs, std::max<size_t>(slabs.size(), 1) * sizeof(PoolSlab)));
+  CVX_CUDA_CHECK(cudaMalloc(&d_off, off.size() * 4));
+  CVX_CUDA_CHECK(cudaMalloc(&d_part, std::max<size_t>(slabs.size(), 1) * 2 * ld * 4));
+  CVX_CUDA_CHECK(cudaMalloc(&d_stats, std::max<size_t>(num_chunks, 1) * 2 * dim * 4));
+  CVX_CUDA_CHECK(cudaMemcpy(d_act, conv.data(), conv.size(), cudaMemcpyHostToDevice));
+  CVX_CUDA_CHECK(cudaMemcpy(d_slabs, slabs.data(), slabs.size() * sizeof(PoolSlab), cudaMemcpyHostToDevice));
+  CVX_CUDA_CHECK(cudaMemcpy(d_off, off.data(), off.size() * 4, cudaMemcpyHostToDevice));
+  CVX_CUDA_CHECK(LaunchStatsPoolPartial(d_act, elem, ld, static_cast<PoolSlab*>(d_slabs), static_cast<int32_t>(slabs.size()),
+                                        static_cast<float*>(d_part), nullptr));
+  CVX_CUDA_CHECK(LaunchStatsPoolFinalize(static_cast<float*>(d_part), ld, static_cast<PoolSlab*>(d_slabs),
+                                         static_cast<int32_t*>(d_off), static_cast<int32_t>(num_chunks), dim, 1,
+                                         variance_floor, static_cast<float*>(d_stats), 2 * dim, nullptr));
+  CVX_CUDA_CHECK(cudaMemcpy(out, d_stats, static_cast<size_t>(num_chunks) * 2 * dim * 4, cudaMemcpyDeviceToHost));
+  cudaFree(d_act);
+  cudaFree(d_slabs);
+  cudaFree(d_off);
+  cudaFree(d_part);
+  cudaFree(d_stats);
+}
+
+}  // namespace cvx

@@ -1,0 +1,140 @@
+// Device-side executor of a Plan: owns weights, activation buffers, TMA
+// descriptors, streams; runs packed ragged batches of chunks.
+#ifndef CVX_ENGINE_H_
+#define CVX_ENGINE_H_
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/cvx.h"
+#include "kernels/kernels.h"
+#include "plan.h"
+
+namespace cvx {
+
+struct CudaError : public std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+struct InvalidArgument : public std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+#define CVX_CUDA_CHECK(expr)                                                                         \
+  do {                                                                                               \
+    cudaError_t cvx_e__ = (expr);                                                                    \
+    if (cvx_e__ != cudaSuccess)                                                                      \
+      throw ::cvx::CudaError(std::string(#expr) + " failed: " + cudaGetErrorString(cvx_e__) + " (" + \
+                             __FILE__ + ":" + std::to_string(__LINE__) + ")");                       \
+  } while (0)
+
+constexpr uint32_t kDebugForceTapPath = 1u;  // cvx_engine_options.reserved[0]
+
+class Engine {
+ public:
+  Engine(const Plan& plan, const cvx_engine_options& opts);
+  ~Engine();
+  Engine(const Engine&) = delete;
+  Engine& operator=(const Engine&) = delete;
+
+  void Extract(const float* const* feats, int32_t num_streams, int64_t total_rows, const int64_t* chunk_start,
+               const int32_t* chunk_len, const int32_t* chunk_utt, const float* chunk_weight, int64_t num_chunks,
+               int32_t num_utts, float* out, uint32_t flags);
+  void LastChunkEmbeddings(float* out, int64_t num_chunks);
+  // Test hook: run only the frame layers on `rows` packed rows and return the last
+  // frame layer's activations as fp32 [rows, out_dim].
+  void DebugForwardFrames(const float* const* feats, int64_t rows, float* out);
+
+  int GetProfile(cvx_kernel_profile* recs, int32_t max_recs);
+  void ResetProfile();
+  int64_t launch_count() const { return launches_; }
+  const Plan& plan() const { return plan_; }
+
+ private:
+  struct Buffer {
+    void* ptr = nullptr;
+    int32_t ld = 0;   // elements per row, multiple of 64
+    int32_t dim = 0;  // logical columns
+  };
+  struct Staging {
+    std::vector<StageTap> taps;
+    int32_t buffer = -1;
+  };
+  struct FrameOp {
+    int32_t layer = 0;
+    int32_t out_buffer = -1;
+    std::vector<int32_t> srcs;  // buffer ids
+    std::vector<KBlockDesc> kb;
+    int32_t n_pad = 0, k_pad = 0;
+    void* d_w = nullptr;        // [n_pad, k_pad] of elem
+    float2* d_post = nullptr;   // [n_pad]
+    TdnnGemmArgs targs;
+  };
+  struct SegOp {
+    int32_t in_dim = 0, out_dim = 0;
+    float *d_w = nullptr, *d_b = nullptr, *d_scale = nullptr, *d_offset = nullptr;
+    bool relu = false;
+  };
+  enum ProfClass { kProfStage = 0, kProfGemm, kProfPool, kProfPoolFin, kProfSegment, kProfAverage, kNumProf };
+  struct PendingEvent {
+    int cls;
+    cudaEvent_t a, b;
+    double flops, bytes;
+  };
+
+  int32_t StagingFor(const std::vector<Tap>& taps);
+  void EnsureRows(int64_t rows);
+  void EncodeMaps();
+  void RunFrames(const float* const* dev_feats, int64_t rows, int64_t src_row_min, int64_t src_row_max);
+  void ProfBegin(int cls, double flops, double bytes);
+  void ProfEnd();
+  void ProfResolve();
+  template <typename T>
+  T* DevAlloc(size_t n);
+  void Grow(void** p, size_t* cap, size_t bytes);
+
+  Plan plan_;
+  cvx_engine_options opts_;
+  int32_t elem_ = kF16;
+  int num_sms_ = 148;
+  uint32_t debug_ = 0;
+  cudaStream_t compute_ = nullptr, copy_ = nullptr;
+  cudaEvent_t feat_ready_[2] = {nullptr, nullptr}, feat_free_[2] = {nullptr, nullptr};
+
+  std::vector<Buffer> buffers_;
+  std::vector<Staging> stagings_;
+  std::vector<FrameOp> frame_ops_;
+  std::vector<SegOp> seg_ops_;
+  std::vector<int32_t> layer_buffer_;
+  int64_t rows_cap_ = 0;
+  int64_t max_batch_rows_ = 0;
+
+  // per-call scratch (grown on demand)
+  void* d_feat_[2][kMaxASources] = {};
+  size_t d_feat_cap_[2][kMaxASources] = {};
+  void *d_slabs_ = nullptr, *d_chunk_slab_off_ = nullptr, *d_weights_ = nullptr, *d_utt_off_ = nullptr;
+  size_t slabs_cap_ = 0, chunk_slab_off_cap_ = 0, weights_cap_ = 0, utt_off_cap_ = 0;
+  void *d_partials_ = nullptr, *d_stats_ = nullptr, *d_seg_[2] = {nullptr, nullptr}, *d_chunk_emb_ = nullptr,
+       *d_out_ = nullptr;
+  size_t partials_cap_ = 0, stats_cap_ = 0, seg_cap_[2] = {0, 0}, chunk_emb_cap_ = 0, out_cap_ = 0;
+  int64_t last_num_chunks_ = 0;
+
+  bool profile_ = false;
+  std::vector<PendingEvent> pending_;
+  std::vector<cudaEvent_t> event_pool_;
+  double prof_ms_[kNumProf] = {}, prof_flops_[kNumProf] = {}, prof_bytes_[kNumProf] = {};
+  int64_t prof_launches_[kNumProf] = {};
+  int64_t launches_ = 0;
+};
+
+// Stand-alone pooling run for tests (cvx_test_stats_pool).
+void TestStatsPool(int32_t device, int32_t precision, const float* in, int64_t rows, int32_t dim, const int64_t* begin,
+                   const int64_t* end, int64_t num_chunks, float variance_floor, float* out);
+
+}  // namespace cvx
+#endif  // CVX_ENGINE_H_

@@ -1,0 +1,110 @@
+// Host-callable launchers of the CUDA kernels (one .cu per kernel family).
+#ifndef CVX_KERNELS_KERNELS_H_
+#define CVX_KERNELS_KERNELS_H_
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cvx {
+
+enum ElemType : int32_t { kF16 = 0, kBF16 = 1, kF32 = 2 };
+inline size_t ElemSize(int32_t e) { return e == kF32 ? 4 : 2; }
+
+// ---- K1: TDNN layer as implicit GEMM -------------------------------------
+// out[r, n] = post( sum_kb A_kb[r + rowoff_kb, col_kb : col_kb+64] . Wp[n, 64*kb : 64*kb+64] )
+// post(v)  = (relu ? max(v + b'[n], 0) : v + b'[n]) + o[n]
+// (test-mode BatchNorm scale is folded into Wp/b' at load; o is its offset.)
+constexpr int kGemmBlockM = 128;
+constexpr int kGemmBlockN = 256;
+constexpr int kGemmBlockK = 64;
+constexpr int kMaxKBlocks = 64;
+constexpr int kMaxASources = 4;
+
+struct KBlockDesc {
+  int32_t src;     // index into the layer's A sources
+  int32_t col;     // first column in that source buffer (multiple of 64)
+  int32_t rowoff;  // time offset of the tap
+};
+
+struct TdnnGemmArgs {
+  CUtensorMap a_maps[kMaxASources];  // [rows_cap, ld] activations, box 64 x 128, SWIZZLE_128B
+  CUtensorMap b_map;                 // Wp [n_pad, k_pad], box 64 x 256, SWIZZLE_128B
+  CUtensorMap c_map;                 // out [rows_cap, ld_out], box 64 x 32, SWIZZLE_128B
+  KBlockDesc kb[kMaxKBlocks];
+  int32_t num_kb;
+  int32_t n_pad;          // multiple of 64
+  int32_t num_m_tiles;    // ceil(rows / 128)
+  int32_t num_n_tiles;    // ceil(n_pad / 256)
+  const float2* post;     // [n_pad] {b', o}
+  int32_t relu;
+  int32_t ab_format;      // 0 = fp16, 1 = bf16 (UMMA F16F32Format)
+};
+
+size_t TdnnGemmSmemBytes();
+cudaError_t LaunchTdnnGemm(const TdnnGemmArgs& args, int num_sms, cudaStream_t stream);
+
+// fp32 CUDA-core version of the same contraction (CVX_PRECISION_FP32; validation aid).
+struct TdnnGemmSimtArgs {
+  const float* a_src[kMaxASources];
+  int32_t a_ld[kMaxASources];
+  KBlockDesc kb[kMaxKBlocks];
+  int32_t num_kb;
+  const float* w;   // Wp [n_pad, k_pad] fp32
+  int32_t k_pad;
+  int32_t n_pad;
+  const float2* post;
+  int32_t relu;
+  float* out;
+  int32_t ld_out;
+  int64_t rows;      // rows to compute
+  int64_t rows_cap;  // rows that exist in the source buffers
+};
+cudaError_t LaunchTdnnGemmSimt(const TdnnGemmSimtArgs& args, cudaStream_t stream);
+
+// ---- input staging: fp32 features -> spliced operand rows ----------------
+constexpr int kMaxStageTaps = 16;
+struct StageTap {
+  int32_t stream;
+  int32_t offset;
+  int32_t dim;
+  int32_t col0;  // first output column of this tap
+};
+struct StageArgs {
+  const float* feats[kMaxASources];  // per stream, row 0 = first row of the batch
+  int32_t feat_dim[kMaxASources];
+  StageTap taps[kMaxStageTaps];
+  int32_t num_taps;
+  void* out;        // [rows, ld_out] of `elem`
+  int32_t ld_out;   // multiple of 64; columns beyond the taps are zero-filled
+  int32_t elem;
+  int64_t rows;
+  int64_t src_row_min, src_row_max;  // source rows that exist, relative to feats[] row 0
+};
+cudaError_t LaunchStageInput(const StageArgs& args, cudaStream_t stream);
+
+// ---- K2: ragged mean + stddev pooling -------------------------------------
+struct PoolSlab {
+  int64_t row_begin;  // first row (in the activation buffer) of this slab
+  int32_t nrows;
+  int32_t chunk;
+};
+constexpr int kPoolSlabRows = 256;
+// partials: [num_slabs][2][ld] fp32 = per-column (mean, M2) of each slab
+cudaError_t LaunchStatsPoolPartial(const void* act, int32_t elem, int32_t ld, const PoolSlab* slabs,
+                                   int32_t num_slabs, float* partials, cudaStream_t stream);
+// stats[c] = [mean(dim) | sqrt(max(var, floor))(dim)] (or just mean), merging the chunk's slabs
+cudaError_t LaunchStatsPoolFinalize(const float* partials, int32_t ld, const PoolSlab* slabs,
+                                    const int32_t* chunk_slab_off, int32_t num_chunks, int32_t dim,
+                                    int32_t output_stddevs, float variance_floor, float* stats,
+                                    int32_t ld_stats, cudaStream_t stream);
+
+// ---- K3: segment-level affine and per-utterance weighted average ----------
+cudaError_t LaunchSegmentAffine(const float* in, int32_t ld_in, int64_t m, int32_t k, const float* w,
+                                const float* bias, int32_t relu, const float* scale, const float* offset,
+                                int32_t n, float* out, int32_t ld_out, cudaStream_t stream);
+cudaError_t LaunchUttAverage(const float* chunk_emb, int32_t dim, const int64_t* utt_chunk_off,
+                             const float* chunk_weight, int32_t num_utts, float* out, cudaStream_t stream);
+
+}  // namespace cvx
+#endif  // CVX_KERNELS_KERNELS_H_

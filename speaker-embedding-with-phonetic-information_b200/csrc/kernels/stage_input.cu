@@ -1,0 +1,71 @@
+// Input staging: fp32 feature rows -> operand rows of the first TDNN layer(s).
+//
+// The first layer's splice (e.g. Append(input@-2..input@2), 5 x 23 = 115 columns,
+// egs/sre/v2/local/nnet3/xvector/run_xvector_new.sh:96) is too narrow for 64-column
+// K blocks per tap, so it is gathered once into a compact [rows, 128] operand
+// (fp32 -> fp16/bf16 conversion fused); pad columns are written as zeros.
+// One thread per (row, 8-column group); 16-byte stores, coalesced along the row.
+#include "kernels.h"
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+namespace cvx {
+namespace {
+
+template <typename T>
+__device__ __forceinline__ T to_elem(float v);
+template <>
+__device__ __forceinline__ __half to_elem<__half>(float v) {
+  return __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+}
+template <>
+__device__ __forceinline__ __nv_bfloat16 to_elem<__nv_bfloat16>(float v) {
+  return __float2bfloat16_rn(v);
+}
+template <>
+__device__ __forceinline__ float to_elem<float>(float v) {
+  return v;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) stage_input_kernel(const __grid_constant__ StageArgs args) {
+  constexpr int kVec = 16 / sizeof(T);
+  const int groups = args.ld_out / kVec;
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t row = idx / groups;
+  if (row >= args.rows) return;
+  const int c0 = static_cast<int>(idx % groups) * kVec;
+  alignas(16) T vals[kVec];
+#pragma unroll
+  for (int e = 0; e < kVec; ++e) {
+    const int c = c0 + e;
+    float v = 0.f;
+    for (int t = 0; t < args.num_taps; ++t) {
+      const StageTap tp = args.taps[t];
+      if (c >= tp.col0 && c < tp.col0 + tp.dim) {
+        const int64_t sr = row + tp.offset;
+        if (sr >= args.src_row_min && sr < args.src_row_max)
+          v = __ldg(args.feats[tp.stream] + sr * args.feat_dim[tp.stream] + (c - tp.col0));
+        break;
+      }
+    }
+    vals[e] = to_elem<T>(v);
+  }
+  *reinterpret_cast<uint4*>(static_cast<T*>(args.out) + row * args.ld_out + c0) = *reinterpret_cast<uint4*>(vals);
+}
+
+}  // namespace
+
+cudaError_t LaunchStageInput(const StageArgs& args, cudaStream_t stream) {
+  if (args.rows <= 0) return cudaSuccess;
+  const int vec = 16 / static_cast<int>(ElemSize(args.elem));
+  const int64_t total = args.rows * (args.ld_out / vec);
+  const unsigned grid = static_cast<unsigned>((total + 255) / 256);
+  if (args.elem == kF16) stage_input_kernel<__half><<<grid, 256, 0, stream>>>(args);
+  else if (args.elem == kBF16) stage_input_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(args);
+  else stage_input_kernel<float><<<grid, 256, 0, stream>>>(args);
+  return cudaGetLastError();
+}
+
+}  // namespace cvx

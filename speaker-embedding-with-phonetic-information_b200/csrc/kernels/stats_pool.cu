@@ -1,0 +1,198 @@
+// K2 -- ragged mean + stddev statistics pooling (HBM-bound streaming reduction).
+//
+// Replaces upstream Kaldi's StatisticsExtractionComponent (materialises
+// [N, 1+2D] = count, x, x^2) + StatisticsPoolingComponent (AddRowRanges,
+// DivRowsVec, AddMatMatElements, ApplyFloor(1e-10), ApplyPow(0.5)), configured by
+// `stats-layer ... config=mean+stddev(0:1:1:10000)`
+// (egs/sre/v2/local/nnet3/xvector/run_xvector_new.sh:106).
+//
+// Each chunk's valid rows [begin, end) are cut into slabs of <= 256 rows; one CTA
+// reduces (slab, 32 x 16-byte column group): every activation is read exactly once
+// with 128-bit loads, a warp reads 512 contiguous bytes of a row, the 8 warps of
+// the CTA take interleaved rows.  Per column the CTA forms shifted sums
+// S1 = sum(x - c), S2 = sum((x - c)^2) (c = the slab's first row) and emits the
+// slab's (mean, M2); a second tiny kernel merges a chunk's slabs with the
+// Chan/Welford pairwise update and writes [mean | sqrt(max(M2/n, floor))].
+// No tensor cores: there is no contraction here.
+#include "kernels.h"
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include <type_traits>
+
+namespace cvx {
+namespace {
+
+constexpr int kPoolWarps = 8;
+constexpr int kPoolUnroll = 4;
+
+template <typename T>
+struct Vec16;
+template <>
+struct Vec16<__half> {
+  static constexpr int kN = 8;
+  __device__ static void unpack(const uint4& u, float (&f)[8]) {
+    const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float2 v = __half22float2(h[i]);
+      f[2 * i] = v.x;
+      f[2 * i + 1] = v.y;
+    }
+  }
+};
+template <>
+struct Vec16<__nv_bfloat16> {
+  static constexpr int kN = 8;
+  __device__ static void unpack(const uint4& u, float (&f)[8]) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float2 v = __bfloat1622float2(h[i]);
+      f[2 * i] = v.x;
+      f[2 * i + 1] = v.y;
+    }
+  }
+};
+template <>
+struct Vec16<float> {
+  static constexpr int kN = 4;
+  __device__ static void unpack(const uint4& u, float (&f)[4]) {
+    f[0] = __uint_as_float(u.x);
+    f[1] = __uint_as_float(u.y);
+    f[2] = __uint_as_float(u.z);
+    f[3] = __uint_as_float(u.w);
+  }
+};
+
+__device__ __forceinline__ uint4 ld_stream(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kPoolWarps * 32) stats_pool_partial_kernel(const T* __restrict__ act, int ld,
+                                                                              const PoolSlab* __restrict__ slabs,
+                                                                              float* __restrict__ partials) {
+  constexpr int kN = Vec16<T>::kN;
+  constexpr int kCols = 32 * kN;  // columns per CTA
+  __shared__ float red[kPoolWarps][2][kCols];
+
+  const PoolSlab slab = slabs[blockIdx.x];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int col0 = blockIdx.y * kCols;
+  const int col = col0 + lane * kN;
+  const bool active = col < ld;
+  const T* base = act + slab.row_begin * ld + (active ? col : 0);
+
+  float c[kN], s1[kN], s2[kN];
+#pragma unroll
+  for (int i = 0; i < kN; ++i) s1[i] = s2[i] = 0.f;
+  if (active) {
+    Vec16<T>::unpack(ld_stream(base), c);  // shift = first row of the slab
+    for (int r = warp; r < slab.nrows; r += kPoolWarps * kPoolUnroll) {
+      uint4 v[kPoolUnroll];
+#pragma unroll
+      for (int u = 0; u < kPoolUnroll; ++u) {
+        const int rr = r + u * kPoolWarps;
+        if (rr < slab.nrows) v[u] = ld_stream(base + static_cast<int64_t>(rr) * ld);
+      }
+#pragma unroll
+      for (int u = 0; u < kPoolUnroll; ++u) {
+        const int rr = r + u * kPoolWarps;
+        if (rr < slab.nrows) {
+          float x[kN];
+          Vec16<T>::unpack(v[u], x);
+#pragma unroll
+          for (int i = 0; i < kN; ++i) {
+            const float d = x[i] - c[i];
+            s1[i] += d;
+            s2[i] = fmaf(d, d, s2[i]);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kN; ++i) {
+    red[warp][0][lane * kN + i] = s1[i];
+    red[warp][1][lane * kN + i] = s2[i];
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < kCols; j += kPoolWarps * 32) {
+    if (col0 + j >= ld) break;
+    float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+    for (int w = 0; w < kPoolWarps; ++w) {
+      t1 += red[w][0][j];
+      t2 += red[w][1][j];
+    }
+    const float n = static_cast<float>(slab.nrows);
+    float cj;
+    if constexpr (sizeof(T) == 4) cj = reinterpret_cast<const float*>(act)[slab.row_begin * ld + col0 + j];
+    else if constexpr (std::is_same<T, __half>::value) cj = __half2float(act[slab.row_begin * ld + col0 + j]);
+    else cj = __bfloat162float(act[slab.row_begin * ld + col0 + j]);
+    const float mean_shift = t1 / n;
+    float* out = partials + static_cast<int64_t>(blockIdx.x) * 2 * ld + col0 + j;
+    out[0] = cj + mean_shift;
+    out[ld] = fmaxf(t2 - t1 * mean_shift, 0.f);  // M2 = sum (x - mean)^2
+  }
+}
+
+__global__ void __launch_bounds__(256) stats_pool_finalize_kernel(const float* __restrict__ partials, int ld,
+                                                                   const PoolSlab* __restrict__ slabs,
+                                                                   const int32_t* __restrict__ chunk_slab_off,
+                                                                   int dim, int output_stddevs, float floor_,
+                                                                   float* __restrict__ stats, int ld_stats) {
+  const int chunk = blockIdx.x;
+  const int j = blockIdx.y * blockDim.x + threadIdx.x;
+  if (j >= dim) return;
+  const int s0 = chunk_slab_off[chunk], s1 = chunk_slab_off[chunk + 1];
+  float n = 0.f, mean = 0.f, m2 = 0.f;
+  for (int s = s0; s < s1; ++s) {
+    const float nb = static_cast<float>(slabs[s].nrows);
+    const float mb = partials[static_cast<int64_t>(s) * 2 * ld + j];
+    const float m2b = partials[static_cast<int64_t>(s) * 2 * ld + ld + j];
+    const float tot = n + nb;
+    const float delta = mb - mean;
+    mean += delta * (nb / tot);
+    m2 += m2b + delta * delta * (n * nb / tot);
+    n = tot;
+  }
+  float* out = stats + static_cast<int64_t>(chunk) * ld_stats;
+  out[j] = mean;
+  if (output_stddevs) out[dim + j] = sqrtf(fmaxf(m2 / n, floor_));
+}
+
+}  // namespace
+
+cudaError_t LaunchStatsPoolPartial(const void* act, int32_t elem, int32_t ld, const PoolSlab* slabs,
+                                   int32_t num_slabs, float* partials, cudaStream_t stream) {
+  if (num_slabs <= 0) return cudaSuccess;
+  const int cols = 32 * (16 / static_cast<int>(ElemSize(elem)));
+  dim3 grid(num_slabs, (ld + cols - 1) / cols);
+  if (elem == kF16)
+    stats_pool_partial_kernel<__half><<<grid, kPoolWarps * 32, 0, stream>>>(static_cast<const __half*>(act), ld, slabs, partials);
+  else if (elem == kBF16)
+    stats_pool_partial_kernel<__nv_bfloat16><<<grid, kPoolWarps * 32, 0, stream>>>(static_cast<const __nv_bfloat16*>(act), ld, slabs, partials);
+  else
+    stats_pool_partial_kernel<float><<<grid, kPoolWarps * 32, 0, stream>>>(static_cast<const float*>(act), ld, slabs, partials);
+  return cudaGetLastError();
+}
+
+cudaError_t LaunchStatsPoolFinalize(const float* partials, int32_t ld, const PoolSlab* slabs,
+                                    const int32_t* chunk_slab_off, int32_t num_chunks, int32_t dim,
+                                    int32_t output_stddevs, float variance_floor, float* stats,
+                                    int32_t ld_stats, cudaStream_t stream) {
+  if (num_chunks <= 0) return cudaSuccess;
+  dim3 grid(num_chunks, (dim + 255) / 256);
+  stats_pool_finalize_kernel<<<grid, 256, 0, stream>>>(partials, ld, slabs, chunk_slab_off, dim, output_stddevs,
+                                                       variance_floor, stats, ld_stats);
+  return cudaGetLastError();
+}
+
+}  // namespace cvx

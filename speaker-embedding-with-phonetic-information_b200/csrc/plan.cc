@@ -1,0 +1,86 @@
+#include "plan.h"
+
+#include <algorithm>
+#include <sstream>
+#include <stdexcept>
+
+namespace cvx {
+
+int64_t Plan::MacPerFrame() const {
+  int64_t m = 0;
+  for (const Layer& l : frame) m += static_cast<int64_t>(l.in_dim) * l.out_dim;
+  return m;
+}
+
+int64_t Plan::MacPerChunk() const {
+  int64_t m = 0;
+  for (const Layer& l : segment) m += static_cast<int64_t>(l.in_dim) * l.out_dim;
+  return m;
+}
+
+void Plan::Finalize() {
+  auto fail = [](const std::string& m) { throw std::runtime_error("invalid plan: " + m); };
+  if (input_dims.empty() || input_dims.size() != input_names.size()) fail("no inputs");
+  for (int32_t d : input_dims)
+    if (d <= 0) fail("input dim <= 0");
+  if (frame.empty()) fail("no frame layers");
+  const int32_t n_in = static_cast<int32_t>(input_dims.size());
+  for (size_t i = 0; i < frame.size(); ++i) {
+    Layer& l = frame[i];
+    if (l.taps.empty()) fail("frame layer " + l.name + " has no taps");
+    int32_t k = 0, left = 0, right = 0;
+    for (const Tap& t : l.taps) {
+      if (t.src >= static_cast<int32_t>(i) || t.src < -n_in) fail("frame layer " + l.name + ": bad tap source");
+      k += SrcDim(t.src);
+      int32_t sl = t.src >= 0 ? frame[t.src].left : 0, sr = t.src >= 0 ? frame[t.src].right : 0;
+      // output t needs the source at t+offset: sl <= t+offset <= T-1-sr
+      left = std::max(left, sl - t.offset);
+      right = std::max(right, sr + t.offset);
+    }
+    // rows exist only for 0 <= t < T, so contexts never go negative
+    l.left = std::max(left, 0);
+    l.right = std::max(right, 0);
+    if (k != l.in_dim) fail("frame layer " + l.name + ": taps give dim " + std::to_string(k) + ", in_dim " + std::to_string(l.in_dim));
+    if (l.out_dim <= 0) fail("frame layer " + l.name + ": out_dim <= 0");
+    if (l.weight.size() != static_cast<size_t>(l.in_dim) * l.out_dim) fail("frame layer " + l.name + ": weight size");
+    if (!l.bias.empty() && static_cast<int32_t>(l.bias.size()) != l.out_dim) fail("frame layer " + l.name + ": bias size");
+    if (l.scale.size() != l.offset.size() || (!l.scale.empty() && static_cast<int32_t>(l.scale.size()) != l.out_dim))
+      fail("frame layer " + l.name + ": scale/offset size");
+  }
+  if (pool_src < 0 || pool_src >= static_cast<int32_t>(frame.size())) fail("pool_src out of range");
+  if (pool_left_context < 0 || pool_right_context < 0) fail("negative pooling context");
+  int32_t d = PooledDim();
+  for (Layer& l : segment) {
+    if (l.in_dim != d) fail("segment layer " + l.name + ": in_dim " + std::to_string(l.in_dim) + " != " + std::to_string(d));
+    if (l.weight.size() != static_cast<size_t>(l.in_dim) * l.out_dim) fail("segment layer " + l.name + ": weight size");
+    if (!l.bias.empty() && static_cast<int32_t>(l.bias.size()) != l.out_dim) fail("segment layer " + l.name + ": bias size");
+    if (l.scale.size() != l.offset.size() || (!l.scale.empty() && static_cast<int32_t>(l.scale.size()) != l.out_dim))
+      fail("segment layer " + l.name + ": scale/offset size");
+    d = l.out_dim;
+  }
+
+  std::ostringstream os;
+  for (size_t i = 0; i < input_dims.size(); ++i)
+    os << "input[" << i << "] " << input_names[i] << " dim=" << input_dims[i] << "\n";
+  for (size_t i = 0; i < frame.size(); ++i) {
+    const Layer& l = frame[i];
+    os << "frame[" << i << "] " << l.name << " " << l.in_dim << "->" << l.out_dim << " taps={";
+    for (size_t t = 0; t < l.taps.size(); ++t) {
+      if (t) os << ",";
+      if (l.taps[t].src >= 0) os << "L" << l.taps[t].src;
+      else os << "in" << (-1 - l.taps[t].src);
+      os << "@" << l.taps[t].offset;
+    }
+    os << "}" << (l.relu ? " relu" : "") << (l.scale.empty() ? "" : " bn") << " ctx=" << l.left << "/" << l.right << "\n";
+  }
+  os << "pool src=L" << pool_src << " window=[-" << pool_left_context << ",+" << pool_right_context << "] "
+     << (pool_output_stddevs ? "mean+stddev" : "mean") << " floor=" << pool_variance_floor << "\n";
+  for (size_t i = 0; i < segment.size(); ++i) {
+    const Layer& l = segment[i];
+    os << "segment[" << i << "] " << l.name << " " << l.in_dim << "->" << l.out_dim << (l.relu ? " relu" : "")
+       << (l.scale.empty() ? "" : " bn") << "\n";
+  }
+  description = os.str();
+}
+
+}  // namespace cvx

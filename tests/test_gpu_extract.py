@@ -1,0 +1,180 @@
+"""End-to-end parity of the CUDA path (through the C ABI) against the oracle."""
+import numpy as np
+import pytest
+
+from conftest import embedding_node
+
+pytestmark = pytest.mark.gpu
+
+# north-star tolerance (BASELINE.json): max|a-b|/max|b| <= 1e-3 and cosine >= 0.9999
+TOL_REL, TOL_COS = 1e-3, 0.9999
+
+
+def _oracle(model, node, dtype=np.float64):
+    from oracle.nnet3_oracle import Oracle
+    return Oracle(model, node, dtype)
+
+
+def _inputs(synth, mod, lengths, seed):
+    return {n: synth.make_features(lengths, d, seed + i) for i, (n, d) in enumerate(zip(mod.input_names, mod.input_dims))}
+
+
+@pytest.mark.parametrize("precision,rel,cos", [("fp32", 2e-5, 0.999999), ("fp16", TOL_REL, TOL_COS)])
+@pytest.mark.parametrize("topology", ["tiny", "tiny2", "v2_xvector", "v3_multitask", "v4_cvector", "v4_two_input",
+                                      "v4_pa_wo_pretrain", "v5_cvector"])
+def test_extract_matches_oracle(cvx, synth, model_dir, require_gpu, topology, precision, rel, cos):
+    from oracle.nnet3_oracle import extract_all, parity_metrics
+    path, model = model_dir(topology)
+    node = embedding_node(synth, topology)
+    mod = cvx.Model(path, node)
+    lengths = [25, 300, 57, 1234, 100, 31, 640]
+    feats = _inputs(synth, mod, lengths, 11)
+    ex = cvx.Extractor(mod, precision=precision)
+    got, ok = ex.extract(feats, lengths, chunk_size=500, min_chunk_size=25)
+    ref, ok_ref = extract_all(_oracle(model, node), feats, lengths, chunk_size=500, min_chunk_size=25)
+    assert ok.tolist() == ok_ref.tolist()
+    r, c = parity_metrics(got[ok], ref[ok])
+    assert r <= rel and c >= cos, f"{topology}/{precision}: rel {r} cos {c}"
+
+
+def test_chunking_semantics(cvx, synth, model_dir, require_gpu):
+    """short tails skipped (old Kaldi) vs padded (new Kaldi), too-short utterances fail,
+    chunk-size -1, chunk boundaries exactly at multiples."""
+    from oracle.nnet3_oracle import extract_all, parity_metrics
+    path, model = model_dir("v2_xvector")
+    mod = cvx.Model(path, "tdnn6.affine")
+    ex = cvx.Extractor(mod, precision="fp32")
+    lengths = [10, 24, 25, 200, 210, 400, 401, 0, 15]
+    feats = _inputs(synth, mod, lengths, 3)
+    for chunk, minc, pad in [(200, 25, False), (200, 25, True), (-1, 25, False), (100, 100, False), (100, 100, True)]:
+        got, ok = ex.extract(feats, lengths, chunk_size=chunk, min_chunk_size=minc, pad_input=pad)
+        ref, ok_ref = extract_all(_oracle(model, "tdnn6.affine"), feats, lengths, chunk_size=chunk,
+                                  min_chunk_size=minc, pad_input=pad)
+        assert ok.tolist() == ok_ref.tolist(), (chunk, minc, pad)
+        r, c = parity_metrics(got[ok], ref[ok])
+        assert r <= 2e-5, (chunk, minc, pad, r)
+        assert np.all(got[~ok] == 0)
+
+
+def test_ragged_batch_is_bit_identical_to_single(cvx, synth, model_dir, require_gpu):
+    """per-chunk results must not depend on what else is in the packed batch, nor on
+    how the engine cuts device batches (guards the edge handling of the packed layout)."""
+    path, model = model_dir("v5_cvector")
+    mod = cvx.Model(path, "tdnn6_xvec.affine")
+    lengths = [300, 45, 1000, 77, 512, 128]
+    feats = _inputs(synth, mod, lengths, 21)
+    big = cvx.Extractor(mod, precision="fp16")
+    small = cvx.Extractor(mod, precision="fp16", max_batch_rows=512)   # forces several device batches
+    a, _ = big.extract(feats, lengths, chunk_size=400, min_chunk_size=25)
+    b, _ = small.extract(feats, lengths, chunk_size=400, min_chunk_size=25)
+    assert np.array_equal(a, b)
+    base = 0
+    for u, T in enumerate(lengths):
+        one, _ = big.extract({k: v[base:base + T] for k, v in feats.items()}, [T], chunk_size=400, min_chunk_size=25)
+        assert np.array_equal(one[0], a[u]), u
+        base += T
+
+
+@pytest.mark.parametrize("name", ["v2_small", "v5_small"])
+@pytest.mark.parametrize("pad", [False, True])
+def test_golden_fixture(cvx, require_gpu, name, pad):
+    """committed golden vectors (tests/golden, made by tests/golden/make_golden.py)."""
+    import os
+    from oracle.nnet3_oracle import parity_metrics
+    g = os.path.join(os.path.dirname(__file__), "golden")
+    z = np.load(os.path.join(g, f"{name}.npz"))
+    mod = cvx.Model(os.path.join(g, f"{name}_final.raw"), str(z["output_node"]))
+    ex = cvx.Extractor(mod, precision="fp16")
+    got, ok = ex.extract({"input": z["feats"]}, z["lengths"].tolist(), chunk_size=int(z["chunk_size"]),
+                         min_chunk_size=int(z["min_chunk_size"]), pad_input=pad)
+    want, want_ok = (z["embeddings_pad_input"], z["ok_pad_input"]) if pad else (z["embeddings"], z["ok"])
+    assert ok.tolist() == want_ok.tolist()
+    r, c = parity_metrics(got[ok], want[ok])
+    assert r <= TOL_REL and c >= TOL_COS, (r, c)
+
+
+@pytest.mark.parametrize("name", ["v2_small", "v5_small"])
+def test_cli_drop_in(cvx, kf, require_gpu, tmp_path, name):
+    """the drop-in program with the recipe's argument shapes
+    (extract_xvectors_new.sh:84-93): model through a pipe, features through a pipe,
+    ark,scp output; embeddings match the golden vectors and the scp offsets resolve."""
+    import os
+    import subprocess
+    from oracle.nnet3_oracle import parity_metrics
+    g = os.path.join(os.path.dirname(__file__), "golden")
+    z = np.load(os.path.join(g, f"{name}.npz"))
+    exe = os.path.join(cvx.BIN_DIR, "nnet3-xvector-compute")
+    ark, scp = str(tmp_path / "xvector.1.ark"), str(tmp_path / "xvector.1.scp")
+    cmd = [exe, "--use-gpu=no", f"--min-chunk-size={int(z['min_chunk_size'])}", f"--chunk-size={int(z['chunk_size'])}",
+           f"--nnet-config={g}/{name}_extract.config", f"cat {g}/{name}_final.raw |",
+           f"ark:cat {g}/{name}_feats.ark |", f"ark,scp:{ark},{scp}"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    assert "Done 5 utterances, failed for 2" in r.stderr, r.stderr
+    assert "real-time factor assuming 100 frames/sec" in r.stderr
+    got = dict(kf.read_scp(scp))
+    keys = [f"utt{i:07d}" for i in range(len(z["lengths"]))]
+    assert list(got) == [k for k, o in zip(keys, z["ok"]) if o]            # input order, failed ones absent
+    a = np.stack([got[k] for k in got])
+    rr, cc = parity_metrics(a, z["embeddings"][z["ok"]])
+    assert rr <= TOL_REL and cc >= TOL_COS, (rr, cc)
+    # text output + --pad-input + --output-node instead of the config file
+    cmd = [exe, "--pad-input=true", f"--min-chunk-size={int(z['min_chunk_size'])}", f"--chunk-size={int(z['chunk_size'])}",
+           f"--output-node={z['output_node']}", f"{g}/{name}_final.raw", f"ark:{g}/{name}_feats.ark", f"ark,t:{tmp_path}/x.txt"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    got = dict(kf.read_ark(f"{tmp_path}/x.txt"))
+    a = np.stack([got[k] for k in got])
+    rr, cc = parity_metrics(a, z["embeddings_pad_input"][z["ok_pad_input"]])
+    assert rr <= TOL_REL and cc >= TOL_COS, (rr, cc)
+
+
+def test_cli_two_input(cvx, kf, synth, model_dir, require_gpu, tmp_path):
+    """nnet3-cvector-compute-multiple-input --name=a,b 2 <nnet> <feats1> <feats2> <wspec>
+    (extract_cvectors_with_am.sh:99-110), names given in swapped order."""
+    import os
+    import subprocess
+    from oracle.nnet3_oracle import Oracle, extract_all, parity_metrics
+    path, model = model_dir("v4_two_input")
+    lengths = [120, 333, 40]
+    f23 = synth.make_features(lengths, 23, 1)
+    f40 = synth.make_features(lengths, 40, 2)
+    starts = np.cumsum([0] + lengths[:-1])
+    keys = synth.utt_keys(3)
+    kf.write_ark(str(tmp_path / "a.ark"), [(k, f23[s:s + n]) for k, s, n in zip(keys, starts, lengths)])
+    kf.write_ark(str(tmp_path / "b.ark"), [(k, f40[s:s + n]) for k, s, n in zip(keys, starts, lengths)], binary=False)
+    exe = os.path.join(cvx.BIN_DIR, "nnet3-cvector-compute-multiple-input")
+    cmd = [exe, "--use-gpu=no", "--min-chunk-size=25", "--chunk-size=200", "--output-node=tdnn6_xvec.affine",
+           "--name=input_am,input", "2", path, f"ark:{tmp_path}/b.ark", f"ark:{tmp_path}/a.ark", f"ark:{tmp_path}/o.ark"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    got = np.stack([v for _, v in kf.read_ark(str(tmp_path / "o.ark"))])
+    ref, ok = extract_all(Oracle(model, "tdnn6_xvec.affine", np.float64), {"input": f23, "input_am": f40}, lengths,
+                          chunk_size=200, min_chunk_size=25)
+    rr, cc = parity_metrics(got, ref[ok])
+    assert rr <= TOL_REL and cc >= TOL_COS, (rr, cc)
+
+
+def test_full_size_properties(cvx, synth, model_dir, require_gpu):
+    """size-independent checks at a BASELINE-sized slice (config 4 style long utterances):
+    (1) the frame-weighted average of per-chunk embeddings reproduces the utterance
+    embedding; (2) duplicating an utterance gives identical embeddings; (3) device-input
+    and host-input paths agree bit for bit."""
+    path, model = model_dir("v5_cvector")
+    mod = cvx.Model(path, "tdnn6_xvec.affine")
+    lengths = [30000, 12345, 30000, 10000, 1000]
+    feats = _inputs(synth, mod, lengths, 5)
+    feats["input"][42345:72345] = feats["input"][0:30000]       # utt 2 := utt 0
+    ex = cvx.Extractor(mod, precision="fp16", max_batch_rows=16384)
+    emb, ok = ex.extract(feats, lengths, chunk_size=10000, min_chunk_size=25)
+    assert ok.all()
+    assert np.array_equal(emb[0], emb[2])
+    n_chunks = sum(len(cvx.chunk_plan(T, 10000, 25, False)) for T in lengths)
+    ce = ex.last_chunk_embeddings(n_chunks)
+    i = 0
+    for u, T in enumerate(lengths):
+        plan = cvx.chunk_plan(T, 10000, 25, False)
+        w = np.array([n for _, n in plan], np.float64)
+        avg = (ce[i:i + len(plan)].astype(np.float64) * w[:, None]).sum(0) / w.sum()
+        assert np.allclose(avg, emb[u], rtol=1e-5, atol=1e-5)
+        i += len(plan)
