@@ -193,13 +193,19 @@ int cvx_engine_get_profile(cvx_engine* engine, cvx_kernel_profile* records, int3
 void cvx_engine_reset_profile(cvx_engine* engine);
 /* Kernels launched by this engine since creation (all classes). */
 int64_t cvx_engine_launch_count(const cvx_engine* engine);
+/* Device time of the last cvx_extract call: CUDA events on the engine's compute stream
+ * bracketing all of its batches (H2D copies of a host-input call are waited on by that
+ * stream, so they are inside the bracket). */
+double cvx_engine_last_extract_ms(const cvx_engine* engine);
 
 /* ---------------------------------------------------- kernel unit entries --
  * Single-kernel entry points used by tests/ to check each kernel in isolation
  * against the oracle (device pointers, default stream, synchronous). */
 
 /* out[r, n] = post(sum_taps A[r+off_tap, :] W_tap^T): one TDNN layer on fp32 host data;
- * converts to `precision`, runs the production kernel, returns fp32 [rows, out_dim]. */
+ * converts to `precision`, runs the production kernel, returns fp32 [rows, out_dim].
+ * The input is treated like a previous layer's output (one 64-column K block walk per
+ * tap, TMA row offsets); `precision | 0x100` selects the compact first-layer splice. */
 int cvx_test_tdnn_layer(int32_t device, int32_t precision, const float* in, int64_t rows,
                         int32_t in_dim, const int32_t* offsets, int32_t num_offsets,
                         const float* weight, const float* bias, int32_t relu, const float* scale,

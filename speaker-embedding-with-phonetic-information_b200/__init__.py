@@ -56,7 +56,7 @@ ABI_SYMBOLS = [
     "cvx_engine_options_default", "cvx_engine_create", "cvx_engine_destroy", "cvx_extract",
     "cvx_engine_last_chunk_embeddings", "cvx_host_alloc", "cvx_host_free", "cvx_device_alloc",
     "cvx_device_free", "cvx_memcpy_h2d", "cvx_device_count", "cvx_engine_get_profile",
-    "cvx_engine_reset_profile", "cvx_engine_launch_count", "cvx_test_tdnn_layer", "cvx_test_stats_pool",
+    "cvx_engine_reset_profile", "cvx_engine_launch_count", "cvx_engine_last_extract_ms", "cvx_test_tdnn_layer", "cvx_test_stats_pool",
 ]
 
 _lib = None
@@ -106,6 +106,8 @@ def load_library() -> C.CDLL:
     lib.cvx_engine_reset_profile.argtypes = [C.c_void_p]
     lib.cvx_engine_launch_count.argtypes = [C.c_void_p]
     lib.cvx_engine_launch_count.restype = C.c_int64
+    lib.cvx_engine_last_extract_ms.argtypes = [C.c_void_p]
+    lib.cvx_engine_last_extract_ms.restype = C.c_double
     lib.cvx_test_tdnn_layer.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32,
                                         C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
                                         C.c_void_p]
@@ -317,6 +319,9 @@ class Extractor:
 
     def launch_count(self) -> int:
         return int(self._lib.cvx_engine_launch_count(self._h))
+
+    def last_extract_ms(self) -> float:
+        return float(self._lib.cvx_engine_last_extract_ms(self._h))
 
 
 # -- single-kernel test entries ------------------------------------------------

@@ -224,6 +224,7 @@ void cvx_engine_reset_profile(cvx_engine* engine) {
   if (engine) engine->impl->ResetProfile();
 }
 int64_t cvx_engine_launch_count(const cvx_engine* engine) { return engine ? engine->impl->launch_count() : 0; }
+double cvx_engine_last_extract_ms(const cvx_engine* engine) { return engine ? engine->impl->last_call_ms() : 0.0; }
 
 int cvx_test_tdnn_layer(int32_t device, int32_t precision, const float* in, int64_t rows, int32_t in_dim,
                         const int32_t* offsets, int32_t num_offsets, const float* weight, const float* bias,

@@ -125,6 +125,8 @@ Engine::Engine(const Plan& plan, const cvx_engine_options& opts) : plan_(plan), 
     CVX_CUDA_CHECK(cudaEventCreateWithFlags(&feat_ready_[i], cudaEventDisableTiming));
     CVX_CUDA_CHECK(cudaEventCreateWithFlags(&feat_free_[i], cudaEventDisableTiming));
   }
+  CVX_CUDA_CHECK(cudaEventCreate(&call_begin_));
+  CVX_CUDA_CHECK(cudaEventCreate(&call_end_));
   if (plan_.input_dims.size() > kMaxASources) throw InvalidArgument("too many input streams");
 
   // ---- lower frame layers ----
@@ -254,6 +256,8 @@ Engine::~Engine() {
     if (feat_ready_[i]) cudaEventDestroy(feat_ready_[i]);
     if (feat_free_[i]) cudaEventDestroy(feat_free_[i]);
   }
+  if (call_begin_) cudaEventDestroy(call_begin_);
+  if (call_end_) cudaEventDestroy(call_end_);
   if (compute_) cudaStreamDestroy(compute_);
   if (copy_) cudaStreamDestroy(copy_);
 }
@@ -315,7 +319,8 @@ void Engine::EncodeMaps() {
       Encode2D(&a.a_maps[s], elem_, b.ptr, rows_cap_, b.ld, kGemmBlockK, kGemmBlockM);
     }
     for (size_t s = op.srcs.size(); s < kMaxASources; ++s) a.a_maps[s] = a.a_maps[0];
-    Encode2D(&a.b_map, elem_, op.d_w, op.n_pad, op.k_pad, kGemmBlockK, kGemmBlockN);
+    a.b_box_rows = std::min(kGemmBlockN, op.n_pad);
+    Encode2D(&a.b_map, elem_, op.d_w, op.n_pad, op.k_pad, kGemmBlockK, a.b_box_rows);
     const Buffer& ob = buffers_[op.out_buffer];
     Encode2D(&a.c_map, elem_, ob.ptr, rows_cap_, ob.ld, 64, 32);
     a.num_kb = static_cast<int32_t>(op.kb.size());
@@ -587,6 +592,7 @@ void Engine::Extract(const float* const* feats, int32_t num_streams, int64_t tot
   CVX_CUDA_CHECK(cudaStreamSynchronize(compute_));
 
   // ---- batches ----
+  CVX_CUDA_CHECK(cudaEventRecord(call_begin_, compute_));
   for (size_t bi = 0; bi < batches.size(); ++bi) {
     const Batch& b = batches[bi];
     const int64_t rows = b.row1 - b.row0;
@@ -655,7 +661,9 @@ void Engine::Extract(const float* const* feats, int32_t num_streams, int64_t tot
   ProfEnd();
   if (!dev_out)
     CVX_CUDA_CHECK(cudaMemcpyAsync(out, d_out_, static_cast<size_t>(num_utts) * E * 4, cudaMemcpyDeviceToHost, compute_));
+  CVX_CUDA_CHECK(cudaEventRecord(call_end_, compute_));
   CVX_CUDA_CHECK(cudaStreamSynchronize(compute_));
+  CVX_CUDA_CHECK(cudaEventElapsedTime(&last_call_ms_, call_begin_, call_end_));
   ProfResolve();
   last_num_chunks_ = num_chunks;
 }

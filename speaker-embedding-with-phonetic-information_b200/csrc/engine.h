@@ -53,6 +53,7 @@ class Engine {
   int GetProfile(cvx_kernel_profile* recs, int32_t max_recs);
   void ResetProfile();
   int64_t launch_count() const { return launches_; }
+  float last_call_ms() const { return last_call_ms_; }
   const Plan& plan() const { return plan_; }
 
  private:
@@ -123,6 +124,8 @@ class Engine {
        *d_out_ = nullptr;
   size_t partials_cap_ = 0, stats_cap_ = 0, seg_cap_[2] = {0, 0}, chunk_emb_cap_ = 0, out_cap_ = 0;
   int64_t last_num_chunks_ = 0;
+  cudaEvent_t call_begin_ = nullptr, call_end_ = nullptr;
+  float last_call_ms_ = 0.f;
 
   bool profile_ = false;
   std::vector<PendingEvent> pending_;

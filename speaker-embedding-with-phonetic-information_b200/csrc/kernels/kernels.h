@@ -36,6 +36,7 @@ struct TdnnGemmArgs {
   int32_t n_pad;          // multiple of 64
   int32_t num_m_tiles;    // ceil(rows / 128)
   int32_t num_n_tiles;    // ceil(n_pad / 256)
+  int32_t b_box_rows;     // rows of the W box = min(256, n_pad)
   const float2* post;     // [n_pad] {b', o}
   int32_t relu;
   int32_t ab_format;      // 0 = fp16, 1 = bf16 (UMMA F16F32Format)

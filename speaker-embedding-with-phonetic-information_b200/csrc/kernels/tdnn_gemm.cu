@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(kThreads, 1) tdnn_gemm_kernel(const __grid_con
         const int n0 = (tile % num_n_tiles) * kGemmBlockN;
         for (int kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-          ptx::mbar_arrive_expect_tx(&full_bar[stage], kABytes + kBBytes);
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], kABytes + args.b_box_rows * kGemmBlockK * 2);
           const KBlockDesc d = args.kb[kb];
           ptx::tma_load_2d(smem_a + stage * kABytes, &args.a_maps[d.src], &full_bar[stage], d.col, m0 + d.rowoff);
           ptx::tma_load_2d(smem_b + stage * kBBytes, &args.b_map, &full_bar[stage], kb * kGemmBlockK, n0);
