@@ -145,7 +145,9 @@ Engine::Engine(const Plan& plan, const cvx_engine_options& opts) : plan_(plan), 
       int32_t b = StagingFor(L.taps);
       op.srcs.push_back(b);
       op.k_pad = buffers_[b].ld;
-      for (int32_t j = 0; j < op.k_pad / kGemmBlockK; ++j) op.kb.push_back({0, j * kGemmBlockK, 0});
+      const int32_t k_real = RoundUp(L.in_dim, 16);
+      for (int32_t j = 0; j * kGemmBlockK < k_real; ++j)
+        op.kb.push_back({0, j * kGemmBlockK, 0, std::min(kGemmBlockK, k_real - j * kGemmBlockK) / 16});
       col_map.push_back({0, 0});
       tap_dims.push_back(L.in_dim);
     } else {
@@ -163,7 +165,9 @@ Engine::Engine(const Plan& plan, const cvx_engine_options& opts) : plan_(plan), 
           op.srcs.push_back(b);
         }
         const int32_t d = buffers_[b].dim, dp = buffers_[b].ld;
-        for (int32_t j = 0; j < dp / kGemmBlockK; ++j) op.kb.push_back({si, j * kGemmBlockK, t.offset});
+        const int32_t d_real = RoundUp(d, 16);  // columns [d, d_real) of a source are exact zeros
+        for (int32_t j = 0; j * kGemmBlockK < d_real; ++j)
+          op.kb.push_back({si, j * kGemmBlockK, t.offset, std::min(kGemmBlockK, d_real - j * kGemmBlockK) / 16});
         col_map.push_back({klog, kpad});
         tap_dims.push_back(d);
         klog += d;
@@ -236,6 +240,7 @@ Engine::~Engine() {
     cudaFree(op.d_w);
     cudaFree(op.d_post);
   }
+  for (Staging& s : stagings_) cudaFree(s.d_colmap);
   for (SegOp& s : seg_ops_) {
     cudaFree(s.d_w);
     cudaFree(s.d_b);
@@ -285,6 +290,16 @@ int32_t Engine::StagingFor(const std::vector<Tap>& taps) {
   Buffer b;
   b.dim = col;
   b.ld = RoundUp(col, 64);
+  std::vector<uint32_t> colmap(b.ld, 0u);
+  for (const StageTap& st : s.taps) {
+    if (st.offset < -kStageMaxOffset || st.offset > kStageMaxOffset || st.dim > 0xFFFF)
+      throw InvalidArgument("input splice offset or dim out of range");
+    for (int32_t c = 0; c < st.dim; ++c)
+      colmap[st.col0 + c] = 0x80000000u | (static_cast<uint32_t>(st.stream) << 28) |
+                            (static_cast<uint32_t>(st.offset + 2048) << 16) | static_cast<uint32_t>(c);
+  }
+  s.d_colmap = DevAlloc<uint32_t>(colmap.size());
+  CVX_CUDA_CHECK(cudaMemcpy(s.d_colmap, colmap.data(), colmap.size() * 4, cudaMemcpyHostToDevice));
   s.buffer = static_cast<int32_t>(buffers_.size());
   buffers_.push_back(b);
   stagings_.push_back(s);
@@ -326,6 +341,7 @@ void Engine::EncodeMaps() {
     a.num_kb = static_cast<int32_t>(op.kb.size());
     for (size_t i = 0; i < op.kb.size(); ++i) a.kb[i] = op.kb[i];
     a.n_pad = op.n_pad;
+    a.n_mma = RoundUp(plan_.frame[op.layer].out_dim, 16);
     a.num_n_tiles = (op.n_pad + kGemmBlockN - 1) / kGemmBlockN;
     a.post = op.d_post;
     a.relu = plan_.frame[op.layer].relu ? 1 : 0;
@@ -400,8 +416,7 @@ void Engine::RunFrames(const float* const* dev_feats, int64_t rows, int64_t src_
       a.feats[i] = dev_feats[i];
       a.feat_dim[i] = plan_.input_dims[i];
     }
-    a.num_taps = static_cast<int32_t>(s.taps.size());
-    for (size_t i = 0; i < s.taps.size(); ++i) a.taps[i] = s.taps[i];
+    a.colmap = s.d_colmap;
     a.out = buffers_[s.buffer].ptr;
     a.ld_out = buffers_[s.buffer].ld;
     a.elem = elem_;
@@ -572,10 +587,14 @@ void Engine::Extract(const float* const* feats, int32_t num_streams, int64_t tot
   Grow(&d_weights_, &weights_cap_, weights.size() * 4);
   Grow(&d_utt_off_, &utt_off_cap_, utt_off.size() * 8);
   Grow(&d_partials_, &partials_cap_, static_cast<size_t>(max_slabs) * 2 * pool_buf.ld * 4);
-  Grow(&d_stats_, &stats_cap_, static_cast<size_t>(max_chunks) * pooled * 4);
+  // pooled statistics of several device batches are collected and the segment layers run on
+  // up to kSegFlushChunks chunks at once (a [few chunks, 3000] GEMM per batch is latency bound)
+  constexpr int64_t kSegFlushChunks = 16384;
+  const int64_t seg_cap_chunks = std::max(max_chunks, std::min<int64_t>(num_chunks, kSegFlushChunks));
+  Grow(&d_stats_, &stats_cap_, static_cast<size_t>(seg_cap_chunks) * pooled * 4);
   int32_t max_seg = 0;
   for (size_t i = 0; i + 1 < seg_ops_.size(); ++i) max_seg = std::max(max_seg, seg_ops_[i].out_dim);
-  for (int i = 0; i < 2; ++i) Grow(&d_seg_[i], &seg_cap_[i], static_cast<size_t>(max_chunks) * std::max(max_seg, 1) * 4);
+  for (int i = 0; i < 2; ++i) Grow(&d_seg_[i], &seg_cap_[i], static_cast<size_t>(seg_cap_chunks) * std::max(max_seg, 1) * 4);
   Grow(&d_chunk_emb_, &chunk_emb_cap_, static_cast<size_t>(num_chunks) * E * 4);
   Grow(&d_out_, &out_cap_, static_cast<size_t>(num_utts) * E * 4);
   if (!dev_in)
@@ -593,6 +612,7 @@ void Engine::Extract(const float* const* feats, int32_t num_streams, int64_t tot
 
   // ---- batches ----
   CVX_CUDA_CHECK(cudaEventRecord(call_begin_, compute_));
+  int64_t pending = 0, pending_c0 = 0;  // chunks whose statistics wait for the segment layers
   for (size_t bi = 0; bi < batches.size(); ++bi) {
     const Batch& b = batches[bi];
     const int64_t rows = b.row1 - b.row0;
@@ -632,26 +652,31 @@ void Engine::Extract(const float* const* feats, int32_t num_streams, int64_t tot
     CVX_CUDA_CHECK(LaunchStatsPoolFinalize(static_cast<const float*>(d_partials_), pool_buf.ld, dsl,
                                            static_cast<const int32_t*>(d_chunk_slab_off_) + slab_off_pos[bi], nchunks, D,
                                            plan_.pool_output_stddevs ? 1 : 0, plan_.pool_variance_floor,
-                                           static_cast<float*>(d_stats_), pooled, compute_));
+                                           static_cast<float*>(d_stats_) + pending * pooled, pooled, compute_));
     ProfEnd();
 
-    const float* cur = static_cast<const float*>(d_stats_);
-    int32_t cur_ld = pooled;
-    float* emb = static_cast<float*>(d_chunk_emb_) + b.c0 * E;
-    if (seg_ops_.empty()) {
-      CVX_CUDA_CHECK(cudaMemcpyAsync(emb, cur, static_cast<size_t>(nchunks) * E * 4, cudaMemcpyDeviceToDevice, compute_));
-    }
-    for (size_t si = 0; si < seg_ops_.size(); ++si) {
-      const SegOp& s = seg_ops_[si];
-      const bool last = si + 1 == seg_ops_.size();
-      float* dst = last ? emb : static_cast<float*>(d_seg_[si & 1]);
-      const int32_t dst_ld = s.out_dim;
-      ProfBegin(kProfSegment, 2.0 * nchunks * s.in_dim * s.out_dim, 0);
-      CVX_CUDA_CHECK(LaunchSegmentAffine(cur, cur_ld, nchunks, s.in_dim, s.d_w, s.d_b, s.relu ? 1 : 0, s.d_scale,
-                                         s.d_offset, s.out_dim, dst, dst_ld, compute_));
-      ProfEnd();
-      cur = dst;
-      cur_ld = dst_ld;
+    pending += nchunks;
+    const bool last_batch = bi + 1 == batches.size();
+    if (last_batch || pending + (batches[bi + 1].c1 - batches[bi + 1].c0) > seg_cap_chunks) {
+      const float* cur = static_cast<const float*>(d_stats_);
+      int32_t cur_ld = pooled;
+      float* emb = static_cast<float*>(d_chunk_emb_) + pending_c0 * E;
+      if (seg_ops_.empty())
+        CVX_CUDA_CHECK(cudaMemcpyAsync(emb, cur, static_cast<size_t>(pending) * E * 4, cudaMemcpyDeviceToDevice, compute_));
+      for (size_t si = 0; si < seg_ops_.size(); ++si) {
+        const SegOp& s = seg_ops_[si];
+        const bool last = si + 1 == seg_ops_.size();
+        float* dst = last ? emb : static_cast<float*>(d_seg_[si & 1]);
+        const int32_t dst_ld = s.out_dim;
+        ProfBegin(kProfSegment, 2.0 * pending * s.in_dim * s.out_dim, 0);
+        CVX_CUDA_CHECK(LaunchSegmentAffine(cur, cur_ld, pending, s.in_dim, s.d_w, s.d_b, s.relu ? 1 : 0, s.d_scale,
+                                           s.d_offset, s.out_dim, dst, dst_ld, compute_));
+        ProfEnd();
+        cur = dst;
+        cur_ld = dst_ld;
+      }
+      pending_c0 += pending;
+      pending = 0;
     }
   }
   ProfBegin(kProfAverage, 0, static_cast<double>(num_chunks + num_utts) * E * 4);

@@ -65,6 +65,7 @@ class Engine {
   struct Staging {
     std::vector<StageTap> taps;
     int32_t buffer = -1;
+    uint32_t* d_colmap = nullptr;
   };
   struct FrameOp {
     int32_t layer = 0;

@@ -25,6 +25,7 @@ struct KBlockDesc {
   int32_t src;     // index into the layer's A sources
   int32_t col;     // first column in that source buffer (multiple of 64)
   int32_t rowoff;  // time offset of the tap
+  int32_t k16;     // 16-column K steps of this block that hold real columns (1..4)
 };
 
 struct TdnnGemmArgs {
@@ -33,7 +34,8 @@ struct TdnnGemmArgs {
   CUtensorMap c_map;                 // out [rows_cap, ld_out], box 64 x 32, SWIZZLE_128B
   KBlockDesc kb[kMaxKBlocks];
   int32_t num_kb;
-  int32_t n_pad;          // multiple of 64
+  int32_t n_pad;          // output row pitch, multiple of 64
+  int32_t n_mma;          // roundup(out_dim, 16): columns the MMAs produce
   int32_t num_m_tiles;    // ceil(rows / 128)
   int32_t num_n_tiles;    // ceil(n_pad / 256)
   int32_t b_box_rows;     // rows of the W box = min(256, n_pad)
@@ -65,6 +67,7 @@ cudaError_t LaunchTdnnGemmSimt(const TdnnGemmSimtArgs& args, cudaStream_t stream
 
 // ---- input staging: fp32 features -> spliced operand rows ----------------
 constexpr int kMaxStageTaps = 16;
+constexpr int kStageMaxOffset = 2047;  // |time offset| representable in the column map
 struct StageTap {
   int32_t stream;
   int32_t offset;
@@ -74,8 +77,7 @@ struct StageTap {
 struct StageArgs {
   const float* feats[kMaxASources];  // per stream, row 0 = first row of the batch
   int32_t feat_dim[kMaxASources];
-  StageTap taps[kMaxStageTaps];
-  int32_t num_taps;
+  const uint32_t* colmap;            // [ld_out] device: output column -> (stream, offset, source column)
   void* out;        // [rows, ld_out] of `elem`
   int32_t ld_out;   // multiple of 64; columns beyond the taps are zero-filled
   int32_t elem;

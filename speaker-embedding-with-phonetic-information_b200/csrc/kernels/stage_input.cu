@@ -28,9 +28,14 @@ __device__ __forceinline__ float to_elem<float>(float v) {
   return v;
 }
 
+// colmap[c] for output column c: bit 31 = valid, [28,31) stream, [16,28) time offset + 2048,
+// [0,16) source column.  Built once per staging buffer on the host (engine.cu).
 template <typename T>
 __global__ void __launch_bounds__(256) stage_input_kernel(const __grid_constant__ StageArgs args) {
   constexpr int kVec = 16 / sizeof(T);
+  extern __shared__ uint32_t s_colmap[];
+  for (int c = threadIdx.x; c < args.ld_out; c += blockDim.x) s_colmap[c] = args.colmap[c];
+  __syncthreads();
   const int groups = args.ld_out / kVec;
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t row = idx / groups;
@@ -39,16 +44,13 @@ __global__ void __launch_bounds__(256) stage_input_kernel(const __grid_constant_
   alignas(16) T vals[kVec];
 #pragma unroll
   for (int e = 0; e < kVec; ++e) {
-    const int c = c0 + e;
+    const uint32_t m = s_colmap[c0 + e];
     float v = 0.f;
-    for (int t = 0; t < args.num_taps; ++t) {
-      const StageTap tp = args.taps[t];
-      if (c >= tp.col0 && c < tp.col0 + tp.dim) {
-        const int64_t sr = row + tp.offset;
-        if (sr >= args.src_row_min && sr < args.src_row_max)
-          v = __ldg(args.feats[tp.stream] + sr * args.feat_dim[tp.stream] + (c - tp.col0));
-        break;
-      }
+    if (m & 0x80000000u) {
+      const int stream = (m >> 28) & 7;
+      const int64_t sr = row + static_cast<int>((m >> 16) & 0xFFF) - 2048;
+      if (sr >= args.src_row_min && sr < args.src_row_max)
+        v = __ldg(args.feats[stream] + sr * args.feat_dim[stream] + (m & 0xFFFF));
     }
     vals[e] = to_elem<T>(v);
   }
@@ -62,9 +64,10 @@ cudaError_t LaunchStageInput(const StageArgs& args, cudaStream_t stream) {
   const int vec = 16 / static_cast<int>(ElemSize(args.elem));
   const int64_t total = args.rows * (args.ld_out / vec);
   const unsigned grid = static_cast<unsigned>((total + 255) / 256);
-  if (args.elem == kF16) stage_input_kernel<__half><<<grid, 256, 0, stream>>>(args);
-  else if (args.elem == kBF16) stage_input_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(args);
-  else stage_input_kernel<float><<<grid, 256, 0, stream>>>(args);
+  const size_t smem = static_cast<size_t>(args.ld_out) * sizeof(uint32_t);
+  if (args.elem == kF16) stage_input_kernel<__half><<<grid, 256, smem, stream>>>(args);
+  else if (args.elem == kBF16) stage_input_kernel<__nv_bfloat16><<<grid, 256, smem, stream>>>(args);
+  else stage_input_kernel<float><<<grid, 256, smem, stream>>>(args);
   return cudaGetLastError();
 }
 

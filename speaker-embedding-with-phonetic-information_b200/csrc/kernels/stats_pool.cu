@@ -9,60 +9,67 @@
 // Each chunk's valid rows [begin, end) are cut into slabs of <= 256 rows; one CTA
 // reduces (slab, 32 x 16-byte column group): every activation is read exactly once
 // with 128-bit loads, a warp reads 512 contiguous bytes of a row, the 8 warps of
-// the CTA take interleaved rows.  Per column the CTA forms shifted sums
-// S1 = sum(x - c), S2 = sum((x - c)^2) (c = the slab's first row) and emits the
-// slab's (mean, M2); a second tiny kernel merges a chunk's slabs with the
-// Chan/Welford pairwise update and writes [mean | sqrt(max(M2/n, floor))].
+// the CTA take interleaved rows.  Per column the CTA forms fp32 sums S1 = sum x,
+// S2 = sum x^2 over its <= 256 rows and emits the slab's (mean, M2 = S2 - S1^2/n); a
+// second tiny kernel merges a chunk's slabs with the Chan/Welford pairwise update
+// (count, mean, M2) and writes [mean | sqrt(max(M2/n, floor))] -- cancellation is
+// confined to one slab, where upstream sums x^2 over the whole chunk in fp32.
 // No tensor cores: there is no contraction here.
 #include "kernels.h"
 
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
-#include <type_traits>
-
 namespace cvx {
 namespace {
 
 constexpr int kPoolWarps = 8;
-constexpr int kPoolUnroll = 4;
+constexpr int kPoolUnroll = 8;
 
+// acc(s1, s2) += (x, x*x) for the 16-byte vector `u` of element type T.  fp16 / bf16
+// use sm_100a's mixed-precision FHADD / FHFMA (add.rn.f32.f16, fma.rn.f32.f16): the
+// 16-bit operand is consumed directly, accumulation is fp32 -- 2 instructions per
+// element and no conversion, which is what keeps this kernel HBM- and not issue-bound.
 template <typename T>
 struct Vec16;
 template <>
 struct Vec16<__half> {
   static constexpr int kN = 8;
-  __device__ static void unpack(const uint4& u, float (&f)[8]) {
-    const __half2* h = reinterpret_cast<const __half2*>(&u);
+  __device__ __forceinline__ static void accumulate(const uint4& u, float (&s1)[8], float (&s2)[8]) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float2 v = __half22float2(h[i]);
-      f[2 * i] = v.x;
-      f[2 * i + 1] = v.y;
-    }
+    for (int i = 0; i < 4; ++i)
+      asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %4;\n\t"
+          "add.rn.f32.f16 %0, lo, %0;\n\tadd.rn.f32.f16 %1, hi, %1;\n\t"
+          "fma.rn.f32.f16 %2, lo, lo, %2;\n\tfma.rn.f32.f16 %3, hi, hi, %3;\n\t}"
+          : "+f"(s1[2 * i]), "+f"(s1[2 * i + 1]), "+f"(s2[2 * i]), "+f"(s2[2 * i + 1])
+          : "r"(w[i]));
   }
 };
 template <>
 struct Vec16<__nv_bfloat16> {
   static constexpr int kN = 8;
-  __device__ static void unpack(const uint4& u, float (&f)[8]) {
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+  __device__ __forceinline__ static void accumulate(const uint4& u, float (&s1)[8], float (&s2)[8]) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float2 v = __bfloat1622float2(h[i]);
-      f[2 * i] = v.x;
-      f[2 * i + 1] = v.y;
-    }
+    for (int i = 0; i < 4; ++i)
+      asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %4;\n\t"
+          "add.rn.f32.bf16 %0, lo, %0;\n\tadd.rn.f32.bf16 %1, hi, %1;\n\t"
+          "fma.rn.f32.bf16 %2, lo, lo, %2;\n\tfma.rn.f32.bf16 %3, hi, hi, %3;\n\t}"
+          : "+f"(s1[2 * i]), "+f"(s1[2 * i + 1]), "+f"(s2[2 * i]), "+f"(s2[2 * i + 1])
+          : "r"(w[i]));
   }
 };
 template <>
 struct Vec16<float> {
   static constexpr int kN = 4;
-  __device__ static void unpack(const uint4& u, float (&f)[4]) {
-    f[0] = __uint_as_float(u.x);
-    f[1] = __uint_as_float(u.y);
-    f[2] = __uint_as_float(u.z);
-    f[3] = __uint_as_float(u.w);
+  __device__ __forceinline__ static void accumulate(const uint4& u, float (&s1)[4], float (&s2)[4]) {
+    const float x[4] = {__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w)};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      s1[i] += x[i];
+      s2[i] = fmaf(x[i], x[i], s2[i]);
+    }
   }
 };
 
@@ -75,9 +82,9 @@ __device__ __forceinline__ uint4 ld_stream(const void* p) {
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kPoolWarps * 32) stats_pool_partial_kernel(const T* __restrict__ act, int ld,
-                                                                              const PoolSlab* __restrict__ slabs,
-                                                                              float* __restrict__ partials) {
+__global__ void __launch_bounds__(kPoolWarps * 32, 4) stats_pool_partial_kernel(const T* __restrict__ act, int ld,
+                                                                                 const PoolSlab* __restrict__ slabs,
+                                                                                 float* __restrict__ partials) {
   constexpr int kN = Vec16<T>::kN;
   constexpr int kCols = 32 * kN;  // columns per CTA
   __shared__ float red[kPoolWarps][2][kCols];
@@ -89,32 +96,19 @@ __global__ void __launch_bounds__(kPoolWarps * 32) stats_pool_partial_kernel(con
   const bool active = col < ld;
   const T* base = act + slab.row_begin * ld + (active ? col : 0);
 
-  float c[kN], s1[kN], s2[kN];
+  float s1[kN], s2[kN];
 #pragma unroll
   for (int i = 0; i < kN; ++i) s1[i] = s2[i] = 0.f;
   if (active) {
-    Vec16<T>::unpack(ld_stream(base), c);  // shift = first row of the slab
     for (int r = warp; r < slab.nrows; r += kPoolWarps * kPoolUnroll) {
       uint4 v[kPoolUnroll];
 #pragma unroll
       for (int u = 0; u < kPoolUnroll; ++u) {
         const int rr = r + u * kPoolWarps;
-        if (rr < slab.nrows) v[u] = ld_stream(base + static_cast<int64_t>(rr) * ld);
+        v[u] = (rr < slab.nrows) ? ld_stream(base + static_cast<int64_t>(rr) * ld) : make_uint4(0u, 0u, 0u, 0u);
       }
 #pragma unroll
-      for (int u = 0; u < kPoolUnroll; ++u) {
-        const int rr = r + u * kPoolWarps;
-        if (rr < slab.nrows) {
-          float x[kN];
-          Vec16<T>::unpack(v[u], x);
-#pragma unroll
-          for (int i = 0; i < kN; ++i) {
-            const float d = x[i] - c[i];
-            s1[i] += d;
-            s2[i] = fmaf(d, d, s2[i]);
-          }
-        }
-      }
+      for (int u = 0; u < kPoolUnroll; ++u) Vec16<T>::accumulate(v[u], s1, s2);  // zeros add nothing
     }
   }
 #pragma unroll
@@ -131,15 +125,10 @@ __global__ void __launch_bounds__(kPoolWarps * 32) stats_pool_partial_kernel(con
       t1 += red[w][0][j];
       t2 += red[w][1][j];
     }
-    const float n = static_cast<float>(slab.nrows);
-    float cj;
-    if constexpr (sizeof(T) == 4) cj = reinterpret_cast<const float*>(act)[slab.row_begin * ld + col0 + j];
-    else if constexpr (std::is_same<T, __half>::value) cj = __half2float(act[slab.row_begin * ld + col0 + j]);
-    else cj = __bfloat162float(act[slab.row_begin * ld + col0 + j]);
-    const float mean_shift = t1 / n;
+    const float mean = t1 / static_cast<float>(slab.nrows);
     float* out = partials + static_cast<int64_t>(blockIdx.x) * 2 * ld + col0 + j;
-    out[0] = cj + mean_shift;
-    out[ld] = fmaxf(t2 - t1 * mean_shift, 0.f);  // M2 = sum (x - mean)^2
+    out[0] = mean;
+    out[ld] = fmaxf(t2 - t1 * mean, 0.f);  // M2 = sum (x - mean)^2 over this slab (<= 256 rows, fp32 sums)
   }
 }
 

@@ -10,9 +10,13 @@
 //
 //   warp 0      TMA producer (one lane): A tile 128x64 + W tile 256x64 per stage
 //   warp 1      TMEM owner; one lane issues tcgen05.mma (128 x N x 16, fp32 accum in TMEM)
-//   warps 2-5   epilogue: tcgen05.ld -> +bias, ReLU, +BN offset -> fp16/bf16 ->
+//   warps 2-9   epilogue (two warps per TMEM lane quarter, alternating 64-column
+//               chunks): tcgen05.ld -> +bias, ReLU, +BN offset -> fp16/bf16 ->
 //               swizzled smem -> TMA store, overlapped with the next tile's MMAs
 //               through two 256-column accumulator stages.
+// Padding is not computed: a tap whose source has d columns issues only
+// ceil(d/16) K steps (KBlockDesc::k16), and the last N tile uses UMMA_N =
+// roundup(out_dim,16) - n0; pad columns beyond that are never read by a consumer.
 // Persistent CTAs (one per SM), static round-robin over (m_tile, n_tile).
 #include "kernels.h"
 #include "ptx.cuh"
@@ -30,14 +34,14 @@ constexpr int kCWarpBytes = 32 * 128;                   // 32 rows x 64 cols x 2
 constexpr int kSmemA = 0;
 constexpr int kSmemB = kSmemA + kStages * kABytes;           // 65536
 constexpr int kSmemC = kSmemB + kStages * kBBytes;           // 196608
-constexpr int kSmemPost = kSmemC + 4 * 2 * kCWarpBytes;      // 229376
+constexpr int kSmemPost = kSmemC + 8 * kCWarpBytes;          // 229376 (one staging buffer per epilogue warp)
 constexpr int kSmemBars = kSmemPost + kGemmBlockN * 8;       // 231424
 constexpr int kNumBars = 2 * kStages + 4;
 constexpr int kSmemTmemPtr = kSmemBars + kNumBars * 8;       // 231520
 constexpr int kSmemTotal = kSmemTmemPtr + 32;                // 231552 <= 232448
 constexpr int kTmemCols = 512;
-constexpr int kThreads = 192;
-constexpr int kEpilogueThreads = 128;
+constexpr int kThreads = 320;
+constexpr int kEpilogueThreads = 256;
 
 template <bool kBF16>
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
@@ -45,10 +49,9 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&v);
   } else {
-    a = fminf(fmaxf(a, -65504.f), 65504.f);
-    b = fminf(fmaxf(b, -65504.f), 65504.f);
-    __half2 v = __floats2half2_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&v);
+    uint32_t r;  // saturating: a finite fp32 never becomes an fp16 infinity
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
   }
 }
 
@@ -127,7 +130,7 @@ __global__ void __launch_bounds__(kThreads, 1) tdnn_gemm_kernel(const __grid_con
       int it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
         const int n0 = (tile % num_n_tiles) * kGemmBlockN;
-        const int n_cols = min(kGemmBlockN, args.n_pad - n0);
+        const int n_cols = min(kGemmBlockN, args.n_mma - n0);  // multiple of 16
         const uint32_t idesc = ptx::make_idesc_f16(kBF16 ? 1u : 0u, kGemmBlockM, n_cols);
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
@@ -139,10 +142,11 @@ __global__ void __launch_bounds__(kThreads, 1) tdnn_gemm_kernel(const __grid_con
           ptx::tcgen05_fence_after();
           const uint64_t a_desc = ptx::make_umma_desc_sw128(ptx::smem_u32(smem_a + stage * kABytes));
           const uint64_t b_desc = ptx::make_umma_desc_sw128(ptx::smem_u32(smem_b + stage * kBBytes));
+          const int k16 = args.kb[kb].k16;  // K steps that hold real columns (1..4)
 #pragma unroll
           for (int k = 0; k < kGemmBlockK / 16; ++k) {
             // +32 bytes per 16-element K step inside the 128-byte swizzle row (>>4 encoded)
-            ptx::umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+            if (k < k16) ptx::umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
           }
           ptx::umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
           if (++stage == kStages) {
@@ -155,15 +159,15 @@ __global__ void __launch_bounds__(kThreads, 1) tdnn_gemm_kernel(const __grid_con
     }
   } else {
     // ---------------------------------------------------------- epilogue --
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;  // which of the quarter's two warps: takes chunks c % 2 == half
     const int et = threadIdx.x - 64;
-    uint8_t* my_c = smem_c + q * 2 * kCWarpBytes;
-    int cbuf = 0;
+    uint8_t* buf = smem_c + (warp - 2) * kCWarpBytes;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m0 = (tile / num_n_tiles) * kGemmBlockM;
       const int n0 = (tile % num_n_tiles) * kGemmBlockN;
-      const int n_cols = min(kGemmBlockN, args.n_pad - n0);
+      const int n_chunks = (min(kGemmBlockN, args.n_mma - n0) + 63) >> 6;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
 
@@ -176,9 +180,8 @@ __global__ void __launch_bounds__(kThreads, 1) tdnn_gemm_kernel(const __grid_con
       ptx::tcgen05_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kGemmBlockN;
 
-      for (int c = 0; c < n_cols / 64; ++c) {
-        uint8_t* buf = my_c + cbuf * kCWarpBytes;
-        if (lane == 0) ptx::tma_store_wait_read<1>();  // the store that last read `buf` is done with it
+      for (int c = half; c < n_chunks; c += 2) {
+        if (lane == 0) ptx::tma_store_wait_read<0>();  // this warp's previous store is done reading `buf`
         __syncwarp();
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -210,7 +213,6 @@ __global__ void __launch_bounds__(kThreads, 1) tdnn_gemm_kernel(const __grid_con
           ptx::tma_store_2d(&args.c_map, buf, n0 + c * 64, m0 + q * 32);
           ptx::tma_store_commit();
         }
-        cbuf ^= 1;
       }
       ptx::tcgen05_fence_before();
       ptx::mbar_arrive(&tmem_empty_bar[as]);

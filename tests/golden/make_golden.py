@@ -44,6 +44,7 @@ CHUNK, MIN_CHUNK = 300, 25
 for name, spec in SPECS.items():
     model = sy.make_model(spec["topology"], seed=42, num_speakers=16, num_senones=24, **spec["kw"])
     kf.write_nnet3(os.path.join(here, f"{name}_final.raw"), model, binary=True)
+    model = kf.read_nnet3(os.path.join(here, f"{name}_final.raw"))   # what every reader of the file sees (fp32 scalars)
     feats = sy.make_features(LENGTHS, 23, seed=1234)
     emb, ok = extract_all(Oracle(model, spec["node"], np.float64), {"input": feats}, LENGTHS,
                           chunk_size=CHUNK, min_chunk_size=MIN_CHUNK)

@@ -1,0 +1,235 @@
+"""The oracle is checked before it is allowed to judge the CUDA path
+(last paragraph).  CPU only."""
+import numpy as np
+import pytest
+
+from oracle.nnet3_oracle import (Oracle, chunk_plan, extract_all, extract_utt, pad_chunk, parity_metrics,
+                                 parse_descriptor, round_bf16, round_fp16)
+from oracle.torch_route import forward_chunk_torch
+
+
+def _feats(synth, oracle, lengths, seed=1):
+    return {n: synth.make_features(lengths, oracle.g.nodes[n].dim, seed + i) for i, n in enumerate(oracle.g.input_names)}
+
+
+# ---- pinned by the reference: descriptor grammar (xconfig/utils.py:599-631) ----
+REFERENCE_DESCRIPTOR_VECTORS = [
+    ("Sum(foo,bar)", "Sum(foo, bar)"),
+    ("Sum(foo1,bar-3_4)", "Sum(foo1, bar-3_4)"),
+    ("Append(input@-3, input@0, input@3)", "Append(Offset(input, -3), input, Offset(input, 3))"),
+    ("Append(-3,0,3)", "Append(Offset(prev_layer, -3), prev_layer, Offset(prev_layer, 3))"),
+    ("[-1]", "prev_layer"),
+    ("[-2]", "last_but_one_layer"),
+    ("[-2]@3", "Offset(last_but_one_layer, 3)"),
+]
+
+
+@pytest.mark.parametrize("src,want", REFERENCE_DESCRIPTOR_VECTORS)
+def test_descriptor_strings_match_reference_self_test(synth, src, want):
+    assert synth.normalize_descriptor(src, ["last_but_one_layer", "prev_layer"]) == want
+
+
+def test_reference_tokenizer_vectors(synth):
+    # utils.py:601-607
+    t = lambda s, p=None: synth.tokenize_descriptor(s, p)
+    assert t("hi") == ["hi"]
+    assert t("hi there") == ["hi", "there"]
+    assert t("hi,there") == ["hi", ",", "there"]
+    assert t("hi@-1,there") == ["hi", "@", "-1", ",", "there"]
+    assert t("hi(there)") == ["hi", "(", "there", ")"]
+    assert t("[-1]@2", ["foo", "bar"]) == ["bar", "@", "2"]
+    assert t("[-2].special@2", ["foo", "bar"]) == ["foo.special", "@", "2"]
+
+
+def test_v2_config_lines_match_hand_derived_final_config(synth):
+    """SURVEY.md Appendix A (derived from basic_layers.py:359,760-834, stats_layer.py:97-132)."""
+    m = synth.make_model("v2_xvector")
+    L = m.config_lines
+    assert L[0] == "input-node name=input dim=23"
+    assert L[1] == ("component-node name=tdnn1.affine component=tdnn1.affine input=Append(Offset(input, -2), "
+                    "Offset(input, -1), input, Offset(input, 1), Offset(input, 2))")
+    assert "component-node name=tdnn3.affine component=tdnn3.affine input=Append(Offset(tdnn2.batchnorm, -3), " \
+           "tdnn2.batchnorm, Offset(tdnn2.batchnorm, 3))" in L
+    assert "component-node name=stats-extraction-0-10000 component=stats-extraction-0-10000 input=tdnn5.batchnorm" in L
+    assert "component-node name=stats-pooling-0-10000 component=stats-pooling-0-10000 input=stats-extraction-0-10000" in L
+    assert "component-node name=tdnn6.affine component=tdnn6.affine input=Round(stats-pooling-0-10000, 1)" in L
+    assert L[-1] == "output-node name=output input=output.log-softmax objective=linear"
+    c = m.components
+    assert c["tdnn1.affine"].fields["LinearParams"].shape == (512, 115)
+    assert c["tdnn5.affine"].fields["LinearParams"].shape == (1500, 512)
+    assert c["tdnn6.affine"].fields["LinearParams"].shape == (512, 3000)
+    assert int(c["stats-pooling-0-10000"].fields["InputDim"]) == 3001
+
+
+def test_parse_descriptor():
+    assert parse_descriptor("Round(stats-pooling-0-10000, 1)") == ("Round", ("node", "stats-pooling-0-10000"), 1)
+    d = parse_descriptor("Append(Offset(a, -2), a, Offset(b.c, 2))")
+    assert d == ("Append", [("Offset", ("node", "a"), -2), ("node", "a"), ("Offset", ("node", "b.c"), 2)])
+    with pytest.raises(ValueError):
+        parse_descriptor("Sum(a, b)")
+
+
+# ---- self-consistency ----------------------------------------------------------
+@pytest.mark.parametrize("topology", ["v2_xvector", "v5_cvector", "v4_two_input"])
+def test_fp32_mode_agrees_with_fp64(synth, topology):
+    m = synth.make_model(topology)
+    node = synth.EMBEDDING_NODE[topology]
+    o64, o32 = Oracle(m, node, np.float64), Oracle(m, node, np.float32)
+    f = _feats(synth, o64, [400])
+    r, c = parity_metrics(o32.forward_chunk(f)[None], o64.forward_chunk(f)[None])
+    assert r < 1e-5 and c > 0.9999999
+
+
+@pytest.mark.parametrize("topology", ["v2_xvector", "v3_multitask", "v4_cvector", "v4_two_input", "v5_cvector"])
+def test_second_route_agrees(synth, topology):
+    """conv1d / batch_norm / var route vs splice+matmul route, both fp64."""
+    m = synth.make_model(topology)
+    node = synth.EMBEDDING_NODE[topology]
+    o = Oracle(m, node, np.float64)
+    f = _feats(synth, o, [137])
+    a = o.forward_chunk(f)
+    b = forward_chunk_torch(m, node, f)
+    r, c = parity_metrics(b[None], a[None])
+    assert r < 1e-9, r
+
+
+@pytest.mark.parametrize("topology,ctx", [("v2_xvector", (7, 7)), ("v3_multitask_3share", (7, 7)),
+                                          ("v4_cvector", (13, 7)), ("v5_cvector", (13, 7))])
+def test_context_and_valid_frame_count(synth, topology, ctx):
+    m = synth.make_model(topology, hidden=32, stats_dim=40, am_hidden=24, am_bottleneck=8)
+    o = Oracle(m, synth.EMBEDDING_NODE[topology], np.float64)
+    assert o.context() == ctx
+    L, R = ctx
+    # exactly L+R+1 frames -> one pooled frame -> stddev at the floor; one fewer -> not computable
+    f = _feats(synth, o, [L + R + 1])
+    e = o.forward_chunk(f)
+    assert np.isfinite(e).all()
+    with pytest.raises(ValueError):
+        o.forward_chunk({k: v[:-1] for k, v in f.items()})
+
+
+def test_tiny_net_against_pure_python_loops(synth):
+    """hand evaluation of every operator with scalar loops (no numpy broadcasting)."""
+    m = synth.make_tiny_model(feat_dim=3, hidden=4, pooled=5, emb=3)
+    o = Oracle(m, "tdnn6.affine", np.float64)
+    T = 12
+    x = synth.make_features([T], 3, 2).astype(np.float64)
+    c = m.components
+
+    def affine(name, rows):  # rows: list of lists
+        W, b = c[name].fields["LinearParams"].astype(np.float64), c[name].fields["BiasParams"].astype(np.float64)
+        return [[sum(W[n][k] * r[k] for k in range(len(r))) + b[n] for n in range(W.shape[0])] for r in rows]
+
+    def relu_bn(name, rows):
+        f = c[name + ".batchnorm"].fields
+        mean, var = f["StatsMean"].astype(np.float64), f["StatsVar"].astype(np.float64)
+        out = []
+        for r in rows:
+            o_ = []
+            for j, v in enumerate(r):
+                v = max(v, 0.0)
+                s = float(f["TargetRms"]) / (max(var[j], 0.0) + float(np.float64(np.float32(f["Epsilon"])))) ** 0.5
+                o_.append(v * s - mean[j] * s)
+            out.append(o_)
+        return out
+
+    xs = [[x[t + o_][k] for o_ in (-2, -1, 0, 1, 2) for k in range(3)] for t in range(2, T - 2)]      # t = 2..9
+    h1 = relu_bn("tdnn1", affine("tdnn1.affine", xs))
+    xs2 = [h1[i - 2] + h1[i] + h1[i + 2] for i in range(2, len(h1) - 2)]                             # t = 4..7
+    h2 = relu_bn("tdnn2", affine("tdnn2.affine", xs2))
+    h3 = relu_bn("tdnn3", affine("tdnn3.affine", h2))
+    n = len(h3)
+    assert n == T - 8
+    mean = [sum(r[j] for r in h3) / n for j in range(5)]
+    std = [max(sum(r[j] * r[j] for r in h3) / n - mean[j] ** 2, 1e-10) ** 0.5 for j in range(5)]
+    want = affine("tdnn6.affine", [mean + std])[0]
+    got = o.forward_chunk({"input": x})
+    assert np.allclose(got, want, rtol=1e-9, atol=1e-12)
+
+
+def test_packed_batch_equals_single_chunks(synth):
+    """extract_all over packed rows == per-utterance calls (bit identical)."""
+    m = synth.make_tiny_model(two_branch=True)
+    o = Oracle(m, "tdnn6.affine", np.float64)
+    lengths = [40, 25, 90]
+    f = _feats(synth, o, lengths)
+    all_, ok = extract_all(o, f, lengths, chunk_size=50, min_chunk_size=25)
+    base = 0
+    for u, T in enumerate(lengths):
+        one = extract_utt(o, {k: v[base:base + T] for k, v in f.items()}, 50, 25)
+        assert np.array_equal(one, all_[u])
+        base += T
+
+
+# ---- chunking / averaging (nnet3-xvector-compute main()) -------------
+def test_chunk_plan_cases():
+    assert chunk_plan(0, 100, 25, False) == []
+    assert chunk_plan(24, 100, 25, False) == []                       # shorter than min: fails
+    assert chunk_plan(24, 100, 25, True) == [(0, 24)]                 # padded instead
+    assert chunk_plan(99, 100, 25, False) == [(0, 99)]                # T < chunk: one chunk of T
+    assert chunk_plan(100, 100, 25, False) == [(0, 100)]
+    assert chunk_plan(210, 100, 25, False) == [(0, 100), (100, 100)]  # 10-frame tail skipped
+    assert chunk_plan(210, 100, 25, True) == [(0, 100), (100, 100), (200, 10)]
+    assert chunk_plan(225, 100, 25, False) == [(0, 100), (100, 100), (200, 25)]
+    assert chunk_plan(25000, -1, 25, False) == [(0, 25000)]
+    assert chunk_plan(25000, 10000, 25, False) == [(0, 10000), (10000, 10000), (20000, 5000)]
+
+
+def test_pad_chunk_replicates_edges():
+    x = np.arange(6, dtype=np.float32).reshape(3, 2)
+    p = pad_chunk(x, 8)
+    assert p.shape == (8, 2)
+    assert np.array_equal(p[:2], np.stack([x[0], x[0]]))      # left = (8-3)//2 = 2
+    assert np.array_equal(p[2:5], x)
+    assert np.array_equal(p[5:], np.stack([x[2]] * 3))
+
+
+def test_average_is_weighted_by_input_frames(synth):
+    m = synth.make_tiny_model()
+    o = Oracle(m, "tdnn6.affine", np.float64)
+    f = _feats(synth, o, [130])
+    e = extract_utt(o, f, chunk_size=50, min_chunk_size=25)
+    parts = [o.forward_chunk({"input": f["input"][s:s + n]}) for s, n in [(0, 50), (50, 50), (100, 30)]]
+    want = (50 * parts[0] + 50 * parts[1] + 30 * parts[2]) / 130
+    assert np.allclose(e, want, rtol=1e-12)
+
+
+def test_batchnorm_count_zero_is_refused(synth):
+    m = synth.make_tiny_model()
+    m.components["tdnn1.batchnorm"].fields["Count"] = 0.0
+    o = Oracle(m, "tdnn6.affine", np.float64)
+    with pytest.raises(ValueError, match="Count"):
+        o.forward_chunk({"input": synth.make_features([30], 5, 1)})
+
+
+# ---- golden vectors ------------------------------------------------------------
+@pytest.mark.parametrize("name", ["v2_small", "v5_small"])
+def test_oracle_reproduces_committed_golden(kf, name):
+    import os
+    g = os.path.join(os.path.dirname(__file__), "golden")
+    z = np.load(os.path.join(g, f"{name}.npz"))
+    model = kf.read_nnet3(os.path.join(g, f"{name}_final.raw"))
+    o = Oracle(model, str(z["output_node"]), np.float64)
+    emb, ok = extract_all(o, {"input": z["feats"]}, z["lengths"].tolist(), chunk_size=int(z["chunk_size"]),
+                          min_chunk_size=int(z["min_chunk_size"]))
+    assert ok.tolist() == z["ok"].tolist()
+    assert np.allclose(emb, z["embeddings"], rtol=1e-10, atol=1e-12)
+    # and the second route on the first utterance's first chunk
+    T0 = int(z["lengths"][0])
+    a = o.forward_chunk({"input": z["feats"][:T0]})
+    b = forward_chunk_torch(model, str(z["output_node"]), {"input": z["feats"][:T0]})
+    assert np.allclose(a, b, rtol=1e-9, atol=1e-11)
+
+
+def test_operand_rounding_model_predicts_tolerance(synth):
+    """Why fp16 and not bf16 operands: emulated operand rounding through the whole
+    net (weights + activations at layer boundaries) -- bf16 misses the north-star
+    1e-3, fp16 meets it with margin (DESIGN.md 'precision')."""
+    m = synth.make_model("v2_xvector")
+    ref = Oracle(m, "tdnn6.affine", np.float64)
+    f = _feats(synth, ref, [300])
+    e = ref.forward_chunk(f)
+    r16, c16 = parity_metrics(Oracle(m, "tdnn6.affine", np.float32, quant=round_fp16).forward_chunk(f)[None], e[None])
+    rbf, cbf = parity_metrics(Oracle(m, "tdnn6.affine", np.float32, quant=round_bf16).forward_chunk(f)[None], e[None])
+    assert r16 < 5e-4 and c16 > 0.99999
+    assert rbf > r16 * 3
