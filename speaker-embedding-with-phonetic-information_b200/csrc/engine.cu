@@ -18,6 +18,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 namespace cvx {
@@ -115,6 +116,9 @@ Engine::Engine(const Plan& plan, const cvx_engine_options& opts) : plan_(plan), 
     throw CudaError("the tcgen05 path needs an sm_100a device (Blackwell B200); found sm_" + std::to_string(prop.major) +
                     std::to_string(prop.minor));
   debug_ = static_cast<uint32_t>(opts.reserved[0]);
+  if (const char* env = std::getenv("CVX_GEMM_1CTA")) {
+    if (env[0] == '1') debug_ |= kDebugSingleCtaGemm;  // A/B aid: same results, 1-CTA tiles
+  }
   profile_ = opts.profile != 0;
   max_batch_rows_ = opts.max_batch_rows > 0 ? opts.max_batch_rows : (int64_t{1} << 19);
   max_batch_rows_ = (max_batch_rows_ + kGemmBlockM - 1) / kGemmBlockM * kGemmBlockM;
@@ -336,6 +340,8 @@ void Engine::EncodeMaps() {
     for (size_t s = op.srcs.size(); s < kMaxASources; ++s) a.a_maps[s] = a.a_maps[0];
     a.b_box_rows = std::min(kGemmBlockN, op.n_pad);
     Encode2D(&a.b_map, elem_, op.d_w, op.n_pad, op.k_pad, kGemmBlockK, a.b_box_rows);
+    a.b_box_rows_pair = std::min(kGemmBlockN / 2, op.n_pad);
+    Encode2D(&a.b_map_pair, elem_, op.d_w, op.n_pad, op.k_pad, kGemmBlockK, a.b_box_rows_pair);
     const Buffer& ob = buffers_[op.out_buffer];
     Encode2D(&a.c_map, elem_, ob.ptr, rows_cap_, ob.ld, 64, 32);
     a.num_kb = static_cast<int32_t>(op.kb.size());
@@ -452,7 +458,8 @@ void Engine::RunFrames(const float* const* dev_feats, int64_t rows, int64_t src_
       CVX_CUDA_CHECK(LaunchTdnnGemmSimt(a, compute_));
     } else {
       op.targs.num_m_tiles = static_cast<int32_t>((rows + kGemmBlockM - 1) / kGemmBlockM);
-      CVX_CUDA_CHECK(LaunchTdnnGemm(op.targs, num_sms_, compute_));
+      if (debug_ & kDebugSingleCtaGemm) CVX_CUDA_CHECK(LaunchTdnnGemm(op.targs, num_sms_, compute_));
+      else CVX_CUDA_CHECK(LaunchTdnnGemmPair(op.targs, num_sms_, compute_));
     }
     ProfEnd();
   }

@@ -33,7 +33,8 @@ struct InvalidArgument : public std::runtime_error {
                              __FILE__ + ":" + std::to_string(__LINE__) + ")");                       \
   } while (0)
 
-constexpr uint32_t kDebugForceTapPath = 1u;  // cvx_engine_options.reserved[0]
+constexpr uint32_t kDebugForceTapPath = 1u;   // cvx_engine_options.reserved[0] bits
+constexpr uint32_t kDebugSingleCtaGemm = 2u;  // use the 1-CTA tcgen05 kernel instead of the CTA-pair one
 
 class Engine {
  public:

@@ -31,6 +31,7 @@ struct KBlockDesc {
 struct TdnnGemmArgs {
   CUtensorMap a_maps[kMaxASources];  // [rows_cap, ld] activations, box 64 x 128, SWIZZLE_128B
   CUtensorMap b_map;                 // Wp [n_pad, k_pad], box 64 x 256, SWIZZLE_128B
+  CUtensorMap b_map_pair;            // same matrix, box 64 x 128 (one CTA's half of a W tile, cta_group::2)
   CUtensorMap c_map;                 // out [rows_cap, ld_out], box 64 x 32, SWIZZLE_128B
   KBlockDesc kb[kMaxKBlocks];
   int32_t num_kb;
@@ -39,6 +40,7 @@ struct TdnnGemmArgs {
   int32_t num_m_tiles;    // ceil(rows / 128)
   int32_t num_n_tiles;    // ceil(n_pad / 256)
   int32_t b_box_rows;     // rows of the W box = min(256, n_pad)
+  int32_t b_box_rows_pair;  // rows of the half-tile W box = min(128, n_pad)
   const float2* post;     // [n_pad] {b', o}
   int32_t relu;
   int32_t ab_format;      // 0 = fp16, 1 = bf16 (UMMA F16F32Format)
@@ -46,6 +48,8 @@ struct TdnnGemmArgs {
 
 size_t TdnnGemmSmemBytes();
 cudaError_t LaunchTdnnGemm(const TdnnGemmArgs& args, int num_sms, cudaStream_t stream);
+// CTA-pair (cta_group::2, 256-row tiles) variant of the same layer; the production path.
+cudaError_t LaunchTdnnGemmPair(const TdnnGemmArgs& args, int num_sms, cudaStream_t stream);
 
 // fp32 CUDA-core version of the same contraction (CVX_PRECISION_FP32; validation aid).
 struct TdnnGemmSimtArgs {

@@ -96,10 +96,18 @@ __global__ void __launch_bounds__(kPoolWarps * 32, 4) stats_pool_partial_kernel(
   const bool active = col < ld;
   const T* base = act + slab.row_begin * ld + (active ? col : 0);
 
-  float s1[kN], s2[kN];
+  // The fp32 validation path sums x - c (c = the slab's first row) so that it tracks the
+  // fp64 oracle to ~1e-6 even for near-constant columns; fp16/bf16 inputs have 11/8-bit
+  // mantissas, their squares are exact in fp32 and the plain sums are accurate enough.
+  constexpr bool kShift = sizeof(T) == 4;
+  float s1[kN], s2[kN], c[kN];
 #pragma unroll
-  for (int i = 0; i < kN; ++i) s1[i] = s2[i] = 0.f;
+  for (int i = 0; i < kN; ++i) s1[i] = s2[i] = c[i] = 0.f;
   if (active) {
+    if constexpr (kShift) {
+      const uint4 u0 = ld_stream(base);
+      c[0] = __uint_as_float(u0.x), c[1] = __uint_as_float(u0.y), c[2] = __uint_as_float(u0.z), c[3] = __uint_as_float(u0.w);
+    }
     for (int r = warp; r < slab.nrows; r += kPoolWarps * kPoolUnroll) {
       uint4 v[kPoolUnroll];
 #pragma unroll
@@ -108,7 +116,21 @@ __global__ void __launch_bounds__(kPoolWarps * 32, 4) stats_pool_partial_kernel(
         v[u] = (rr < slab.nrows) ? ld_stream(base + static_cast<int64_t>(rr) * ld) : make_uint4(0u, 0u, 0u, 0u);
       }
 #pragma unroll
-      for (int u = 0; u < kPoolUnroll; ++u) Vec16<T>::accumulate(v[u], s1, s2);  // zeros add nothing
+      for (int u = 0; u < kPoolUnroll; ++u) {
+        if constexpr (kShift) {
+          if (r + u * kPoolWarps < slab.nrows) {
+            const float x[4] = {__uint_as_float(v[u].x), __uint_as_float(v[u].y), __uint_as_float(v[u].z), __uint_as_float(v[u].w)};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float d = x[i] - c[i];
+              s1[i] += d;
+              s2[i] = fmaf(d, d, s2[i]);
+            }
+          }
+        } else {
+          Vec16<T>::accumulate(v[u], s1, s2);  // zero rows add nothing
+        }
+      }
     }
   }
 #pragma unroll
@@ -125,9 +147,11 @@ __global__ void __launch_bounds__(kPoolWarps * 32, 4) stats_pool_partial_kernel(
       t1 += red[w][0][j];
       t2 += red[w][1][j];
     }
-    const float mean = t1 / static_cast<float>(slab.nrows);
+    const float mean = t1 / static_cast<float>(slab.nrows);  // of x (or of x - c)
+    float cj = 0.f;
+    if constexpr (kShift) cj = reinterpret_cast<const float*>(act)[slab.row_begin * ld + col0 + j];
     float* out = partials + static_cast<int64_t>(blockIdx.x) * 2 * ld + col0 + j;
-    out[0] = mean;
+    out[0] = cj + mean;
     out[ld] = fmaxf(t2 - t1 * mean, 0.f);  // M2 = sum (x - mean)^2 over this slab (<= 256 rows, fp32 sums)
   }
 }

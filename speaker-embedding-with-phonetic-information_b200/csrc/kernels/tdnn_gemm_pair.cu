@@ -1,0 +1,252 @@
+// K1 (CTA-pair variant) -- TDNN frame layer as an implicit GEMM with cta_group::2.
+//
+// Same contraction and epilogue as tdnn_gemm.cu, but two CTAs on the two SMs of a TPC
+// form one 256 x N tile: each CTA stages its own 128 activation rows and only HALF of the
+// weight tile (N/2 rows) per K block; one thread of the leader CTA issues
+// tcgen05.mma.cta_group::2 (M = 256), which reads both CTAs' shared memory and writes a
+// 128 x N accumulator into each CTA's TMEM.  Per K block a CTA therefore moves 32 KB
+// (16 A + 16 W) instead of 48 KB for the same 512 MMA cycles, which is what the 1-CTA
+// kernel was bound by (ncu: ~590 cycles per K block at 48 KB regardless of MMA work),
+// and the freed shared memory deepens the ring from 4 to 6 stages.
+//
+//   both CTAs   warp 0: TMA producer -> own smem, completion counted on the LEADER's
+//                       full barrier (cp.async.bulk.tensor ... .cta_group::2)
+//   leader      warp 1: waits full, issues the MMAs, tcgen05.commit multicast frees the
+//                       stage in both CTAs / publishes the accumulator to both epilogues
+//   both CTAs   warps 2-9: epilogue of their own 128 rows; lane 0 of each warp arrives on
+//                       the leader's tmem_empty barrier.
+#include "kernels.h"
+#include "ptx.cuh"
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+namespace cvx {
+namespace {
+
+constexpr int kStages = 6;
+constexpr int kABytes = kGemmBlockM * kGemmBlockK * 2;        // 16 KB: 128 rows of this CTA
+constexpr int kBBytes = (kGemmBlockN / 2) * kGemmBlockK * 2;  // 16 KB: this CTA's half of W
+constexpr int kCWarpBytes = 32 * 128;
+constexpr int kSmemA = 0;
+constexpr int kSmemB = kSmemA + kStages * kABytes;      // 98304
+constexpr int kSmemC = kSmemB + kStages * kBBytes;      // 196608
+constexpr int kSmemPost = kSmemC + 8 * kCWarpBytes;     // 229376
+constexpr int kSmemBars = kSmemPost + kGemmBlockN * 8;  // 231424
+constexpr int kNumBars = 2 * kStages + 4;
+constexpr int kSmemTmemPtr = kSmemBars + kNumBars * 8;  // 231552
+constexpr int kSmemTotal = kSmemTmemPtr + 32;           // 231584 <= 232448
+constexpr int kTmemCols = 512;
+constexpr int kThreads = 320;
+constexpr int kEpilogueThreads = 256;
+constexpr int kEpilogueWarps = 8;
+
+template <bool kBF16>
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  if constexpr (kBF16) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+  } else {
+    uint32_t r;  // saturating: a finite fp32 never becomes an fp16 infinity
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+  }
+}
+
+template <bool kBF16>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+    tdnn_gemm_pair_kernel(const __grid_constant__ TdnnGemmArgs args) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* smem_a = smem + kSmemA;
+  uint8_t* smem_b = smem + kSmemB;
+  uint8_t* smem_c = smem + kSmemC;
+  float2* smem_post = reinterpret_cast<float2*>(smem + kSmemPost);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kSmemBars);  // used in the leader
+  uint64_t* empty_bar = full_bar + kStages;                            // per CTA
+  uint64_t* tmem_full_bar = empty_bar + kStages;                       // per CTA
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;                        // used in the leader
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + kSmemTmemPtr);
+
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x) >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+
+  if (threadIdx.x == 0) {
+    if (ptx::smem_u32(smem) & 1023u) __trap();
+    for (int i = 0; i < kStages; ++i) {
+      ptx::mbar_init(&full_bar[i], 2);   // one arrive.expect_tx per CTA of the pair
+      ptx::mbar_init(&empty_bar[i], 1);  // the leader's multicast commit
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&tmem_full_bar[i], 1);
+      ptx::mbar_init(&tmem_empty_bar[i], 2 * kEpilogueWarps);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&args.b_map_pair);
+    ptx::prefetch_tensormap(&args.c_map);
+    ptx::prefetch_tensormap(&args.a_maps[0]);
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc_pair(tmem_ptr, kTmemCols);
+    ptx::tmem_relinquish_pair();
+  }
+  ptx::tcgen05_fence_before();
+  ptx::cluster_sync_all();  // barriers of both CTAs are initialised before any remote arrive
+  ptx::tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int num_n_tiles = args.num_n_tiles;
+  const int num_tiles = ((args.num_m_tiles + 1) >> 1) * num_n_tiles;  // 256-row tiles
+  const int num_kb = args.num_kb;
+  const int first_tile = blockIdx.x >> 1;
+  const int tile_step = gridDim.x >> 1;
+
+  if (warp == 0) {
+    // ------------------------------------------------------ TMA producer --
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t stage_bytes = kABytes + args.b_box_rows_pair * kGemmBlockK * 2;
+      for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+        const int m0 = (tile / num_n_tiles) * (2 * kGemmBlockM) + static_cast<int>(rank) * kGemmBlockM;
+        const int n0 = (tile % num_n_tiles) * kGemmBlockN;
+        const int n_cols = min(kGemmBlockN, args.n_mma - n0);
+        const int nb0 = n0 + static_cast<int>(rank) * (n_cols >> 1);  // this CTA's half of the W tile
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          ptx::mbar_arrive_expect_tx_cluster(&full_bar[stage], stage_bytes, 0);
+          const KBlockDesc d = args.kb[kb];
+          ptx::tma_load_2d_pair(smem_a + stage * kABytes, &args.a_maps[d.src], &full_bar[stage], 0, d.col,
+                                m0 + d.rowoff);
+          ptx::tma_load_2d_pair(smem_b + stage * kBBytes, &args.b_map_pair, &full_bar[stage], 0, kb * kGemmBlockK,
+                                nb0);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------- MMA issuer (leader CTA) --
+    if (lane == 0 && rank == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
+        const int n0 = (tile % num_n_tiles) * kGemmBlockN;
+        const int n_cols = min(kGemmBlockN, args.n_mma - n0);  // multiple of 16
+        const uint32_t idesc = ptx::make_idesc_f16(kBF16 ? 1u : 0u, 2 * kGemmBlockM, n_cols);
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        ptx::mbar_wait(&tmem_empty_bar[as], aphase ^ 1);  // both epilogues drained this accumulator
+        ptx::tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + as * kGemmBlockN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);  // both CTAs' A and W halves have landed
+          ptx::tcgen05_fence_after();
+          const uint64_t a_desc = ptx::make_umma_desc_sw128(ptx::smem_u32(smem_a + stage * kABytes));
+          const uint64_t b_desc = ptx::make_umma_desc_sw128(ptx::smem_u32(smem_b + stage * kBBytes));
+          const int k16 = args.kb[kb].k16;
+#pragma unroll
+          for (int k = 0; k < kGemmBlockK / 16; ++k) {
+            if (k < k16) ptx::umma_f16_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+          }
+          ptx::umma_commit_pair_mc(&empty_bar[stage], 0x3);  // frees the stage in both CTAs
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        ptx::umma_commit_pair_mc(&tmem_full_bar[as], 0x3);  // accumulators complete -> both epilogues
+      }
+    }
+  } else {
+    // ---------------------------------------------------------- epilogue --
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;  // which of the quarter's two warps: takes chunks c % 2 == half
+    const int et = threadIdx.x - 64;
+    uint8_t* buf = smem_c + (warp - 2) * kCWarpBytes;
+    int it = 0;
+    for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
+      const int m0 = (tile / num_n_tiles) * (2 * kGemmBlockM) + static_cast<int>(rank) * kGemmBlockM;
+      const int n0 = (tile % num_n_tiles) * kGemmBlockN;
+      const int n_chunks = (min(kGemmBlockN, args.n_mma - n0) + 63) >> 6;
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpilogueThreads) : "memory");  // previous tile's params no longer read
+      for (int j = et; j < kGemmBlockN; j += kEpilogueThreads)
+        smem_post[j] = (n0 + j < args.n_pad) ? __ldg(&args.post[n0 + j]) : make_float2(0.f, 0.f);
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpilogueThreads) : "memory");
+
+      ptx::mbar_wait(&tmem_full_bar[as], aphase);
+      ptx::tcgen05_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kGemmBlockN;
+
+      for (int c = half; c < n_chunks; c += 2) {
+        if (lane == 0) ptx::tma_store_wait_read<0>();  // this warp's previous store is done reading `buf`
+        __syncwarp();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32b_x32(t_row + c * 64 + h * 32, r);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int e = 0; e < 8; e += 2) {
+              const float4 p = *reinterpret_cast<const float4*>(&smem_post[c * 64 + h * 32 + j + e]);
+              float v0 = __uint_as_float(r[j + e]) + p.x;
+              float v1 = __uint_as_float(r[j + e + 1]) + p.z;
+              if (args.relu) {
+                v0 = fmaxf(v0, 0.f);
+                v1 = fmaxf(v1, 0.f);
+              }
+              pk[e >> 1] = pack2<kBF16>(v0 + p.y, v1 + p.w);
+            }
+            const int unit = h * 4 + (j >> 3);  // 16-byte unit inside the 128-byte row
+            *reinterpret_cast<uint4*>(buf + lane * 128 + ((unit ^ (lane & 7)) << 4)) =
+                make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
+        }
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          ptx::tma_store_2d(&args.c_map, buf, n0 + c * 64, m0 + q * 32);
+          ptx::tma_store_commit();
+        }
+      }
+      ptx::tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_cluster(&tmem_empty_bar[as], 0);
+    }
+    if (lane == 0) ptx::tma_store_wait<0>();
+  }
+
+  ptx::tcgen05_fence_before();
+  ptx::cluster_sync_all();  // the peer may still be reading this CTA's smem / arriving on its barriers
+  if (warp == 1) {
+    ptx::tcgen05_fence_after();
+    ptx::tmem_dealloc_pair(tmem_base, kTmemCols);
+  }
+}
+
+}  // namespace
+
+cudaError_t LaunchTdnnGemmPair(const TdnnGemmArgs& args, int num_sms, cudaStream_t stream) {
+  const bool bf16 = args.ab_format == 1;
+  auto kern = bf16 ? tdnn_gemm_pair_kernel<true> : tdnn_gemm_pair_kernel<false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
+  if (e != cudaSuccess) return e;
+  const int tiles = ((args.num_m_tiles + 1) / 2) * args.num_n_tiles;
+  if (tiles <= 0) return cudaSuccess;
+  const int clusters = tiles < num_sms / 2 ? tiles : num_sms / 2;
+  kern<<<2 * clusters, kThreads, kSmemTotal, stream>>>(args);
+  return cudaGetLastError();
+}
+
+}  // namespace cvx

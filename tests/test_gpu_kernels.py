@@ -49,6 +49,12 @@ def test_tdnn_layer(cvx, require_gpu, precision, tol, rows, in_dim, offsets, out
     assert err < tol, f"{precision}: max rel err {err}"
 
 
+@pytest.mark.parametrize("rows,in_dim,offsets,out_dim", CASES)
+def test_tdnn_layer_single_cta_kernel(cvx, require_gpu, monkeypatch, rows, in_dim, offsets, out_dim):
+    monkeypatch.setenv("CVX_GEMM_1CTA", "1")
+    test_tdnn_layer(cvx, require_gpu, "fp16", 2e-3, rows, in_dim, offsets, out_dim)
+
+
 @pytest.mark.parametrize("precision", ["fp32", "fp16"])
 def test_tdnn_layer_compact_splice_and_plain(cvx, require_gpu, precision):
     """compact first-layer staging path; no relu / no batchnorm epilogue."""
@@ -62,9 +68,12 @@ def test_tdnn_layer_compact_splice_and_plain(cvx, require_gpu, precision):
     assert err < (2e-5 if precision == "fp32" else 2e-3)
 
 
-def test_tdnn_layer_many_tiles(cvx, require_gpu):
+@pytest.mark.parametrize("single_cta", [False, True])
+def test_tdnn_layer_many_tiles(cvx, require_gpu, monkeypatch, single_cta):
     """more tiles than SMs: exercises the persistent loop, both accumulator
-    stages and the smem ring wrap-around."""
+    stages and the smem ring wrap-around -- for the CTA-pair kernel (default) and
+    the 1-CTA kernel (CVX_GEMM_1CTA=1)."""
+    monkeypatch.setenv("CVX_GEMM_1CTA", "1" if single_cta else "0")
     rng = np.random.default_rng(9)
     rows = 128 * 200 + 37
     x = rng.standard_normal((rows, 128)).astype(np.float32)
