@@ -211,6 +211,12 @@ int cvx_test_tdnn_layer(int32_t device, int32_t precision, const float* in, int6
                         const float* weight, const float* bias, int32_t relu, const float* scale,
                         const float* offset, int32_t out_dim, float* out);
 
+/* Average device time (ms, CUDA events) of the production kernel for one such layer on
+ * `rows` rows of pseudo-random data, `iters` timed launches after warm-up. */
+int cvx_test_tdnn_layer_bench(int32_t device, int32_t precision, int64_t rows, int32_t in_dim,
+                              const int32_t* offsets, int32_t num_offsets, int32_t out_dim,
+                              int32_t iters, double* avg_ms);
+
 /* mean|stddev over row ranges [begin[c], end[c]) of an fp32 host matrix [rows, dim]. */
 int cvx_test_stats_pool(int32_t device, int32_t precision, const float* in, int64_t rows,
                         int32_t dim, const int64_t* begin, const int64_t* end, int64_t num_chunks,

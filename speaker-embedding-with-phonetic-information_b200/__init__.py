@@ -56,7 +56,7 @@ ABI_SYMBOLS = [
     "cvx_engine_options_default", "cvx_engine_create", "cvx_engine_destroy", "cvx_extract",
     "cvx_engine_last_chunk_embeddings", "cvx_host_alloc", "cvx_host_free", "cvx_device_alloc",
     "cvx_device_free", "cvx_memcpy_h2d", "cvx_device_count", "cvx_engine_get_profile",
-    "cvx_engine_reset_profile", "cvx_engine_launch_count", "cvx_engine_last_extract_ms", "cvx_test_tdnn_layer", "cvx_test_stats_pool",
+    "cvx_engine_reset_profile", "cvx_engine_launch_count", "cvx_engine_last_extract_ms", "cvx_test_tdnn_layer", "cvx_test_tdnn_layer_bench", "cvx_test_stats_pool",
 ]
 
 _lib = None
@@ -111,6 +111,8 @@ def load_library() -> C.CDLL:
     lib.cvx_test_tdnn_layer.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32,
                                         C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
                                         C.c_void_p]
+    lib.cvx_test_tdnn_layer_bench.argtypes = [C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
+                                              C.c_int32, C.POINTER(C.c_double)]
     lib.cvx_test_stats_pool.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
                                         C.c_int64, C.c_float, C.c_void_p]
     _lib = lib
@@ -339,6 +341,17 @@ def test_tdnn_layer(x: np.ndarray, offsets: Sequence[int], weight: np.ndarray, b
                                    x.shape[1], _ptr(offs), len(offs), _ptr(w), _ptr(b), int(relu), _ptr(s), _ptr(o),
                                    w.shape[0], _ptr(out)))
     return out
+
+
+def bench_tdnn_layer(rows: int, in_dim: int, offsets: Sequence[int], out_dim: int, iters: int = 10,
+                     precision: str = "fp16", device: int = 0) -> float:
+    """avg ms per launch of the production TDNN GEMM kernel for one layer shape."""
+    lib = load_library()
+    offs = np.ascontiguousarray(offsets, np.int32)
+    ms = C.c_double(0.0)
+    _check(lib.cvx_test_tdnn_layer_bench(device, PRECISION[precision], rows, in_dim, _ptr(offs), len(offs), out_dim,
+                                         iters, C.byref(ms)))
+    return ms.value
 
 
 def test_stats_pool(x: np.ndarray, begin: Sequence[int], end: Sequence[int], precision: str = "fp16",

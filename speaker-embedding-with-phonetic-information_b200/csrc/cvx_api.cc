@@ -264,6 +264,46 @@ int cvx_test_tdnn_layer(int32_t device, int32_t precision, const float* in, int6
   });
 }
 
+int cvx_test_tdnn_layer_bench(int32_t device, int32_t precision, int64_t rows, int32_t in_dim, const int32_t* offsets,
+                              int32_t num_offsets, int32_t out_dim, int32_t iters, double* avg_ms) {
+  if (!offsets || !avg_ms || num_offsets <= 0 || rows <= 0) return Fail(CVX_ERR_INVALID, "cvx_test_tdnn_layer_bench: bad argument");
+  return Guard([&] {
+    cvx::Plan plan;
+    plan.input_names = {"input"};
+    plan.input_dims = {in_dim};
+    cvx::Layer L;
+    L.name = "bench";
+    for (int32_t i = 0; i < num_offsets; ++i) L.taps.push_back({-1, offsets[i]});
+    L.in_dim = in_dim * num_offsets;
+    L.out_dim = out_dim;
+    L.weight.resize(static_cast<size_t>(L.in_dim) * out_dim);
+    uint32_t s = 12345u;
+    auto rnd = [&s]() {  // small LCG: values in [-0.5, 0.5)
+      s = s * 1664525u + 1013904223u;
+      return static_cast<float>(s >> 8) * (1.0f / 16777216.0f) - 0.5f;
+    };
+    for (float& w : L.weight) w = rnd() * 0.1f;
+    L.bias.assign(out_dim, 0.1f);
+    L.relu = true;
+    L.scale.assign(out_dim, 1.0f);
+    L.offset.assign(out_dim, -0.1f);
+    plan.frame.push_back(L);
+    plan.pool_src = 0;
+    plan.pool_right_context = 1 << 30;
+    plan.Finalize();
+    cvx_engine_options o;
+    cvx_engine_options_default(&o);
+    o.device = device;
+    o.precision = precision & 0xff;
+    o.reserved[0] = (precision & 0x100) ? 0 : static_cast<int32_t>(cvx::kDebugForceTapPath);
+    cvx::Engine eng(plan, o);
+    std::vector<float> x(static_cast<size_t>(rows) * in_dim);
+    for (float& v : x) v = rnd() * 4.0f;
+    const float* feats[1] = {x.data()};
+    *avg_ms = eng.DebugBenchFrames(feats, rows, iters);
+  });
+}
+
 int cvx_test_stats_pool(int32_t device, int32_t precision, const float* in, int64_t rows, int32_t dim,
                         const int64_t* begin, const int64_t* end, int64_t num_chunks, float variance_floor,
                         float* out) {

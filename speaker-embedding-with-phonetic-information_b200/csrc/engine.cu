@@ -352,6 +352,8 @@ void Engine::EncodeMaps() {
     a.post = op.d_post;
     a.relu = plan_.frame[op.layer].relu ? 1 : 0;
     a.ab_format = elem_ == kBF16 ? 1 : 0;
+    a.num_stages = 64;
+    if (const char* env = std::getenv("CVX_GEMM_STAGES")) a.num_stages = std::max(1, std::atoi(env));
   }
 }
 
@@ -484,6 +486,32 @@ void Engine::DebugForwardFrames(const float* const* feats, int64_t rows, float* 
   ProfResolve();
   for (int64_t r = 0; r < rows; ++r)
     for (int32_t c = 0; c < b.dim; ++c) out[r * b.dim + c] = ElemToFloat(host.data(), static_cast<size_t>(r) * b.ld + c, elem_);
+}
+
+double Engine::DebugBenchFrames(const float* const* feats, int64_t rows, int32_t iters) {
+  CVX_CUDA_CHECK(cudaSetDevice(opts_.device));
+  if (rows <= 0 || iters <= 0) throw InvalidArgument("rows and iters must be positive");
+  EnsureRows(rows);
+  const float* dev[kMaxASources] = {};
+  for (size_t s = 0; s < plan_.input_dims.size(); ++s) {
+    size_t bytes = static_cast<size_t>(rows) * plan_.input_dims[s] * 4;
+    Grow(&d_feat_[0][s], &d_feat_cap_[0][s], bytes);
+    CVX_CUDA_CHECK(cudaMemcpyAsync(d_feat_[0][s], feats[s], bytes, cudaMemcpyHostToDevice, compute_));
+    dev[s] = static_cast<const float*>(d_feat_[0][s]);
+  }
+  const bool was = profile_;
+  profile_ = false;
+  for (int i = 0; i < 3; ++i) RunFrames(dev, rows, 0, rows);  // warm-up
+  CVX_CUDA_CHECK(cudaStreamSynchronize(compute_));
+  profile_ = true;
+  ResetProfile();
+  for (int i = 0; i < iters; ++i) RunFrames(dev, rows, 0, rows);
+  CVX_CUDA_CHECK(cudaStreamSynchronize(compute_));
+  ProfResolve();
+  const double ms = prof_ms_[kProfGemm] / static_cast<double>(std::max<int64_t>(prof_launches_[kProfGemm], 1));
+  ResetProfile();
+  profile_ = was;
+  return ms;
 }
 
 // -------------------------------------------------------------- extract ----

@@ -50,6 +50,9 @@ class Engine {
   // Test hook: run only the frame layers on `rows` packed rows and return the last
   // frame layer's activations as fp32 [rows, out_dim].
   void DebugForwardFrames(const float* const* feats, int64_t rows, float* out);
+  // Test hook: average device time (ms) of the frame-layer GEMM launches over `iters`
+  // repetitions of the frame pass on `rows` rows (CUDA events around each launch).
+  double DebugBenchFrames(const float* const* feats, int64_t rows, int32_t iters);
 
   int GetProfile(cvx_kernel_profile* recs, int32_t max_recs);
   void ResetProfile();

@@ -44,6 +44,7 @@ struct TdnnGemmArgs {
   const float2* post;     // [n_pad] {b', o}
   int32_t relu;
   int32_t ab_format;      // 0 = fp16, 1 = bf16 (UMMA F16F32Format)
+  int32_t num_stages;     // smem ring depth actually used (<= the kernel's maximum; tuning aid)
 };
 
 size_t TdnnGemmSmemBytes();

@@ -100,6 +100,7 @@ __global__ void __launch_bounds__(kThreads, 1) tdnn_gemm_kernel(const __grid_con
   const int num_n_tiles = args.num_n_tiles;
   const int num_tiles = args.num_m_tiles * num_n_tiles;
   const int num_kb = args.num_kb;
+  const int nstages = min(max(args.num_stages, 1), kStages);
 
   if (warp == 0) {
     // ------------------------------------------------------ TMA producer --
@@ -115,7 +116,7 @@ __global__ void __launch_bounds__(kThreads, 1) tdnn_gemm_kernel(const __grid_con
           const KBlockDesc d = args.kb[kb];
           ptx::tma_load_2d(smem_a + stage * kABytes, &args.a_maps[d.src], &full_bar[stage], d.col, m0 + d.rowoff);
           ptx::tma_load_2d(smem_b + stage * kBBytes, &args.b_map, &full_bar[stage], kb * kGemmBlockK, n0);
-          if (++stage == kStages) {
+          if (++stage == nstages) {
             stage = 0;
             phase ^= 1;
           }
@@ -149,7 +150,7 @@ __global__ void __launch_bounds__(kThreads, 1) tdnn_gemm_kernel(const __grid_con
             if (k < k16) ptx::umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
           }
           ptx::umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
-          if (++stage == kStages) {
+          if (++stage == nstages) {
             stage = 0;
             phase ^= 1;
           }

@@ -100,6 +100,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   const int num_n_tiles = args.num_n_tiles;
   const int num_tiles = ((args.num_m_tiles + 1) >> 1) * num_n_tiles;  // 256-row tiles
   const int num_kb = args.num_kb;
+  const int nstages = min(max(args.num_stages, 1), kStages);
   const int first_tile = blockIdx.x >> 1;
   const int tile_step = gridDim.x >> 1;
 
@@ -122,7 +123,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                                 m0 + d.rowoff);
           ptx::tma_load_2d_pair(smem_b + stage * kBBytes, &args.b_map_pair, &full_bar[stage], 0, kb * kGemmBlockK,
                                 nb0);
-          if (++stage == kStages) {
+          if (++stage == nstages) {
             stage = 0;
             phase ^= 1;
           }
@@ -155,7 +156,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
             if (k < k16) ptx::umma_f16_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
           }
           ptx::umma_commit_pair_mc(&empty_bar[stage], 0x3);  // frees the stage in both CTAs
-          if (++stage == kStages) {
+          if (++stage == nstages) {
             stage = 0;
             phase ^= 1;
           }
