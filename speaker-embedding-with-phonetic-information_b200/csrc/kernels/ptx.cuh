@@ -14,6 +14,22 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// One deterministically elected lane of a fully active warp.  Role code (TMA producer, MMA
+// issuer) stays warp-convergent and predicates only the async instructions with this:
+// inside an `if (lane == 0)` region ptxas has to wrap every uniform-datapath instruction
+// (UTMALDG, UTCHMMA, UTCBAR) in an ELECT / BRA.U.ANY loop, ~100 issue cycles each.
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ------------------------------------------------------------- mbarrier ----
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

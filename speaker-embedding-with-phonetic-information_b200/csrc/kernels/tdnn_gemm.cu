@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(kThreads, 1) tdnn_gemm_kernel(const __grid_con
 
   if (warp == 0) {
     // ------------------------------------------------------ TMA producer --
-    if (lane == 0) {
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -112,10 +112,13 @@ __global__ void __launch_bounds__(kThreads, 1) tdnn_gemm_kernel(const __grid_con
         const int n0 = (tile % num_n_tiles) * kGemmBlockN;
         for (int kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-          ptx::mbar_arrive_expect_tx(&full_bar[stage], kABytes + args.b_box_rows * kGemmBlockK * 2);
-          const KBlockDesc d = args.kb[kb];
-          ptx::tma_load_2d(smem_a + stage * kABytes, &args.a_maps[d.src], &full_bar[stage], d.col, m0 + d.rowoff);
-          ptx::tma_load_2d(smem_b + stage * kBBytes, &args.b_map, &full_bar[stage], kb * kGemmBlockK, n0);
+          if (ptx::elect_one_sync()) {
+            ptx::mbar_arrive_expect_tx(&full_bar[stage], kABytes + args.b_box_rows * kGemmBlockK * 2);
+            const KBlockDesc d = args.kb[kb];
+            ptx::tma_load_2d(smem_a + stage * kABytes, &args.a_maps[d.src], &full_bar[stage], d.col, m0 + d.rowoff);
+            ptx::tma_load_2d(smem_b + stage * kBBytes, &args.b_map, &full_bar[stage], kb * kGemmBlockK, n0);
+          }
+          __syncwarp();
           if (++stage == nstages) {
             stage = 0;
             phase ^= 1;
@@ -125,7 +128,7 @@ __global__ void __launch_bounds__(kThreads, 1) tdnn_gemm_kernel(const __grid_con
     }
   } else if (warp == 1) {
     // -------------------------------------------------------- MMA issuer --
-    if (lane == 0) {
+    {
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -144,18 +147,21 @@ __global__ void __launch_bounds__(kThreads, 1) tdnn_gemm_kernel(const __grid_con
           const uint64_t a_desc = ptx::make_umma_desc_sw128(ptx::smem_u32(smem_a + stage * kABytes));
           const uint64_t b_desc = ptx::make_umma_desc_sw128(ptx::smem_u32(smem_b + stage * kBBytes));
           const int k16 = args.kb[kb].k16;  // K steps that hold real columns (1..4)
+          if (ptx::elect_one_sync()) {
 #pragma unroll
-          for (int k = 0; k < kGemmBlockK / 16; ++k) {
-            // +32 bytes per 16-element K step inside the 128-byte swizzle row (>>4 encoded)
-            if (k < k16) ptx::umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+            for (int k = 0; k < kGemmBlockK / 16; ++k) {
+              // +32 bytes per 16-element K step inside the 128-byte swizzle row (>>4 encoded)
+              if (k < k16) ptx::umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+            }
+            ptx::umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+            if (kb == num_kb - 1) ptx::umma_commit(&tmem_full_bar[as]);  // accumulator complete -> epilogue
           }
-          ptx::umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          __syncwarp();
           if (++stage == nstages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        ptx::umma_commit(&tmem_full_bar[as]);  // accumulator complete -> epilogue
       }
     }
   } else {
@@ -182,7 +188,7 @@ __global__ void __launch_bounds__(kThreads, 1) tdnn_gemm_kernel(const __grid_con
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kGemmBlockN;
 
       for (int c = half; c < n_chunks; c += 2) {
-        if (lane == 0) ptx::tma_store_wait_read<0>();  // this warp's previous store is done reading `buf`
+        if (ptx::elect_one_sync()) ptx::tma_store_wait_read<0>();  // this warp's previous store is done with `buf`
         __syncwarp();
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -210,7 +216,7 @@ __global__ void __launch_bounds__(kThreads, 1) tdnn_gemm_kernel(const __grid_con
         }
         ptx::fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) {
+        if (ptx::elect_one_sync()) {
           ptx::tma_store_2d(&args.c_map, buf, n0 + c * 64, m0 + q * 32);
           ptx::tma_store_commit();
         }
@@ -218,7 +224,7 @@ __global__ void __launch_bounds__(kThreads, 1) tdnn_gemm_kernel(const __grid_con
       ptx::tcgen05_fence_before();
       ptx::mbar_arrive(&tmem_empty_bar[as]);
     }
-    if (lane == 0) ptx::tma_store_wait<0>();
+    if (ptx::elect_one_sync()) ptx::tma_store_wait<0>();
   }
 
   ptx::tcgen05_fence_before();

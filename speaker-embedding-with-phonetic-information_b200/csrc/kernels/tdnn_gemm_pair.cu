@@ -106,7 +106,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 
   if (warp == 0) {
     // ------------------------------------------------------ TMA producer --
-    if (lane == 0) {
+    {
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t stage_bytes = kABytes + args.b_box_rows_pair * kGemmBlockK * 2;
@@ -117,12 +117,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         const int nb0 = n0 + static_cast<int>(rank) * (n_cols >> 1);  // this CTA's half of the W tile
         for (int kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-          ptx::mbar_arrive_expect_tx_cluster(&full_bar[stage], stage_bytes, 0);
-          const KBlockDesc d = args.kb[kb];
-          ptx::tma_load_2d_pair(smem_a + stage * kABytes, &args.a_maps[d.src], &full_bar[stage], 0, d.col,
-                                m0 + d.rowoff);
-          ptx::tma_load_2d_pair(smem_b + stage * kBBytes, &args.b_map_pair, &full_bar[stage], 0, kb * kGemmBlockK,
-                                nb0);
+          if (ptx::elect_one_sync()) {
+            ptx::mbar_arrive_expect_tx_cluster(&full_bar[stage], stage_bytes, 0);
+            const KBlockDesc d = args.kb[kb];
+            ptx::tma_load_2d_pair(smem_a + stage * kABytes, &args.a_maps[d.src], &full_bar[stage], 0, d.col,
+                                  m0 + d.rowoff);
+            ptx::tma_load_2d_pair(smem_b + stage * kBBytes, &args.b_map_pair, &full_bar[stage], 0,
+                                  kb * kGemmBlockK, nb0);
+          }
+          __syncwarp();
           if (++stage == nstages) {
             stage = 0;
             phase ^= 1;
@@ -132,7 +135,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     }
   } else if (warp == 1) {
     // ------------------------------------------- MMA issuer (leader CTA) --
-    if (lane == 0 && rank == 0) {
+    if (rank == 0) {
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -151,17 +154,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
           const uint64_t a_desc = ptx::make_umma_desc_sw128(ptx::smem_u32(smem_a + stage * kABytes));
           const uint64_t b_desc = ptx::make_umma_desc_sw128(ptx::smem_u32(smem_b + stage * kBBytes));
           const int k16 = args.kb[kb].k16;
+          if (ptx::elect_one_sync()) {
 #pragma unroll
-          for (int k = 0; k < kGemmBlockK / 16; ++k) {
-            if (k < k16) ptx::umma_f16_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+            for (int k = 0; k < kGemmBlockK / 16; ++k) {
+              if (k < k16) ptx::umma_f16_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+            }
+            ptx::umma_commit_pair_mc(&empty_bar[stage], 0x3);  // frees the stage in both CTAs
+            if (kb == num_kb - 1) ptx::umma_commit_pair_mc(&tmem_full_bar[as], 0x3);  // accumulators complete
           }
-          ptx::umma_commit_pair_mc(&empty_bar[stage], 0x3);  // frees the stage in both CTAs
+          __syncwarp();
           if (++stage == nstages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        ptx::umma_commit_pair_mc(&tmem_full_bar[as], 0x3);  // accumulators complete -> both epilogues
       }
     }
   } else {
@@ -188,7 +194,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kGemmBlockN;
 
       for (int c = half; c < n_chunks; c += 2) {
-        if (lane == 0) ptx::tma_store_wait_read<0>();  // this warp's previous store is done reading `buf`
+        if (ptx::elect_one_sync()) ptx::tma_store_wait_read<0>();  // this warp's previous store is done with `buf`
         __syncwarp();
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -216,16 +222,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         }
         ptx::fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) {
+        if (ptx::elect_one_sync()) {
           ptx::tma_store_2d(&args.c_map, buf, n0 + c * 64, m0 + q * 32);
           ptx::tma_store_commit();
         }
       }
       ptx::tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive_cluster(&tmem_empty_bar[as], 0);
+      if (ptx::elect_one_sync()) ptx::mbar_arrive_cluster(&tmem_empty_bar[as], 0);
     }
-    if (lane == 0) ptx::tma_store_wait<0>();
+    if (ptx::elect_one_sync()) ptx::tma_store_wait<0>();
   }
 
   ptx::tcgen05_fence_before();
