@@ -37,11 +37,22 @@ sys.path.insert(0, ROOT)
 PKG = "speaker-embedding-with-phonetic-information_b200"
 METRIC = "c-vector extraction audio-sec/sec"
 UNIT = "audio-sec/sec"
-UTTS_PER_GPU = 1250
-MIN_FRAMES, MAX_FRAMES = 1000, 30000
-CHUNK_SIZE, MIN_CHUNK_SIZE = 10000, 25
-TOPOLOGY = "v5_cvector"
-LENGTH_SEED = 1234 + 4
+# name -> (topology, utterances per GPU, min frames, max frames, chunk-size, length seed, description)
+WORKLOADS = {
+    "cfg4": ("v5_cvector", 1250, 1000, 30000, 10000, 1234 + 4,
+             "BASELINE configs[3]: egs/sre/v5 final c-vector at SRE16 scale, utterance-sharded "
+             "(1250 utts of 10-300 s per GPU; 8 GPUs = the 10k-utt config)"),
+    "cfg1": ("v2_xvector", 200, 300, 3000, 10000, 1234 + 1, "BASELINE configs[0]: v2 x-vector, 200 utts of 3-30 s"),
+    "cfg2": ("v3_multitask", 1000, 300, 3000, 10000, 1234 + 2, "BASELINE configs[1]: v3 multitask c-vector, 1k utts of 3-30 s"),
+    "cfg3": ("v4_two_input", 1000, 300, 3000, 10000, 1234 + 3,
+             "BASELINE configs[2]: v4 phonetic-adaptation c-vector, 23-dim + 40-dim hires streams, 1k utts"),
+    "cfg5x": ("v2_xvector", 125000, 200, 200, -1, 1234 + 5,
+              "BASELINE configs[4]: short-segment sweep, 2 s segments, x-vector net (125k segments per GPU; 8 GPUs = 1M)"),
+    "cfg5c": ("v5_cvector", 125000, 200, 200, -1, 1234 + 5,
+              "BASELINE configs[4]: short-segment sweep, 2 s segments, c-vector net (125k segments per GPU; 8 GPUs = 1M)"),
+}
+MIN_CHUNK_SIZE = 25
+TOPOLOGY, UTTS_PER_GPU, MIN_FRAMES, MAX_FRAMES, CHUNK_SIZE, LENGTH_SEED, WORKLOAD_DESC = WORKLOADS["cfg4"]
 
 
 def peaks():
@@ -110,7 +121,7 @@ def run_reference(args, rank: int) -> None:
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": float(np.mean(per_step)), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "BASELINE configs[3]: v5 c-vector, 10-300 s utterances, chunk-size 10000 (bounded sample)",
+        "config": {"workload": WORKLOAD_DESC + " (bounded sample)", "workload_id": args.workload,
                    "topology": TOPOLOGY, "chunk_size": CHUNK_SIZE, "min_chunk_size": MIN_CHUNK_SIZE},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -123,12 +134,18 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--utts-per-gpu", type=int, default=UTTS_PER_GPU)
+    ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS),
+                    help="cfg4 = the headline workload; the others are extra measurements for BASELINE.md's table")
+    ap.add_argument("--utts-per-gpu", type=int, default=0)
     ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16"])
     ap.add_argument("--max-batch-rows", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    global TOPOLOGY, UTTS_PER_GPU, MIN_FRAMES, MAX_FRAMES, CHUNK_SIZE, LENGTH_SEED, WORKLOAD_DESC
+    TOPOLOGY, UTTS_PER_GPU, MIN_FRAMES, MAX_FRAMES, CHUNK_SIZE, LENGTH_SEED, WORKLOAD_DESC = WORKLOADS[args.workload]
+    if args.utts_per_gpu <= 0:
+        args.utts_per_gpu = UTTS_PER_GPU
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -176,12 +193,13 @@ def main() -> None:
     model = cvx.Model(model_path, sy.EMBEDDING_NODE[TOPOLOGY])
     os.unlink(model_path)
     info = model.info
-    pinned = cvx.PinnedArray((total_rows, model.input_dims[0]))
+    pinned = [cvx.PinnedArray((total_rows, d)) for d in model.input_dims]
     rng = np.random.default_rng(LENGTH_SEED * 1000 + rank)
     step_rows = 1 << 20
-    for r0 in range(0, total_rows, step_rows):
-        r1 = min(total_rows, r0 + step_rows)
-        pinned.array[r0:r1] = rng.standard_normal((r1 - r0, model.input_dims[0]), dtype=np.float32)
+    for pa, d in zip(pinned, model.input_dims):
+        for r0 in range(0, total_rows, step_rows):
+            r1 = min(total_rows, r0 + step_rows)
+            pa.array[r0:r1] = rng.standard_normal((r1 - r0, d), dtype=np.float32)
     starts, lens, utts = [], [], []
     base = 0
     for u, T in enumerate(lengths.tolist()):
@@ -196,20 +214,23 @@ def main() -> None:
                        profile=True)
     lib = cvx.load_library()
     import ctypes as C
-    dptr = C.c_void_p()
-    nbytes = total_rows * model.input_dims[0] * 4
-    assert lib.cvx_device_alloc(local_rank, C.byref(dptr), nbytes) == 0, lib.cvx_last_error()
-    assert lib.cvx_memcpy_h2d(local_rank, dptr, pinned.array.ctypes.data_as(C.c_void_p), nbytes) == 0
+    dptrs, nbytes = [], 0
+    for pa, d in zip(pinned, model.input_dims):
+        dp = C.c_void_p()
+        nb = total_rows * d * 4
+        assert lib.cvx_device_alloc(local_rank, C.byref(dp), nb) == 0, lib.cvx_last_error()
+        assert lib.cvx_memcpy_h2d(local_rank, dp, pa.array.ctypes.data_as(C.c_void_p), nb) == 0
+        dptrs.append(dp.value)
+        nbytes += nb
     out = np.zeros((n_utts, info.embedding_dim), np.float32)
 
     def step_device():
-        ex.extract_chunks([dptr.value], total_rows, starts, lens, utts, None, n_utts, out=out,
-                          flags=cvx.FLAG_DEVICE_INPUT)
+        ex.extract_chunks(dptrs, total_rows, starts, lens, utts, None, n_utts, out=out, flags=cvx.FLAG_DEVICE_INPUT)
         return ex.last_extract_ms()
 
     def step_host():
         t0 = time.perf_counter()
-        ex.extract_chunks([pinned.array], total_rows, starts, lens, utts, None, n_utts, out=out)
+        ex.extract_chunks([pa.array for pa in pinned], total_rows, starts, lens, utts, None, n_utts, out=out)
         return (time.perf_counter() - t0) * 1e3
 
     # ---- device-resident leg -------------------------------------------------------
@@ -225,7 +246,6 @@ def main() -> None:
     dev_ms = [step_device() for _ in range(args.steps)]
     barrier()
     wall_ms = (time.perf_counter() - t_wall0) * 1e3
-    clocks = sampler.stop() if sampler else None
     launches = ex.launch_count() - launches0
     prof = {p["name"]: p for p in ex.profile()}
     emb_dev = out.copy()
@@ -239,6 +259,7 @@ def main() -> None:
     barrier()
     e2e_ms = [step_host() for _ in range(args.steps)]
     barrier()
+    clocks = sampler.stop() if sampler else None     # sampled over both timed regions
     assert np.array_equal(out, emb_dev), "host-input and device-input passes disagree"
     e2e_total_ms = reduce(float(sum(e2e_ms)), "max")
     e2e_value = total_audio / (e2e_total_ms / 1e3)
@@ -260,12 +281,11 @@ def main() -> None:
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.precision, "data": "synthetic",
-            "config": {"workload": "BASELINE configs[3]: egs/sre/v5 final c-vector at SRE16 scale, utterance-sharded "
-                                   f"({args.utts_per_gpu} utts of 10-300 s per GPU; 8 GPUs = the 10k-utt config)",
+            "config": {"workload": WORKLOAD_DESC, "workload_id": args.workload,
                        "topology": TOPOLOGY, "utts_per_gpu": args.utts_per_gpu, "frames_per_gpu": total_rows,
                        "chunk_size": CHUNK_SIZE, "min_chunk_size": MIN_CHUNK_SIZE, "parallelism": f"utterance-shards x{world} (LPT, no collective)",
                        "operands": f"{args.precision} operands, fp32 accumulate; pooling+tdnn6 fp32",
-                       "l2": "inputs larger than L2 (1.8 GB features, multi-GB activations per step)",
+                       "l2": f"inputs larger than L2 ({nbytes / 1e9:.2f} GB features, multi-GB activations per step)",
                        "mac_per_frame": int(info.mac_per_frame), "outputs_finite": finite},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(nbytes), "d2h_bytes_per_step": int(out.nbytes),
