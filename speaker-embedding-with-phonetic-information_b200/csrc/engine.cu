@@ -43,12 +43,15 @@ EncodeTiledFn GetEncodeTiled() {
 // 2-D map over a row-major [rows, ld] matrix of 2-byte elements, box = box_cols x box_rows,
 // 128-byte swizzle (box_cols * 2 bytes == 128), out-of-bounds reads give zeros.
 void Encode2D(CUtensorMap* map, int32_t elem, void* base, int64_t rows, int64_t ld, uint32_t box_cols,
-              uint32_t box_rows) {
-  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(ld), static_cast<cuuint64_t>(rows)};
-  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 2};
+              uint32_t box_rows, int64_t cols = -1) {
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols < 0 ? ld : cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * ElemSize(elem)};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = GetEncodeTiled()(map, elem == kBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+  const CUtensorMapDataType dt = elem == kBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                 : elem == kF32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                                : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUresult r = GetEncodeTiled()(map, dt, 2,
                                 base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -231,6 +234,44 @@ Engine::Engine(const Plan& plan, const cvx_engine_options& opts) : plan_(plan), 
       CVX_CUDA_CHECK(cudaMemcpy(s.d_scale, L.scale.data(), L.scale.size() * 4, cudaMemcpyHostToDevice));
       CVX_CUDA_CHECK(cudaMemcpy(s.d_offset, L.offset.data(), L.offset.size() * 4, cudaMemcpyHostToDevice));
     }
+    bool scale_ok = true;
+    for (float v : L.scale) scale_ok = scale_ok && (!L.relu || v > 0.f);
+    s.kp = RoundUp(L.in_dim, kGemmBlockK);
+    if (elem_ != kF32 && L.out_dim % 4 == 0 && scale_ok && 3 * (s.kp / kGemmBlockK) <= kMaxKBlocks) {
+      s.tensor = true;
+      s.n_pad = RoundUp(L.out_dim, 64);
+      const size_t kc = static_cast<size_t>(3) * s.kp;
+      std::vector<float> whi(static_cast<size_t>(s.n_pad) * kc, 0.f), wlo_src(static_cast<size_t>(s.n_pad) * s.kp, 0.f);
+      std::vector<float2> post(s.n_pad, make_float2(0.f, 0.f));
+      for (int32_t n = 0; n < L.out_dim; ++n) {
+        const float sc = L.scale.empty() ? 1.f : L.scale[n];
+        for (int32_t k = 0; k < L.in_dim; ++k) wlo_src[static_cast<size_t>(n) * s.kp + k] = L.weight[static_cast<size_t>(n) * L.in_dim + k] * sc;
+        post[n] = make_float2((L.bias.empty() ? 0.f : L.bias[n]) * sc, L.offset.empty() ? 0.f : L.offset[n]);
+      }
+      // Wh = round16(W), Wl = round16(W - Wh)
+      std::vector<uint8_t> h16(wlo_src.size() * 2), l16(wlo_src.size() * 2);
+      ConvertToElem(wlo_src.data(), wlo_src.size(), elem_, h16.data());
+      std::vector<float> resid(wlo_src.size());
+      for (size_t i = 0; i < resid.size(); ++i) resid[i] = wlo_src[i] - ElemToFloat(h16.data(), i, elem_);
+      ConvertToElem(resid.data(), resid.size(), elem_, l16.data());
+      std::vector<uint8_t> wcat(static_cast<size_t>(s.n_pad) * kc * 2);
+      for (int32_t n = 0; n < s.n_pad; ++n) {
+        uint8_t* row = wcat.data() + static_cast<size_t>(n) * kc * 2;
+        std::memcpy(row, h16.data() + static_cast<size_t>(n) * s.kp * 2, static_cast<size_t>(s.kp) * 2);
+        std::memcpy(row + static_cast<size_t>(s.kp) * 2, h16.data() + static_cast<size_t>(n) * s.kp * 2, static_cast<size_t>(s.kp) * 2);
+        std::memcpy(row + static_cast<size_t>(s.kp) * 4, l16.data() + static_cast<size_t>(n) * s.kp * 2, static_cast<size_t>(s.kp) * 2);
+      }
+      CVX_CUDA_CHECK(cudaMalloc(&s.d_wcat, wcat.size()));
+      CVX_CUDA_CHECK(cudaMemcpy(s.d_wcat, wcat.data(), wcat.size(), cudaMemcpyHostToDevice));
+      s.d_post = DevAlloc<float2>(post.size());
+      CVX_CUDA_CHECK(cudaMemcpy(s.d_post, post.data(), post.size() * sizeof(float2), cudaMemcpyHostToDevice));
+      const int32_t k_real = RoundUp(L.in_dim, 16);
+      for (int pass = 0; pass < 3; ++pass)
+        for (int32_t j = 0; j * kGemmBlockK < k_real; ++j)
+          s.kb.push_back({pass == 1 ? 1 : 0, j * kGemmBlockK, 0, std::min(kGemmBlockK, k_real - j * kGemmBlockK) / 16});
+      // every pass must cover the same kp/64 blocks so that W's column offset is kb*64
+      if (static_cast<int32_t>(s.kb.size()) != 3 * (s.kp / kGemmBlockK)) s.tensor = false;
+    }
     seg_ops_.push_back(s);
   }
 }
@@ -245,7 +286,11 @@ Engine::~Engine() {
     cudaFree(op.d_post);
   }
   for (Staging& s : stagings_) cudaFree(s.d_colmap);
+  cudaFree(d_seg_hi_);
+  cudaFree(d_seg_lo_);
   for (SegOp& s : seg_ops_) {
+    cudaFree(s.d_wcat);
+    cudaFree(s.d_post);
     cudaFree(s.d_w);
     cudaFree(s.d_b);
     cudaFree(s.d_scale);
@@ -630,6 +675,15 @@ void Engine::Extract(const float* const* feats, int32_t num_streams, int64_t tot
   int32_t max_seg = 0;
   for (size_t i = 0; i + 1 < seg_ops_.size(); ++i) max_seg = std::max(max_seg, seg_ops_[i].out_dim);
   for (int i = 0; i < 2; ++i) Grow(&d_seg_[i], &seg_cap_[i], static_cast<size_t>(seg_cap_chunks) * std::max(max_seg, 1) * 4);
+  int32_t max_kp = 0;
+  for (const SegOp& so : seg_ops_)
+    if (so.tensor) max_kp = std::max(max_kp, so.kp);
+  if (max_kp > 0) {
+    const int64_t split_rows = (seg_cap_chunks + 2 * kGemmBlockM - 1) / (2 * kGemmBlockM) * (2 * kGemmBlockM);
+    Grow(&d_seg_hi_, &seg_hi_cap_, static_cast<size_t>(split_rows) * max_kp * 2);
+    Grow(&d_seg_lo_, &seg_lo_cap_, static_cast<size_t>(split_rows) * max_kp * 2);
+    seg_split_rows_ = split_rows;
+  }
   Grow(&d_chunk_emb_, &chunk_emb_cap_, static_cast<size_t>(num_chunks) * E * 4);
   Grow(&d_out_, &out_cap_, static_cast<size_t>(num_utts) * E * 4);
   if (!dev_in)
@@ -704,8 +758,35 @@ void Engine::Extract(const float* const* feats, int32_t num_streams, int64_t tot
         float* dst = last ? emb : static_cast<float*>(d_seg_[si & 1]);
         const int32_t dst_ld = s.out_dim;
         ProfBegin(kProfSegment, 2.0 * pending * s.in_dim * s.out_dim, 0);
-        CVX_CUDA_CHECK(LaunchSegmentAffine(cur, cur_ld, pending, s.in_dim, s.d_w, s.d_b, s.relu ? 1 : 0, s.d_scale,
-                                           s.d_offset, s.out_dim, dst, dst_ld, compute_));
+        if (s.tensor) {
+          CVX_CUDA_CHECK(LaunchSplitF32(cur, cur_ld, pending, s.in_dim, d_seg_hi_, d_seg_lo_, s.kp, elem_, compute_));
+          TdnnGemmArgs a;
+          std::memset(&a, 0, sizeof(a));
+          Encode2D(&a.a_maps[0], elem_, d_seg_hi_, seg_split_rows_, s.kp, kGemmBlockK, kGemmBlockM);
+          Encode2D(&a.a_maps[1], elem_, d_seg_lo_, seg_split_rows_, s.kp, kGemmBlockK, kGemmBlockM);
+          a.a_maps[2] = a.a_maps[3] = a.a_maps[0];
+          a.b_box_rows = std::min(kGemmBlockN, s.n_pad);
+          a.b_box_rows_pair = std::min(kGemmBlockN / 2, s.n_pad);
+          Encode2D(&a.b_map, elem_, s.d_wcat, s.n_pad, 3 * s.kp, kGemmBlockK, a.b_box_rows);
+          Encode2D(&a.b_map_pair, elem_, s.d_wcat, s.n_pad, 3 * s.kp, kGemmBlockK, a.b_box_rows_pair);
+          // fp32 output; rows beyond `pending` and columns beyond out_dim are clipped by the map
+          Encode2D(&a.c_map, kF32, dst, pending, dst_ld, 32, 32, s.out_dim);
+          a.num_kb = static_cast<int32_t>(s.kb.size());
+          for (size_t i = 0; i < s.kb.size(); ++i) a.kb[i] = s.kb[i];
+          a.n_pad = s.n_pad;
+          a.n_mma = RoundUp(s.out_dim, 16);
+          a.num_m_tiles = static_cast<int32_t>((pending + kGemmBlockM - 1) / kGemmBlockM);
+          a.num_n_tiles = (a.n_mma + kGemmBlockN - 1) / kGemmBlockN;
+          a.post = s.d_post;
+          a.relu = s.relu ? 1 : 0;
+          a.ab_format = elem_ == kBF16 ? 1 : 0;
+          a.out_f32 = 1;
+          a.num_stages = 64;
+          CVX_CUDA_CHECK(LaunchTdnnGemmPair(a, num_sms_, compute_));
+        } else {
+          CVX_CUDA_CHECK(LaunchSegmentAffine(cur, cur_ld, pending, s.in_dim, s.d_w, s.d_b, s.relu ? 1 : 0, s.d_scale,
+                                             s.d_offset, s.out_dim, dst, dst_ld, compute_));
+        }
         ProfEnd();
         cur = dst;
         cur_ld = dst_ld;

@@ -85,6 +85,12 @@ class Engine {
     int32_t in_dim = 0, out_dim = 0;
     float *d_w = nullptr, *d_b = nullptr, *d_scale = nullptr, *d_offset = nullptr;
     bool relu = false;
+    // tensor-core path: x = hi + lo, W = Wh + Wl (16-bit splits), y = hi*Wh + lo*Wh + hi*Wl
+    bool tensor = false;
+    int32_t kp = 0, n_pad = 0;
+    void* d_wcat = nullptr;      // [n_pad, 3*kp] = [Wh | Wh | Wl]
+    float2* d_post = nullptr;    // [n_pad]
+    std::vector<KBlockDesc> kb;  // hi blocks, lo blocks, hi blocks
   };
   enum ProfClass { kProfStage = 0, kProfGemm, kProfPool, kProfPoolFin, kProfSegment, kProfAverage, kNumProf };
   struct PendingEvent {
@@ -128,6 +134,9 @@ class Engine {
   void *d_partials_ = nullptr, *d_stats_ = nullptr, *d_seg_[2] = {nullptr, nullptr}, *d_chunk_emb_ = nullptr,
        *d_out_ = nullptr;
   size_t partials_cap_ = 0, stats_cap_ = 0, seg_cap_[2] = {0, 0}, chunk_emb_cap_ = 0, out_cap_ = 0;
+  void *d_seg_hi_ = nullptr, *d_seg_lo_ = nullptr;  // 16-bit splits of a segment layer's fp32 input
+  size_t seg_hi_cap_ = 0, seg_lo_cap_ = 0;
+  int64_t seg_split_rows_ = 0;
   int64_t last_num_chunks_ = 0;
   cudaEvent_t call_begin_ = nullptr, call_end_ = nullptr;
   float last_call_ms_ = 0.f;

@@ -18,7 +18,7 @@ inline size_t ElemSize(int32_t e) { return e == kF32 ? 4 : 2; }
 constexpr int kGemmBlockM = 128;
 constexpr int kGemmBlockN = 256;
 constexpr int kGemmBlockK = 64;
-constexpr int kMaxKBlocks = 64;
+constexpr int kMaxKBlocks = 160;
 constexpr int kMaxASources = 4;
 
 struct KBlockDesc {
@@ -44,6 +44,8 @@ struct TdnnGemmArgs {
   const float2* post;     // [n_pad] {b', o}
   int32_t relu;
   int32_t ab_format;      // 0 = fp16, 1 = bf16 (UMMA F16F32Format)
+  int32_t out_f32;        // pair kernel only: write fp32 output (c_map is an fp32 map with 32-column boxes)
+  int32_t c_row0;         // row offset added to every output store (segment layers write into a slice)
   int32_t num_stages;     // smem ring depth actually used (<= the kernel's maximum; tuning aid)
 };
 
@@ -106,6 +108,10 @@ cudaError_t LaunchStatsPoolFinalize(const float* partials, int32_t ld, const Poo
                                     const int32_t* chunk_slab_off, int32_t num_chunks, int32_t dim,
                                     int32_t output_stddevs, float variance_floor, float* stats,
                                     int32_t ld_stats, cudaStream_t stream);
+
+// fp32 [m, k] -> fp16 hi / lo split (x = hi + lo to ~2^-22), pad columns [k, ld_out) zeroed
+cudaError_t LaunchSplitF32(const float* in, int32_t ld_in, int64_t m, int32_t k, void* hi, void* lo,
+                           int32_t ld_out, int32_t elem, cudaStream_t stream);
 
 // ---- K3: segment-level affine and per-utterance weighted average ----------
 cudaError_t LaunchSegmentAffine(const float* in, int32_t ld_in, int64_t m, int32_t k, const float* w,

@@ -10,8 +10,36 @@
 // its operands (pooled statistics) are kept in full precision.
 #include "kernels.h"
 
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include <type_traits>
+
 namespace cvx {
 namespace {
+
+// x -> (hi, lo) with hi = round16(x), lo = round16(x - hi): the tensor-core segment GEMM
+// computes hi*Wh + lo*Wh + hi*Wl, i.e. an fp32-accurate product from 16-bit operands.
+template <typename T>
+__global__ void __launch_bounds__(256) split_f32_kernel(const float* __restrict__ in, int ld_in, int64_t m, int k,
+                                                         T* __restrict__ hi, T* __restrict__ lo, int ld_out) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t row = idx / ld_out;
+  const int c = static_cast<int>(idx % ld_out);
+  if (row >= m) return;
+  float x = c < k ? in[row * ld_in + c] : 0.f;
+  T h, l;
+  if constexpr (sizeof(T) == 2 && std::is_same<T, __half>::value) {
+    x = fminf(fmaxf(x, -65504.f), 65504.f);
+    h = __float2half_rn(x);
+    l = __float2half_rn(x - __half2float(h));
+  } else {
+    h = __float2bfloat16_rn(x);
+    l = __float2bfloat16_rn(x - __bfloat162float(h));
+  }
+  hi[row * ld_out + c] = h;
+  lo[row * ld_out + c] = l;
+}
 
 constexpr int kTile = 64;
 constexpr int kTileK = 16;
@@ -85,6 +113,19 @@ __global__ void __launch_bounds__(128) utt_average_kernel(const float* __restric
 }
 
 }  // namespace
+
+cudaError_t LaunchSplitF32(const float* in, int32_t ld_in, int64_t m, int32_t k, void* hi, void* lo,
+                           int32_t ld_out, int32_t elem, cudaStream_t stream) {
+  if (m <= 0) return cudaSuccess;
+  const int64_t total = m * ld_out;
+  const unsigned grid = static_cast<unsigned>((total + 255) / 256);
+  if (elem == kF16)
+    split_f32_kernel<__half><<<grid, 256, 0, stream>>>(in, ld_in, m, k, static_cast<__half*>(hi), static_cast<__half*>(lo), ld_out);
+  else
+    split_f32_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(in, ld_in, m, k, static_cast<__nv_bfloat16*>(hi),
+                                                              static_cast<__nv_bfloat16*>(lo), ld_out);
+  return cudaGetLastError();
+}
 
 cudaError_t LaunchSegmentAffine(const float* in, int32_t ld_in, int64_t m, int32_t k, const float* w,
                                 const float* bias, int32_t relu, const float* scale, const float* offset,

@@ -53,7 +53,9 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   }
 }
 
-template <bool kBF16>
+// kOutF32: the epilogue writes fp32 (32-column chunks) instead of the operand type -- used for
+// the segment-level layers, whose fp32 inputs/weights are fed as fp16 hi/lo splits.
+template <bool kBF16, bool kOutF32>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     tdnn_gemm_pair_kernel(const __grid_constant__ TdnnGemmArgs args) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -180,7 +182,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
       const int m0 = (tile / num_n_tiles) * (2 * kGemmBlockM) + static_cast<int>(rank) * kGemmBlockM;
       const int n0 = (tile % num_n_tiles) * kGemmBlockN;
-      const int n_chunks = (min(kGemmBlockN, args.n_mma - n0) + 63) >> 6;
+      constexpr int kChunkCols = kOutF32 ? 32 : 64;  // 128 bytes of output per row and chunk
+      const int n_chunks = (min(kGemmBlockN, args.n_mma - n0) + kChunkCols - 1) / kChunkCols;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
 
@@ -196,34 +199,58 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       for (int c = half; c < n_chunks; c += 2) {
         if (ptx::elect_one_sync()) ptx::tma_store_wait_read<0>();  // this warp's previous store is done with `buf`
         __syncwarp();
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        if constexpr (kOutF32) {
           uint32_t r[32];
-          ptx::tmem_ld_32x32b_x32(t_row + c * 64 + h * 32, r);
+          ptx::tmem_ld_32x32b_x32(t_row + c * 32, r);
           ptx::tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            uint32_t pk[4];
+          for (int j = 0; j < 32; j += 4) {
+            float v[4];
 #pragma unroll
-            for (int e = 0; e < 8; e += 2) {
-              const float4 p = *reinterpret_cast<const float4*>(&smem_post[c * 64 + h * 32 + j + e]);
-              float v0 = __uint_as_float(r[j + e]) + p.x;
-              float v1 = __uint_as_float(r[j + e + 1]) + p.z;
+            for (int e = 0; e < 4; e += 2) {
+              const float4 p = *reinterpret_cast<const float4*>(&smem_post[c * 32 + j + e]);
+              v[e] = __uint_as_float(r[j + e]) + p.x;
+              v[e + 1] = __uint_as_float(r[j + e + 1]) + p.z;
               if (args.relu) {
-                v0 = fmaxf(v0, 0.f);
-                v1 = fmaxf(v1, 0.f);
+                v[e] = fmaxf(v[e], 0.f);
+                v[e + 1] = fmaxf(v[e + 1], 0.f);
               }
-              pk[e >> 1] = pack2<kBF16>(v0 + p.y, v1 + p.w);
+              v[e] += p.y;
+              v[e + 1] += p.w;
             }
-            const int unit = h * 4 + (j >> 3);  // 16-byte unit inside the 128-byte row
-            *reinterpret_cast<uint4*>(buf + lane * 128 + ((unit ^ (lane & 7)) << 4)) =
-                make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            const int unit = j >> 2;  // 16-byte unit (4 floats) inside the 128-byte row
+            *reinterpret_cast<float4*>(buf + lane * 128 + ((unit ^ (lane & 7)) << 4)) = make_float4(v[0], v[1], v[2], v[3]);
+          }
+        } else {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint32_t r[32];
+            ptx::tmem_ld_32x32b_x32(t_row + c * 64 + h * 32, r);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint32_t pk[4];
+#pragma unroll
+              for (int e = 0; e < 8; e += 2) {
+                const float4 p = *reinterpret_cast<const float4*>(&smem_post[c * 64 + h * 32 + j + e]);
+                float v0 = __uint_as_float(r[j + e]) + p.x;
+                float v1 = __uint_as_float(r[j + e + 1]) + p.z;
+                if (args.relu) {
+                  v0 = fmaxf(v0, 0.f);
+                  v1 = fmaxf(v1, 0.f);
+                }
+                pk[e >> 1] = pack2<kBF16>(v0 + p.y, v1 + p.w);
+              }
+              const int unit = h * 4 + (j >> 3);  // 16-byte unit inside the 128-byte row
+              *reinterpret_cast<uint4*>(buf + lane * 128 + ((unit ^ (lane & 7)) << 4)) =
+                  make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
           }
         }
         ptx::fence_proxy_async_smem();
         __syncwarp();
         if (ptx::elect_one_sync()) {
-          ptx::tma_store_2d(&args.c_map, buf, n0 + c * 64, m0 + q * 32);
+          ptx::tma_store_2d(&args.c_map, buf, n0 + c * kChunkCols, args.c_row0 + m0 + q * 32);
           ptx::tma_store_commit();
         }
       }
@@ -246,7 +273,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 
 cudaError_t LaunchTdnnGemmPair(const TdnnGemmArgs& args, int num_sms, cudaStream_t stream) {
   const bool bf16 = args.ab_format == 1;
-  auto kern = bf16 ? tdnn_gemm_pair_kernel<true> : tdnn_gemm_pair_kernel<false>;
+  auto kern = args.out_f32 ? (bf16 ? tdnn_gemm_pair_kernel<true, true> : tdnn_gemm_pair_kernel<false, true>)
+                           : (bf16 ? tdnn_gemm_pair_kernel<true, false> : tdnn_gemm_pair_kernel<false, false>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
   if (e != cudaSuccess) return e;
   const int tiles = ((args.num_m_tiles + 1) / 2) * args.num_n_tiles;
