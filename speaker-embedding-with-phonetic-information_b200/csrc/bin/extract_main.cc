@@ -284,6 +284,15 @@ int ExtractMain(int argc, const char* const* argv, bool multiple_input) {
     };
 
     int cur = 0;
+    if (num_inputs == 1 && !pad_input) {
+      // binary float matrices are read straight into the pinned batch at its tail
+      readers[0]->Value().placer = [&](int32_t rows, int32_t cols) -> float* {
+        HostBatch& b = hb[cur];
+        if (cols != b.dims[0]) return nullptr;
+        b.Reserve(b.rows + rows + std::max(min_chunk_size, 0));
+        return b.feats[0] + static_cast<size_t>(b.rows) * b.dims[0];
+      };
+    }
     std::vector<const Matrix*> mats(num_inputs);
     std::vector<const float*> row_ptrs(num_inputs);
     for (; !readers[0]->Done(); ) {
@@ -322,6 +331,17 @@ int ExtractMain(int argc, const char* const* argv, bool multiple_input) {
         const int32_t utt_index = static_cast<int32_t>(b.keys.size());
         const size_t chunks_before = b.chunk_start.size();
         const int64_t rows_before = b.rows;
+        // Fast path (no replicated rows needed): the utterance's rows go into the batch as one
+        // block -- or are already there when the reader placed them (single stream).
+        const bool tail_needs_pad = pad_input && (T - (num_chunks - 1) * this_chunk) < min_chunk_size;
+        bool block_copied = false;
+        if (!tail_needs_pad) {
+          for (int s = 0; s < num_inputs; ++s) {
+            float* dst = b.feats[s] + static_cast<size_t>(b.rows) * b.dims[s];
+            if (mats[s]->Data() != dst) std::memcpy(dst, mats[s]->Data(), static_cast<size_t>(T) * b.dims[s] * sizeof(float));
+          }
+          block_copied = true;
+        }
         for (int32_t ci = 0; ci < num_chunks; ++ci) {
           const int32_t begin = ci * this_chunk;
           const int32_t offset = std::min(this_chunk, T - begin);
@@ -341,13 +361,17 @@ int ExtractMain(int argc, const char* const* argv, bool multiple_input) {
             use = false;
           }
           const int64_t start = b.rows;
-          auto put = [&](int32_t r) {
-            for (int s = 0; s < num_inputs; ++s) row_ptrs[s] = mats[s]->Row(r);
-            b.AppendRow(row_ptrs);
-          };
-          for (int32_t k = 0; k < left_pad; ++k) put(begin);
-          for (int32_t r = begin; r < begin + offset; ++r) put(r);
-          for (int32_t k = 0; k < right_pad; ++k) put(begin + offset - 1);
+          if (block_copied) {
+            b.rows += offset;
+          } else {
+            auto put = [&](int32_t r) {
+              for (int s = 0; s < num_inputs; ++s) row_ptrs[s] = mats[s]->Row(r);
+              b.AppendRow(row_ptrs);
+            };
+            for (int32_t k = 0; k < left_pad; ++k) put(begin);
+            for (int32_t r = begin; r < begin + offset; ++r) put(r);
+            for (int32_t k = 0; k < right_pad; ++k) put(begin + offset - 1);
+          }
           if (use) {
             b.chunk_start.push_back(start);
             b.chunk_len.push_back(rows_here);

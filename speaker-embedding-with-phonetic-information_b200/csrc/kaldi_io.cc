@@ -114,6 +114,14 @@ int Input::Get() {
 void Input::Read(void* dst, size_t n) {
   unsigned char* d = static_cast<unsigned char*>(dst);
   while (n) {
+    if (pos_ >= end_ && n >= buf_.size() && fp_) {
+      // large body: read straight into the destination, bypassing the buffer
+      size_t got = std::fread(d, 1, n, fp_);
+      if (got == 0) throw KaldiError("unexpected end of input in " + name_);
+      d += got;
+      n -= got;
+      continue;
+    }
     if (pos_ >= end_ && !Fill()) throw KaldiError("unexpected end of input in " + name_);
     size_t k = std::min(n, end_ - pos_);
     std::memcpy(d, buf_.data() + pos_, k);
@@ -361,6 +369,7 @@ static void ReadCompressed(Input& in, const std::string& tag, Matrix* m) {
 }
 
 void ReadVectorOrMatrix(Input& in, bool binary, Matrix* m, bool* was_vector) {
+  m->ext = nullptr;
   if (!binary) {
     ReadTextMatrix(in, m);
     if (was_vector) *was_vector = (m->rows <= 1);
@@ -390,6 +399,12 @@ void ReadVectorOrMatrix(Input& in, bool binary, Matrix* m, bool* was_vector) {
     m->rows = rows;
     m->cols = cols;
     const size_t n = static_cast<size_t>(rows) * cols;
+    m->ext = (tag == "FM" && m->placer) ? m->placer(rows, cols) : nullptr;
+    if (m->ext) {
+      m->data.clear();
+      in.Read(m->ext, n * 4);
+      return;
+    }
     m->data.resize(n);
     if (tag == "FM") {
       in.Read(m->data.data(), n * 4);

@@ -13,6 +13,7 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <functional>
 #include <map>
 #include <memory>
 #include <stdexcept>
@@ -111,9 +112,15 @@ bool ReadBool(Input& in, bool binary);
 
 struct Matrix {
   int32_t rows = 0, cols = 0;
-  std::vector<float> data;  // row-major
-  float* Row(int32_t r) { return data.data() + static_cast<size_t>(r) * cols; }
-  const float* Row(int32_t r) const { return data.data() + static_cast<size_t>(r) * cols; }
+  std::vector<float> data;  // row-major (unless `ext` is set)
+  // Optional placement: called with (rows, cols) of an uncompressed binary float matrix before
+  // its body is read; a non-null result receives the data directly (e.g. the tail of a pinned
+  // staging buffer) and `ext` points at it.
+  std::function<float*(int32_t, int32_t)> placer;
+  float* ext = nullptr;
+  const float* Data() const { return ext ? ext : data.data(); }
+  float* Row(int32_t r) { return (ext ? ext : data.data()) + static_cast<size_t>(r) * cols; }
+  const float* Row(int32_t r) const { return Data() + static_cast<size_t>(r) * cols; }
 };
 
 // After an optional binary header: FM/DM/CM/CM2/CM3 (binary) or "[ ... ]" (text).
