@@ -166,6 +166,36 @@ int cvx_extract(cvx_engine* engine, const float* const* feats, int32_t num_strea
                 const int32_t* chunk_utt, const float* chunk_weight, int64_t num_chunks,
                 int32_t num_utts, float* out, uint32_t flags);
 
+/* ----------------------------------------------------- feature pre-step --
+ * Optional: the step immediately before the hot path in the reference's feature pipe
+ * (extract_xvectors_new.sh:79), done on the device instead of by two extra processes:
+ *   apply-cmvn-sliding --norm-vars=false --center=true --cmn-window=300   (per stream)
+ *   select-voiced-frames ... vad.scp                                      (same frames for every stream)
+ */
+typedef struct cvx_prestep {
+  int32_t cmn_window;     /* 0: no sliding CMN for this stream */
+  int32_t cmn_center;     /* --center */
+  int32_t min_cmn_window; /* --min-cmn-window (only used when center = 0) */
+  int32_t norm_vars;      /* must be 0 */
+} cvx_prestep;
+
+/* cvx_extract on RAW features: raw_feats[s] [total_raw_rows, dim(s)] fp32 host rows of all
+ * utterances; utterance u owns raw rows [utt_raw_start[u], utt_raw_start[u+1]); keep[] lists, per
+ * utterance and in increasing order, the frame indices (inside the utterance) that survive VAD
+ * selection -- kept rows of utterance u are [utt_kept_start[u], utt_kept_start[u+1]) of the
+ * selected matrix (keep == NULL: keep every frame).  prestep[s] configures stream s.  Chunk arrays
+ * are in selected-row coordinates, exactly as for cvx_extract. */
+int cvx_extract_raw(cvx_engine* engine, const float* const* raw_feats, const cvx_prestep* prestep,
+                    int32_t num_streams, int64_t total_raw_rows, const int64_t* utt_raw_start,
+                    const int32_t* keep, const int64_t* utt_kept_start, int32_t num_utts,
+                    const int64_t* chunk_start, const int32_t* chunk_len, const int32_t* chunk_utt,
+                    const float* chunk_weight, int64_t num_chunks, float* out, uint32_t flags);
+
+/* Test entry: the pre-step alone on one stream; out = [total_kept, dim] fp32 host. */
+int cvx_test_prestep(cvx_engine* engine, const float* raw, int32_t dim, const cvx_prestep* prestep,
+                     int64_t total_raw_rows, const int64_t* utt_raw_start, const int32_t* keep,
+                     const int64_t* utt_kept_start, int32_t num_utts, float* out);
+
 /* Per-chunk embeddings of the last cvx_extract call (before averaging),
  * [num_chunks, embedding_dim] copied to host memory. */
 int cvx_engine_last_chunk_embeddings(cvx_engine* engine, float* out, int64_t num_chunks);

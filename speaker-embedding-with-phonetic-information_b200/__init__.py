@@ -54,7 +54,7 @@ ABI_SYMBOLS = [
     "cvx_last_error", "cvx_version", "cvx_model_load", "cvx_model_from_plan", "cvx_model_free",
     "cvx_model_get_info", "cvx_model_input_name", "cvx_model_input_dim", "cvx_model_describe",
     "cvx_engine_options_default", "cvx_engine_create", "cvx_engine_destroy", "cvx_extract",
-    "cvx_engine_last_chunk_embeddings", "cvx_host_alloc", "cvx_host_free", "cvx_device_alloc",
+    "cvx_engine_last_chunk_embeddings", "cvx_extract_raw", "cvx_test_prestep", "cvx_host_alloc", "cvx_host_free", "cvx_device_alloc",
     "cvx_device_free", "cvx_memcpy_h2d", "cvx_device_count", "cvx_engine_get_profile",
     "cvx_engine_reset_profile", "cvx_engine_launch_count", "cvx_engine_last_extract_ms", "cvx_test_tdnn_layer", "cvx_test_tdnn_layer_bench", "cvx_test_stats_pool",
 ]

@@ -240,6 +240,8 @@ int ExtractMain(int argc, const char* const* argv, bool multiple_input) {
       b.cap_rows.assign(num_inputs, 0);
       b.dims.resize(num_inputs);
       for (int s = 0; s < num_inputs; ++s) b.dims[s] = cvx_model_input_dim(model, s);
+      // pin the whole batch up front: growing pinned memory step by step costs more than the I/O
+      b.Reserve(batch_rows + batch_rows / 8 + 65536);
     }
     const int32_t E = info.embedding_dim;
     const int32_t ctx = info.left_context + info.right_context + 1;

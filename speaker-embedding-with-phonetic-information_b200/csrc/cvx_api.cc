@@ -176,6 +176,28 @@ int cvx_extract(cvx_engine* engine, const float* const* feats, int32_t num_strea
   });
 }
 
+int cvx_extract_raw(cvx_engine* engine, const float* const* raw_feats, const cvx_prestep* prestep, int32_t num_streams,
+                    int64_t total_raw_rows, const int64_t* utt_raw_start, const int32_t* keep,
+                    const int64_t* utt_kept_start, int32_t num_utts, const int64_t* chunk_start,
+                    const int32_t* chunk_len, const int32_t* chunk_utt, const float* chunk_weight, int64_t num_chunks,
+                    float* out, uint32_t flags) {
+  if (!engine) return Fail(CVX_ERR_INVALID, "cvx_extract_raw: NULL engine");
+  if (num_chunks > 0 && (!chunk_start || !chunk_len || !chunk_utt)) return Fail(CVX_ERR_INVALID, "cvx_extract_raw: NULL chunk arrays");
+  return Guard([&] {
+    engine->impl->ExtractRaw(raw_feats, prestep, num_streams, total_raw_rows, utt_raw_start, keep, utt_kept_start,
+                             num_utts, chunk_start, chunk_len, chunk_utt, chunk_weight, num_chunks, out, flags);
+  });
+}
+
+int cvx_test_prestep(cvx_engine* engine, const float* raw, int32_t dim, const cvx_prestep* prestep,
+                     int64_t total_raw_rows, const int64_t* utt_raw_start, const int32_t* keep,
+                     const int64_t* utt_kept_start, int32_t num_utts, float* out) {
+  if (!engine || !raw || !prestep || !out) return Fail(CVX_ERR_INVALID, "cvx_test_prestep: NULL argument");
+  return Guard([&] {
+    engine->impl->DebugPrestep(raw, dim, *prestep, total_raw_rows, utt_raw_start, keep, utt_kept_start, num_utts, out);
+  });
+}
+
 int cvx_engine_last_chunk_embeddings(cvx_engine* engine, float* out, int64_t num_chunks) {
   if (!engine || !out) return Fail(CVX_ERR_INVALID, "cvx_engine_last_chunk_embeddings: NULL argument");
   return Guard([&] { engine->impl->LastChunkEmbeddings(out, num_chunks); });

@@ -18,6 +18,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <climits>
 #include <cstdlib>
 #include <cstring>
 
@@ -286,6 +287,12 @@ Engine::~Engine() {
     cudaFree(op.d_post);
   }
   for (Staging& s : stagings_) cudaFree(s.d_colmap);
+  for (int s = 0; s < kMaxASources; ++s) {
+    cudaFree(d_raw_[s]);
+    cudaFree(d_sel_[s]);
+  }
+  void* pre_scratch[] = {d_prefix_, d_pre_utt_start_, d_pre_kept_utt_, d_pre_keep_};
+  for (void* p : pre_scratch) cudaFree(p);
   cudaFree(d_seg_hi_);
   cudaFree(d_seg_lo_);
   for (SegOp& s : seg_ops_) {
@@ -807,6 +814,115 @@ void Engine::Extract(const float* const* feats, int32_t num_streams, int64_t tot
   CVX_CUDA_CHECK(cudaEventElapsedTime(&last_call_ms_, call_begin_, call_end_));
   ProfResolve();
   last_num_chunks_ = num_chunks;
+}
+
+// ------------------------------------------------------------ pre-step ----
+void Engine::RunPrestep(int32_t s, int32_t dim, const float* host_raw, const cvx_prestep& pre, int64_t total_raw_rows,
+                        const int64_t* utt_raw_start, const int32_t* keep, const int64_t* utt_kept_start,
+                        int32_t num_utts) {
+  if (pre.norm_vars) throw InvalidArgument("sliding CMN with --norm-vars=true is not on this path (the recipes use false)");
+  if (pre.cmn_window < 0) throw InvalidArgument("negative cmn_window");
+  const int64_t total_kept = utt_kept_start[num_utts];
+  Grow(&d_raw_[s], &raw_cap_[s], static_cast<size_t>(total_raw_rows) * dim * 4);
+  Grow(&d_sel_[s], &sel_cap_[s], static_cast<size_t>(std::max<int64_t>(total_kept, 1)) * dim * 4);
+  CVX_CUDA_CHECK(cudaMemcpyAsync(d_raw_[s], host_raw, static_cast<size_t>(total_raw_rows) * dim * 4, cudaMemcpyHostToDevice,
+                                 compute_));
+  if (pre.cmn_window > 0) {
+    Grow(&d_prefix_, &prefix_cap_, static_cast<size_t>(total_raw_rows + num_utts) * dim * 8);
+    ProfBegin(kProfStage, 0, static_cast<double>(total_raw_rows) * dim * 12.0);
+    CVX_CUDA_CHECK(LaunchCmnPrefix(static_cast<const float*>(d_raw_[s]), dim, static_cast<const int64_t*>(d_pre_utt_start_),
+                                   num_utts, static_cast<double*>(d_prefix_), compute_));
+    ProfEnd();
+  }
+  ProfBegin(kProfStage, 0, static_cast<double>(total_kept) * dim * (pre.cmn_window > 0 ? 24.0 : 8.0));
+  CVX_CUDA_CHECK(LaunchCmnSelect(static_cast<const float*>(d_raw_[s]), dim, static_cast<const int64_t*>(d_pre_utt_start_),
+                                 static_cast<const int32_t*>(d_pre_kept_utt_), keep ? static_cast<const int32_t*>(d_pre_keep_) : nullptr,
+                                 total_kept, static_cast<const double*>(d_prefix_), pre.cmn_window, pre.cmn_center,
+                                 pre.min_cmn_window, static_cast<float*>(d_sel_[s]), compute_));
+  ProfEnd();
+}
+
+static void CheckPrestepIndex(int64_t total_raw_rows, const int64_t* utt_raw_start, const int32_t* keep,
+                              const int64_t* utt_kept_start, int32_t num_utts, std::vector<int32_t>* kept_utt) {
+  if (num_utts < 0 || !utt_raw_start || !utt_kept_start) throw InvalidArgument("pre-step: NULL utterance offsets");
+  if (utt_raw_start[0] != 0 || utt_kept_start[0] != 0 || utt_raw_start[num_utts] != total_raw_rows)
+    throw InvalidArgument("pre-step: utterance offsets must start at 0 and end at the row count");
+  kept_utt->clear();
+  kept_utt->reserve(static_cast<size_t>(utt_kept_start[num_utts]));
+  for (int32_t u = 0; u < num_utts; ++u) {
+    const int64_t T = utt_raw_start[u + 1] - utt_raw_start[u], K = utt_kept_start[u + 1] - utt_kept_start[u];
+    if (T < 0 || K < 0 || K > T || T > INT32_MAX) throw InvalidArgument("pre-step: bad offsets for utterance " + std::to_string(u));
+    if (!keep && K != T) throw InvalidArgument("pre-step: keep == NULL requires kept == raw row counts");
+    int32_t prev = -1;
+    for (int64_t j = utt_kept_start[u]; j < utt_kept_start[u + 1]; ++j) {
+      if (keep) {
+        if (keep[j] <= prev || keep[j] >= T) throw InvalidArgument("pre-step: keep[] must be increasing frame indices inside the utterance");
+        prev = keep[j];
+      }
+      kept_utt->push_back(u);
+    }
+  }
+}
+
+void Engine::ExtractRaw(const float* const* raw, const cvx_prestep* pre, int32_t num_streams, int64_t total_raw_rows,
+                        const int64_t* utt_raw_start, const int32_t* keep, const int64_t* utt_kept_start, int32_t num_utts,
+                        const int64_t* chunk_start, const int32_t* chunk_len, const int32_t* chunk_utt,
+                        const float* chunk_weight, int64_t num_chunks, float* out, uint32_t flags) {
+  CVX_CUDA_CHECK(cudaSetDevice(opts_.device));
+  if (flags & CVX_FLAG_DEVICE_INPUT) throw InvalidArgument("cvx_extract_raw takes host features");
+  if (num_streams != static_cast<int32_t>(plan_.input_dims.size())) throw InvalidArgument("wrong number of input streams");
+  if (!raw || !pre) throw InvalidArgument("pre-step: NULL argument");
+  std::vector<int32_t> kept_utt;
+  CheckPrestepIndex(total_raw_rows, utt_raw_start, keep, utt_kept_start, num_utts, &kept_utt);
+  const int64_t total_kept = utt_kept_start[num_utts];
+  Grow(&d_pre_utt_start_, &pre_utt_start_cap_, static_cast<size_t>(num_utts + 1) * 8);
+  Grow(&d_pre_kept_utt_, &pre_kept_utt_cap_, std::max<size_t>(kept_utt.size(), 1) * 4);
+  CVX_CUDA_CHECK(cudaMemcpyAsync(d_pre_utt_start_, utt_raw_start, static_cast<size_t>(num_utts + 1) * 8, cudaMemcpyHostToDevice, compute_));
+  CVX_CUDA_CHECK(cudaMemcpyAsync(d_pre_kept_utt_, kept_utt.data(), kept_utt.size() * 4, cudaMemcpyHostToDevice, compute_));
+  if (keep) {
+    Grow(&d_pre_keep_, &pre_keep_cap_, std::max<size_t>(static_cast<size_t>(total_kept), 1) * 4);
+    CVX_CUDA_CHECK(cudaMemcpyAsync(d_pre_keep_, keep, static_cast<size_t>(total_kept) * 4, cudaMemcpyHostToDevice, compute_));
+  }
+  // all Grow()s first: they synchronise and may free buffers earlier kernels of this call read
+  for (int32_t s = 0; s < num_streams; ++s) {
+    Grow(&d_raw_[s], &raw_cap_[s], static_cast<size_t>(total_raw_rows) * plan_.input_dims[s] * 4);
+    Grow(&d_sel_[s], &sel_cap_[s], static_cast<size_t>(std::max<int64_t>(total_kept, 1)) * plan_.input_dims[s] * 4);
+    if (pre[s].cmn_window > 0)
+      Grow(&d_prefix_, &prefix_cap_, static_cast<size_t>(total_raw_rows + num_utts) * plan_.input_dims[s] * 8);
+  }
+  const float* sel[kMaxASources] = {};
+  for (int32_t s = 0; s < num_streams; ++s) {
+    if (!raw[s]) throw InvalidArgument("pre-step: NULL feature stream");
+    RunPrestep(s, plan_.input_dims[s], raw[s], pre[s], total_raw_rows, utt_raw_start, keep, utt_kept_start, num_utts);
+    sel[s] = static_cast<const float*>(d_sel_[s]);
+  }
+  CVX_CUDA_CHECK(cudaStreamSynchronize(compute_));  // kept_utt (host vector) has been consumed
+  Extract(sel, num_streams, total_kept, chunk_start, chunk_len, chunk_utt, chunk_weight, num_chunks, num_utts, out,
+          flags | CVX_FLAG_DEVICE_INPUT);
+}
+
+void Engine::DebugPrestep(const float* raw, int32_t dim, const cvx_prestep& pre, int64_t total_raw_rows,
+                          const int64_t* utt_raw_start, const int32_t* keep, const int64_t* utt_kept_start,
+                          int32_t num_utts, float* out) {
+  CVX_CUDA_CHECK(cudaSetDevice(opts_.device));
+  std::vector<int32_t> kept_utt;
+  CheckPrestepIndex(total_raw_rows, utt_raw_start, keep, utt_kept_start, num_utts, &kept_utt);
+  const int64_t total_kept = utt_kept_start[num_utts];
+  Grow(&d_pre_utt_start_, &pre_utt_start_cap_, static_cast<size_t>(num_utts + 1) * 8);
+  Grow(&d_pre_kept_utt_, &pre_kept_utt_cap_, std::max<size_t>(kept_utt.size(), 1) * 4);
+  CVX_CUDA_CHECK(cudaMemcpyAsync(d_pre_utt_start_, utt_raw_start, static_cast<size_t>(num_utts + 1) * 8, cudaMemcpyHostToDevice, compute_));
+  CVX_CUDA_CHECK(cudaMemcpyAsync(d_pre_kept_utt_, kept_utt.data(), kept_utt.size() * 4, cudaMemcpyHostToDevice, compute_));
+  if (keep) {
+    Grow(&d_pre_keep_, &pre_keep_cap_, std::max<size_t>(static_cast<size_t>(total_kept), 1) * 4);
+    CVX_CUDA_CHECK(cudaMemcpyAsync(d_pre_keep_, keep, static_cast<size_t>(total_kept) * 4, cudaMemcpyHostToDevice, compute_));
+  }
+  Grow(&d_raw_[0], &raw_cap_[0], static_cast<size_t>(total_raw_rows) * dim * 4);
+  Grow(&d_sel_[0], &sel_cap_[0], static_cast<size_t>(std::max<int64_t>(total_kept, 1)) * dim * 4);
+  if (pre.cmn_window > 0) Grow(&d_prefix_, &prefix_cap_, static_cast<size_t>(total_raw_rows + num_utts) * dim * 8);
+  RunPrestep(0, dim, raw, pre, total_raw_rows, utt_raw_start, keep, utt_kept_start, num_utts);
+  CVX_CUDA_CHECK(cudaMemcpyAsync(out, d_sel_[0], static_cast<size_t>(total_kept) * dim * 4, cudaMemcpyDeviceToHost, compute_));
+  CVX_CUDA_CHECK(cudaStreamSynchronize(compute_));
+  ProfResolve();
 }
 
 void Engine::LastChunkEmbeddings(float* out, int64_t num_chunks) {

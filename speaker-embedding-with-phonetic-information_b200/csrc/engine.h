@@ -47,6 +47,15 @@ class Engine {
                const int32_t* chunk_len, const int32_t* chunk_utt, const float* chunk_weight, int64_t num_chunks,
                int32_t num_utts, float* out, uint32_t flags);
   void LastChunkEmbeddings(float* out, int64_t num_chunks);
+  // Extract() preceded by the device pre-step (sliding CMN + frame selection) on raw features.
+  void ExtractRaw(const float* const* raw, const cvx_prestep* pre, int32_t num_streams, int64_t total_raw_rows,
+                  const int64_t* utt_raw_start, const int32_t* keep, const int64_t* utt_kept_start, int32_t num_utts,
+                  const int64_t* chunk_start, const int32_t* chunk_len, const int32_t* chunk_utt,
+                  const float* chunk_weight, int64_t num_chunks, float* out, uint32_t flags);
+  // Test hook: the pre-step alone; `out` receives the selected, normalised rows of stream 0.
+  void DebugPrestep(const float* raw, int32_t dim, const cvx_prestep& pre, int64_t total_raw_rows,
+                    const int64_t* utt_raw_start, const int32_t* keep, const int64_t* utt_kept_start, int32_t num_utts,
+                    float* out);
   // Test hook: run only the frame layers on `rows` packed rows and return the last
   // frame layer's activations as fp32 [rows, out_dim].
   void DebugForwardFrames(const float* const* feats, int64_t rows, float* out);
@@ -138,6 +147,12 @@ class Engine {
   size_t seg_hi_cap_ = 0, seg_lo_cap_ = 0;
   int64_t seg_split_rows_ = 0;
   int64_t last_num_chunks_ = 0;
+  void RunPrestep(int32_t s, int32_t dim, const float* host_raw, const cvx_prestep& pre, int64_t total_raw_rows,
+                  const int64_t* utt_raw_start, const int32_t* keep, const int64_t* utt_kept_start, int32_t num_utts);
+  void *d_raw_[kMaxASources] = {}, *d_sel_[kMaxASources] = {};
+  size_t raw_cap_[kMaxASources] = {}, sel_cap_[kMaxASources] = {};
+  void *d_prefix_ = nullptr, *d_pre_utt_start_ = nullptr, *d_pre_kept_utt_ = nullptr, *d_pre_keep_ = nullptr;
+  size_t prefix_cap_ = 0, pre_utt_start_cap_ = 0, pre_kept_utt_cap_ = 0, pre_keep_cap_ = 0;
   cudaEvent_t call_begin_ = nullptr, call_end_ = nullptr;
   float last_call_ms_ = 0.f;
 

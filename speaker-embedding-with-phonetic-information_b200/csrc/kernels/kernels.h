@@ -120,5 +120,14 @@ cudaError_t LaunchSegmentAffine(const float* in, int32_t ld_in, int64_t m, int32
 cudaError_t LaunchUttAverage(const float* chunk_emb, int32_t dim, const int64_t* utt_chunk_off,
                              const float* chunk_weight, int32_t num_utts, float* out, cudaStream_t stream);
 
+// ---- feature pre-step: sliding-window CMN + voiced-frame selection (prestep.cu) ----
+// prefix: double [(total_raw_rows + num_utts), dim]; utterance u owns T_u + 1 rows from utt_start[u] + u
+cudaError_t LaunchCmnPrefix(const float* x, int32_t dim, const int64_t* utt_start, int32_t num_utts, double* prefix,
+                            cudaStream_t stream);
+// out[j] = x[frame keep[j] of utterance kept_utt[j]] - window mean (cmn_window == 0: plain selection)
+cudaError_t LaunchCmnSelect(const float* x, int32_t dim, const int64_t* utt_start, const int32_t* kept_utt,
+                            const int32_t* keep, int64_t total_kept, const double* prefix, int32_t cmn_window,
+                            int32_t center, int32_t min_window, float* out, cudaStream_t stream);
+
 }  // namespace cvx
 #endif  // CVX_KERNELS_KERNELS_H_

@@ -1,0 +1,62 @@
+"""Device feature pre-step (sliding CMN + VAD selection) against its oracle, alone and
+fused in front of the extraction."""
+import importlib
+
+import numpy as np
+import pytest
+
+from conftest import PKG
+
+pytestmark = pytest.mark.gpu
+
+
+def _data(lengths, dim, seed, voiced_p=0.7):
+    rng = np.random.default_rng(seed)
+    x = (rng.standard_normal((sum(lengths), dim)) * 3 + rng.standard_normal(dim) * 10).astype(np.float32)
+    vad = [(rng.random(T) < voiced_p).astype(np.float32) for T in lengths]
+    return x, vad
+
+
+@pytest.mark.parametrize("center,window", [(True, 300), (False, 300), (True, 7), (True, 0)])
+def test_prestep_matches_oracle(cvx, model_dir, require_gpu, center, window):
+    from oracle.prestep_oracle import select_voiced, sliding_cmn
+    ps = importlib.import_module(PKG + ".prestep")
+    path, _ = model_dir("tiny")
+    ex = cvx.Extractor(cvx.Model(path, "tdnn6.affine"), precision="fp32")
+    lengths = [1, 5, 149, 150, 299, 300, 301, 1000, 37]          # around the window / half-window edges
+    x, vad = _data(lengths, 5, 1)
+    vad[0][:] = 1
+    got = ps.run_prestep(ex, x, lengths, vad, cmn_window=window, center=center)
+    want, r = [], 0
+    for T, v in zip(lengths, vad):
+        seg = x[r:r + T]
+        seg = sliding_cmn(seg, window, center) if window > 0 else seg
+        want.append(select_voiced(seg, v))
+        r += T
+    want = np.concatenate(want)
+    assert got.shape == want.shape
+    assert np.max(np.abs(got - want)) <= 2e-5 * max(1.0, np.max(np.abs(want)))
+    # no VAD: every frame kept
+    got_all = ps.run_prestep(ex, x, lengths, None, cmn_window=window, center=center)
+    assert got_all.shape == x.shape
+
+
+def test_extract_raw_equals_pipe_then_extract(cvx, synth, model_dir, require_gpu):
+    """fused pre-step + extraction == (oracle pre-step) -> cvx_extract: bit identical inputs
+    are not expected (double vs oracle order), so compare embeddings to tolerance, and the
+    failure rule (no voiced frames / too few frames) to exactness."""
+    from oracle.prestep_oracle import select_voiced, sliding_cmn
+    ps = importlib.import_module(PKG + ".prestep")
+    path, _ = model_dir("v2_xvector")
+    ex = cvx.Extractor(cvx.Model(path, "tdnn6.affine"), precision="fp32")
+    lengths = [400, 90, 700, 30, 250]
+    x, vad = _data(lengths, 23, 2)
+    vad[3][:] = 0                                                   # nothing voiced -> fails
+    emb, ok = ps.extract_raw(ex, {"input": x}, lengths, vad, {"input": 300}, chunk_size=200, min_chunk_size=25)
+    pieces, kept, r = [], [], 0
+    for T, v in zip(lengths, vad):
+        seg = select_voiced(sliding_cmn(x[r:r + T], 300, True), v)
+        pieces.append(seg); kept.append(len(seg)); r += T
+    ref, ok_ref = ex.extract({"input": np.concatenate(pieces)}, kept, chunk_size=200, min_chunk_size=25)
+    assert ok.tolist() == ok_ref.tolist() and not ok[3]
+    assert np.max(np.abs(emb[ok] - ref[ok])) <= 1e-4 * np.max(np.abs(ref[ok]))
