@@ -38,6 +38,10 @@ struct HostBatch {
   std::vector<float> chunk_weight;
   std::vector<float> out;
   int64_t frames = 0;  // un-padded input frames of the successful utterances
+  // raw-feature mode (device pre-step): rows are raw frames, chunks index the selected frames
+  int64_t kept_rows = 0;
+  std::vector<int64_t> utt_raw_start{0}, utt_kept_start{0};
+  std::vector<int32_t> keep;
 
   void Reset() {
     rows = 0;
@@ -47,6 +51,10 @@ struct HostBatch {
     chunk_len.clear();
     chunk_utt.clear();
     chunk_weight.clear();
+    kept_rows = 0;
+    utt_raw_start.assign(1, 0);
+    utt_kept_start.assign(1, 0);
+    keep.clear();
   }
   void Reserve(int64_t need_rows) {
     for (size_t s = 0; s < feats.size(); ++s) {
@@ -118,8 +126,9 @@ int ExtractMain(int argc, const char* const* argv, bool multiple_input) {
         "<raw-nnet-in> <features-rspecifier-1> ... <features-rspecifier-n> <vector-wspecifier>\n";
     ParseOptions po(multiple_input ? usage_multi : usage_single);
 
-    std::string use_gpu = "yes", output_node, nnet_config, precision = "fp16", names;
-    int32_t chunk_size = -1, min_chunk_size = 100, gpu_id = -1;
+    std::string use_gpu = "yes", output_node, nnet_config, precision = "fp16", names, vad_rspecifier;
+    int32_t chunk_size = -1, min_chunk_size = 100, gpu_id = -1, cmn_window = 0, min_cmn_window = 100;
+    bool cmn_center = true, cmn_norm_vars = false;
     int64_t batch_rows = 1 << 20, max_batch_rows = 0;
     bool pad_input = false, profile = false;
     // accepted for command-line compatibility with nnet3 programs; no effect here
@@ -144,6 +153,15 @@ int ExtractMain(int argc, const char* const* argv, bool multiple_input) {
     po.Register("batch-rows", &batch_rows, "Frames read from the feature pipe(s) per cvx_extract call");
     po.Register("max-batch-rows", &max_batch_rows, "Frames per packed device batch (0 = engine default)");
     po.Register("profile", &profile, "Print per-kernel CUDA-event times at the end");
+    po.Register("vad-rspecifier", &vad_rspecifier,
+                "If set, the features are RAW: keep only frames whose VAD value is non-zero (what piping through "
+                "select-voiced-frames does), on the GPU");
+    po.Register("cmn-window", &cmn_window,
+                "If > 0, the features are RAW: apply sliding-window CMN with this window to the first stream before "
+                "frame selection (what piping through apply-cmvn-sliding does), on the GPU");
+    po.Register("center", &cmn_center, "apply-cmvn-sliding --center");
+    po.Register("min-cmn-window", &min_cmn_window, "apply-cmvn-sliding --min-cmn-window (only if --center=false)");
+    po.Register("norm-vars", &cmn_norm_vars, "apply-cmvn-sliding --norm-vars (only false is supported)");
     if (multiple_input) po.Register("name", &names, "Comma-separated input-node names, one per feature stream");
     po.Register("frame-subsampling-factor", &ign_i[0], "ignored");
     po.Register("extra-left-context", &ign_i[1], "ignored");
@@ -180,6 +198,9 @@ int ExtractMain(int argc, const char* const* argv, bool multiple_input) {
       throw KaldiError("invalid value for --use-gpu: " + use_gpu);
     if (use_gpu == "no") CVX_LOG("--use-gpu=no requested; this implementation has no CPU path and runs on the GPU");
     if (!nnet_config.empty()) output_node = ReadOutputNodeFromConfig(nnet_config);
+    const bool raw_mode = !vad_rspecifier.empty() || cmn_window > 0;
+    if (raw_mode && pad_input) throw KaldiError("--pad-input=true is not supported together with --vad-rspecifier / --cmn-window");
+    if (cmn_norm_vars) throw KaldiError("--norm-vars=true is not supported (the recipes use false)");
     int32_t prec;
     if (precision == "fp16") prec = CVX_PRECISION_FP16;
     else if (precision == "bf16") prec = CVX_PRECISION_BF16;
@@ -233,6 +254,10 @@ int ExtractMain(int argc, const char* const* argv, bool multiple_input) {
     std::vector<std::unique_ptr<SequentialMatrixReader>> readers;
     for (int i = 0; i < num_inputs; ++i) readers.emplace_back(new SequentialMatrixReader(feat_rspecifiers[i]));
     VectorWriter writer(vector_wspecifier);
+    std::unique_ptr<SequentialMatrixReader> vad_reader;
+    if (!vad_rspecifier.empty()) vad_reader.reset(new SequentialMatrixReader(vad_rspecifier, /*allow_vectors=*/true));
+    std::vector<cvx_prestep> prestep(num_inputs);
+    for (int s = 0; s < num_inputs; ++s) prestep[s] = cvx_prestep{s == 0 ? cmn_window : 0, cmn_center ? 1 : 0, min_cmn_window, 0};
 
     HostBatch hb[2];
     for (HostBatch& b : hb) {
@@ -278,9 +303,16 @@ int ExtractMain(int argc, const char* const* argv, bool multiple_input) {
       worker = std::thread([&, which]() {
         HostBatch& w = hb[which];
         std::vector<const float*> f(w.feats.begin(), w.feats.end());
-        worker_status = cvx_extract(engine, f.data(), num_inputs, w.rows, w.chunk_start.data(), w.chunk_len.data(),
-                                    w.chunk_utt.data(), w.chunk_weight.data(), static_cast<int64_t>(w.chunk_start.size()),
-                                    static_cast<int32_t>(w.keys.size()), w.out.data(), 0);
+        if (raw_mode)
+          worker_status = cvx_extract_raw(engine, f.data(), prestep.data(), num_inputs, w.rows, w.utt_raw_start.data(),
+                                          vad_reader ? w.keep.data() : nullptr, w.utt_kept_start.data(),
+                                          static_cast<int32_t>(w.keys.size()), w.chunk_start.data(), w.chunk_len.data(),
+                                          w.chunk_utt.data(), w.chunk_weight.data(),
+                                          static_cast<int64_t>(w.chunk_start.size()), w.out.data(), 0);
+        else
+          worker_status = cvx_extract(engine, f.data(), num_inputs, w.rows, w.chunk_start.data(), w.chunk_len.data(),
+                                      w.chunk_utt.data(), w.chunk_weight.data(), static_cast<int64_t>(w.chunk_start.size()),
+                                      static_cast<int32_t>(w.keys.size()), w.out.data(), 0);
         if (worker_status != CVX_OK) worker_error = cvx_last_error();
       });
     };
@@ -305,17 +337,37 @@ int ExtractMain(int argc, const char* const* argv, bool multiple_input) {
           throw KaldiError("feature streams are not in lock-step at utterance " + utt);
         mats[stream_of_arg[i]] = &readers[i]->Value();
       }
-      const int32_t T = mats[0]->rows;
+      const int32_t Traw = mats[0]->rows;
+      // raw mode: select-voiced-frames' rule (frames with VAD != 0, in order)
+      std::vector<int32_t> utt_keep;
+      if (vad_reader) {
+        if (vad_reader->Done() || vad_reader->Key() != utt)
+          throw KaldiError("the VAD table is not in lock-step with the features at utterance " + utt);
+        const Matrix& v = vad_reader->Value();
+        const int64_t n = static_cast<int64_t>(v.rows) * v.cols;
+        if (n != Traw) {
+          CVX_WARN("Mismatch in number for frames " << Traw << " for features and VAD " << n << ", for utterance " << utt);
+          ok = false;
+        } else {
+          for (int32_t i = 0; i < Traw; ++i)
+            if (v.Data()[i] != 0.0f) utt_keep.push_back(i);
+          if (utt_keep.empty()) {
+            CVX_WARN("No features were judged as voiced for utterance " << utt);
+            ok = false;
+          }
+        }
+      }
+      const int32_t T = vad_reader ? static_cast<int32_t>(utt_keep.size()) : Traw;  // frames the chunks are cut from
       for (int s = 0; s < num_inputs; ++s) {
-        if (mats[s]->rows != T) {
-          CVX_WARN("Feature streams of " << utt << " have different numbers of rows (" << T << " vs " << mats[s]->rows << ")");
+        if (mats[s]->rows != Traw) {
+          CVX_WARN("Feature streams of " << utt << " have different numbers of rows (" << Traw << " vs " << mats[s]->rows << ")");
           ok = false;
         }
-        if (T > 0 && mats[s]->cols != hb[cur].dims[s])
+        if (Traw > 0 && mats[s]->cols != hb[cur].dims[s])
           throw KaldiError("feature dimension " + std::to_string(mats[s]->cols) + " of " + utt + " does not match the network's input dim " +
                            std::to_string(hb[cur].dims[s]));
       }
-      if (ok && T == 0) {
+      if (ok && Traw == 0) {
         CVX_WARN("Zero-length utterance: " << utt);
         ok = false;
       }
@@ -329,7 +381,8 @@ int ExtractMain(int argc, const char* const* argv, bool multiple_input) {
         if (chunk_size == -1 || T < chunk_size) this_chunk = T;
         const int32_t num_chunks = (T + this_chunk - 1) / this_chunk;
         HostBatch& b = hb[cur];
-        b.Reserve(b.rows + T + std::max(min_chunk_size, 0));
+        b.Reserve(b.rows + Traw + std::max(min_chunk_size, 0));
+        const int64_t chunk_base = raw_mode ? b.kept_rows : b.rows;
         const int32_t utt_index = static_cast<int32_t>(b.keys.size());
         const size_t chunks_before = b.chunk_start.size();
         const int64_t rows_before = b.rows;
@@ -340,7 +393,7 @@ int ExtractMain(int argc, const char* const* argv, bool multiple_input) {
         if (!tail_needs_pad) {
           for (int s = 0; s < num_inputs; ++s) {
             float* dst = b.feats[s] + static_cast<size_t>(b.rows) * b.dims[s];
-            if (mats[s]->Data() != dst) std::memcpy(dst, mats[s]->Data(), static_cast<size_t>(T) * b.dims[s] * sizeof(float));
+            if (mats[s]->Data() != dst) std::memcpy(dst, mats[s]->Data(), static_cast<size_t>(Traw) * b.dims[s] * sizeof(float));
           }
           block_copied = true;
         }
@@ -362,9 +415,9 @@ int ExtractMain(int argc, const char* const* argv, bool multiple_input) {
                                  << ctx << " frames); skipping it");
             use = false;
           }
-          const int64_t start = b.rows;
+          const int64_t start = raw_mode ? chunk_base + begin : b.rows;
           if (block_copied) {
-            b.rows += offset;
+            if (!raw_mode) b.rows += offset;
           } else {
             auto put = [&](int32_t r) {
               for (int s = 0; s < num_inputs; ++s) row_ptrs[s] = mats[s]->Row(r);
@@ -388,10 +441,18 @@ int ExtractMain(int argc, const char* const* argv, bool multiple_input) {
         } else {
           b.keys.push_back(utt);
           b.frames += T;
+          if (raw_mode) {
+            b.rows = rows_before + Traw;
+            b.kept_rows += T;
+            b.utt_raw_start.push_back(b.rows);
+            b.utt_kept_start.push_back(b.kept_rows);
+            b.keep.insert(b.keep.end(), utt_keep.begin(), utt_keep.end());
+          }
         }
       }
       if (!ok) ++num_fail;
       for (int i = 0; i < num_inputs; ++i) readers[i]->Next();
+      if (vad_reader) vad_reader->Next();
       if (hb[cur].rows >= batch_rows) {
         launch(cur);
         cur ^= 1;

@@ -540,8 +540,8 @@ static TableSpec ParseSpec(const std::string& spec, bool is_write) {
 TableSpec ParseRspecifier(const std::string& s) { return ParseSpec(s, false); }
 TableSpec ParseWspecifier(const std::string& s) { return ParseSpec(s, true); }
 
-SequentialMatrixReader::SequentialMatrixReader(const std::string& rspecifier)
-    : spec_(ParseRspecifier(rspecifier)) {
+SequentialMatrixReader::SequentialMatrixReader(const std::string& rspecifier, bool allow_vectors)
+    : spec_(ParseRspecifier(rspecifier)), allow_vectors_(allow_vectors) {
   if (spec_.is_ark) ark_.Open(spec_.ark_name);
   else scp_.Open(spec_.scp_name);
   Advance();
@@ -554,7 +554,8 @@ void SequentialMatrixReader::Advance() {
     if (ark_.Eof()) { done_ = true; return; }
     key_ = ark_.ReadToken();
     bool binary = ReadBinaryHeader(ark_);
-    ReadMatrix(ark_, binary, &value_);
+    if (allow_vectors_) ReadVectorOrMatrix(ark_, binary, &value_, nullptr);
+    else ReadMatrix(ark_, binary, &value_);
     have_ = true;
     return;
   }
@@ -569,7 +570,8 @@ void SequentialMatrixReader::Advance() {
     if (!rx.empty() && rx.back() == ']') throw KaldiError("scp range specifiers are not supported: " + line);
     Input in(rx);
     bool binary = ReadBinaryHeader(in);
-    ReadMatrix(in, binary, &value_);
+    if (allow_vectors_) ReadVectorOrMatrix(in, binary, &value_, nullptr);
+    else ReadMatrix(in, binary, &value_);
     have_ = true;
     return;
   }

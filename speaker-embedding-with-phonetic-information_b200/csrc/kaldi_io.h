@@ -147,7 +147,8 @@ TableSpec ParseWspecifier(const std::string& wspecifier);
 // SequentialBaseFloatMatrixReader equivalent.
 class SequentialMatrixReader {
  public:
-  explicit SequentialMatrixReader(const std::string& rspecifier);
+  // allow_vectors: entries may be Kaldi vectors (returned as 1 x n), e.g. a vad.scp table
+  explicit SequentialMatrixReader(const std::string& rspecifier, bool allow_vectors = false);
   bool Done();            // true when no more entries
   const std::string& Key() const { return key_; }
   Matrix& Value() { return value_; }
@@ -162,7 +163,7 @@ class SequentialMatrixReader {
   Input scp_;                 // for scp: the list itself
   std::string key_;
   Matrix value_;
-  bool have_ = false, done_ = false;
+  bool have_ = false, done_ = false, allow_vectors_ = false;
 };
 
 // BaseFloatVectorWriter equivalent for ark / ark,t / ark,scp / scp-less forms.

@@ -60,3 +60,39 @@ def test_extract_raw_equals_pipe_then_extract(cvx, synth, model_dir, require_gpu
     ref, ok_ref = ex.extract({"input": np.concatenate(pieces)}, kept, chunk_size=200, min_chunk_size=25)
     assert ok.tolist() == ok_ref.tolist() and not ok[3]
     assert np.max(np.abs(emb[ok] - ref[ok])) <= 1e-4 * np.max(np.abs(ref[ok]))
+
+
+def test_cli_raw_features_with_vad(cvx, kf, synth, model_dir, require_gpu, tmp_path):
+    """the drop-in program reading RAW features + vad table directly:
+    `--cmn-window=300 --center=true --vad-rspecifier=scp:vad.scp scp:feats.scp` replaces the
+    `apply-cmvn-sliding | select-voiced-frames` pipe of extract_xvectors_new.sh:79."""
+    import os
+    import subprocess
+    from oracle.nnet3_oracle import Oracle, extract_all, parity_metrics
+    from oracle.prestep_oracle import select_voiced, sliding_cmn
+    path, model = model_dir("v2_xvector")
+    lengths = [500, 60, 900, 40]
+    x, vad = _data(lengths, 23, 5)
+    vad[3][:] = 0
+    keys = synth.utt_keys(len(lengths))
+    starts = np.cumsum([0] + lengths[:-1])
+    kf.write_ark(str(tmp_path / "feats.ark"), [(k, x[s:s + n]) for k, s, n in zip(keys, starts, lengths)],
+                 scp_path=str(tmp_path / "feats.scp"))
+    kf.write_ark(str(tmp_path / "vad.ark"), [(k, v) for k, v in zip(keys, vad)], scp_path=str(tmp_path / "vad.scp"))
+    exe = os.path.join(cvx.BIN_DIR, "nnet3-xvector-compute")
+    cmd = [exe, "--use-gpu=no", "--min-chunk-size=25", "--chunk-size=300", "--output-node=tdnn6.affine",
+           "--cmn-window=300", "--center=true", f"--vad-rspecifier=scp,s,cs:{tmp_path}/vad.scp", path,
+           f"scp:{tmp_path}/feats.scp", f"ark:{tmp_path}/o.ark"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    assert "No features were judged as voiced" in r.stderr and "Done 3 utterances, failed for 1" in r.stderr
+    got = dict(kf.read_ark(str(tmp_path / "o.ark")))
+    pieces, kept = [], []
+    for s, n, v in zip(starts, lengths, vad):
+        seg = select_voiced(sliding_cmn(x[s:s + n], 300, True), v)
+        pieces.append(seg); kept.append(len(seg))
+    ref, ok = extract_all(Oracle(model, "tdnn6.affine", np.float64), {"input": np.concatenate(pieces)}, kept,
+                          chunk_size=300, min_chunk_size=25)
+    assert list(got) == [k for k, o in zip(keys, ok) if o]
+    rr, cc = parity_metrics(np.stack([got[k] for k in got]), ref[ok])
+    assert rr <= 1e-3 and cc >= 0.9999, (rr, cc)

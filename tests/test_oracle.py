@@ -233,3 +233,25 @@ def test_operand_rounding_model_predicts_tolerance(synth):
     rbf, cbf = parity_metrics(Oracle(m, "tdnn6.affine", np.float32, quant=round_bf16).forward_chunk(f)[None], e[None])
     assert r16 < 5e-4 and c16 > 0.99999
     assert rbf > r16 * 3
+
+
+# ---- feature pre-step oracle ------------------------------------------
+def test_prestep_oracle_window_rule():
+    from oracle.prestep_oracle import select_voiced, sliding_cmn
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((50, 3)).astype(np.float32)
+    # utterance shorter than the window: every frame is normalised by the global mean
+    assert np.allclose(sliding_cmn(x, 300, True), x - x.mean(0), atol=1e-6)
+    # centred window of 5 on a ramp: interior frames see a symmetric window -> 0; edges see the
+    # first / last 5 frames
+    r = np.arange(20, dtype=np.float32)[:, None]
+    y = sliding_cmn(r, 5, True)[:, 0]
+    assert np.allclose(y[2:18], 0.0, atol=1e-6) and np.isclose(y[1], -1.0) and np.isclose(y[18], 1.0)
+    assert np.isclose(y[0], 0 - 2.0) and np.isclose(y[19], 19 - 17.0)
+    # non-centred: frame t normalised by frames [t-W, t], grown to min window at the start
+    z = sliding_cmn(r, 4, False, min_cmn_window=3)[:, 0]
+    assert np.isclose(z[0], 0 - 1.0) and np.isclose(z[10], 10 - 8.0)
+    v = np.array([1, 0, 1, 1, 0] * 10, np.float32)
+    assert select_voiced(x, v).shape == (30, 3) and np.array_equal(select_voiced(x, v)[1], x[2])
+    with pytest.raises(ValueError):
+        select_voiced(x, v[:-1])
