@@ -120,6 +120,9 @@ Engine::Engine(const Plan& plan, const cvx_engine_options& opts) : plan_(plan), 
     throw CudaError("the tcgen05 path needs an sm_100a device (Blackwell B200); found sm_" + std::to_string(prop.major) +
                     std::to_string(prop.minor));
   debug_ = static_cast<uint32_t>(opts.reserved[0]);
+  if (const char* env = std::getenv("CVX_GEMM_HALO")) {
+    if (env[0] == '0') debug_ |= kDebugNoHaloGemm;  // A/B aid: plain CTA-pair kernel
+  }
   if (const char* env = std::getenv("CVX_GEMM_1CTA")) {
     if (env[0] == '1') debug_ |= kDebugSingleCtaGemm;  // A/B aid: same results, 1-CTA tiles
   }
@@ -406,7 +409,79 @@ void Engine::EncodeMaps() {
     a.ab_format = elem_ == kBF16 ? 1 : 0;
     a.num_stages = 64;
     if (const char* env = std::getenv("CVX_GEMM_STAGES")) a.num_stages = std::max(1, std::atoi(env));
+    BuildHaloArgs(op);
   }
+}
+
+// Groups the layer's K blocks by (source, column block): taps of one source whose offsets span
+// <= kMaxHaloSpan rows share one activation tile (tdnn_gemm_halo.cu).
+void Engine::BuildHaloArgs(FrameOp& op) {
+  const TdnnGemmArgs& a = op.targs;
+  TdnnGemmHaloArgs& h = op.hargs;
+  std::memset(&h, 0, sizeof(h));
+  op.halo_ok = false;
+  // blocks of one tap are consecutive in op.kb; taps appear in Append order
+  struct TapRun { int32_t src, rowoff, first_kb, nblocks; };
+  std::vector<TapRun> runs;
+  for (size_t i = 0; i < op.kb.size(); ++i) {
+    const KBlockDesc& d = op.kb[i];
+    if (d.col == 0) runs.push_back({d.src, d.rowoff, static_cast<int32_t>(i), 0});
+    if (runs.empty()) return;
+    runs.back().nblocks++;
+  }
+  std::vector<HaloGroup> groups;
+  std::vector<bool> used(runs.size(), false);
+  int32_t span_max = 0;
+  for (size_t r = 0; r < runs.size(); ++r) {
+    if (used[r]) continue;
+    // collect later runs of the same source with the same block count that fit the span / tap limits
+    std::vector<size_t> members{r};
+    int32_t lo = runs[r].rowoff, hi = runs[r].rowoff;
+    for (size_t q = r + 1; q < runs.size() && members.size() < kMaxHaloTaps; ++q) {
+      if (used[q] || runs[q].src != runs[r].src || runs[q].nblocks != runs[r].nblocks) continue;
+      const int32_t nlo = std::min(lo, runs[q].rowoff), nhi = std::max(hi, runs[q].rowoff);
+      if (nhi - nlo > kMaxHaloSpan) continue;
+      lo = nlo;
+      hi = nhi;
+      members.push_back(q);
+    }
+    for (size_t m : members) used[m] = true;
+    span_max = std::max(span_max, hi - lo);
+    for (int32_t j = 0; j < runs[r].nblocks; ++j) {
+      HaloGroup g;
+      std::memset(&g, 0, sizeof(g));
+      g.src = runs[r].src;
+      g.col = j * kGemmBlockK;
+      g.rowoff = lo;
+      g.ntaps = static_cast<int32_t>(members.size());
+      g.k16 = op.kb[runs[r].first_kb + j].k16;
+      for (size_t t = 0; t < members.size(); ++t) {
+        g.shift[t] = runs[members[t]].rowoff - lo;
+        g.wkb[t] = runs[members[t]].first_kb + j;
+      }
+      groups.push_back(g);
+    }
+  }
+  if (groups.size() > kMaxHaloGroups) return;
+  h.num_groups = static_cast<int32_t>(groups.size());
+  for (size_t i = 0; i < groups.size(); ++i) h.groups[i] = groups[i];
+  h.a_box_rows = kGemmBlockM + span_max;
+  for (size_t s = 0; s < op.srcs.size(); ++s) {
+    const Buffer& b = buffers_[op.srcs[s]];
+    Encode2D(&h.a_maps[s], elem_, b.ptr, rows_cap_, b.ld, kGemmBlockK, h.a_box_rows);
+  }
+  for (size_t s = op.srcs.size(); s < kMaxASources; ++s) h.a_maps[s] = h.a_maps[0];
+  h.b_map_pair = a.b_map_pair;
+  h.c_map = a.c_map;
+  h.b_box_rows_pair = a.b_box_rows_pair;
+  h.n_pad = a.n_pad;
+  h.n_mma = a.n_mma;
+  h.num_n_tiles = a.num_n_tiles;
+  h.post = a.post;
+  h.relu = a.relu;
+  h.ab_format = a.ab_format;
+  h.out_f32 = 0;
+  op.halo_ok = true;
 }
 
 // ------------------------------------------------------------- profile ----
@@ -512,8 +587,14 @@ void Engine::RunFrames(const float* const* dev_feats, int64_t rows, int64_t src_
       CVX_CUDA_CHECK(LaunchTdnnGemmSimt(a, compute_));
     } else {
       op.targs.num_m_tiles = static_cast<int32_t>((rows + kGemmBlockM - 1) / kGemmBlockM);
-      if (debug_ & kDebugSingleCtaGemm) CVX_CUDA_CHECK(LaunchTdnnGemm(op.targs, num_sms_, compute_));
-      else CVX_CUDA_CHECK(LaunchTdnnGemmPair(op.targs, num_sms_, compute_));
+      if (debug_ & kDebugSingleCtaGemm) {
+        CVX_CUDA_CHECK(LaunchTdnnGemm(op.targs, num_sms_, compute_));
+      } else if (op.halo_ok && !(debug_ & kDebugNoHaloGemm)) {
+        op.hargs.num_m_tiles = op.targs.num_m_tiles;
+        CVX_CUDA_CHECK(LaunchTdnnGemmHalo(op.hargs, num_sms_, compute_));
+      } else {
+        CVX_CUDA_CHECK(LaunchTdnnGemmPair(op.targs, num_sms_, compute_));
+      }
     }
     ProfEnd();
   }

@@ -35,6 +35,7 @@ struct InvalidArgument : public std::runtime_error {
 
 constexpr uint32_t kDebugForceTapPath = 1u;   // cvx_engine_options.reserved[0] bits
 constexpr uint32_t kDebugSingleCtaGemm = 2u;  // use the 1-CTA tcgen05 kernel instead of the CTA-pair one
+constexpr uint32_t kDebugNoHaloGemm = 4u;     // use the plain CTA-pair kernel instead of the tap-halo one
 
 class Engine {
  public:
@@ -89,6 +90,8 @@ class Engine {
     void* d_w = nullptr;        // [n_pad, k_pad] of elem
     float2* d_post = nullptr;   // [n_pad]
     TdnnGemmArgs targs;
+    TdnnGemmHaloArgs hargs;
+    bool halo_ok = false;  // the layer fits the tap-halo kernel's limits
   };
   struct SegOp {
     int32_t in_dim = 0, out_dim = 0;
@@ -111,6 +114,7 @@ class Engine {
   int32_t StagingFor(const std::vector<Tap>& taps);
   void EnsureRows(int64_t rows);
   void EncodeMaps();
+  void BuildHaloArgs(FrameOp& op);
   void RunFrames(const float* const* dev_feats, int64_t rows, int64_t src_row_min, int64_t src_row_max);
   void ProfBegin(int cls, double flops, double bytes);
   void ProfEnd();

@@ -54,6 +54,34 @@ cudaError_t LaunchTdnnGemm(const TdnnGemmArgs& args, int num_sms, cudaStream_t s
 // CTA-pair (cta_group::2, 256-row tiles) variant of the same layer; the production path.
 cudaError_t LaunchTdnnGemmPair(const TdnnGemmArgs& args, int num_sms, cudaStream_t stream);
 
+// Tap-halo variant (tdnn_gemm_halo.cu): one activation tile of 128 + span rows per (source,
+// 64-column block) serves every tap of that source; the production kernel.
+constexpr int kMaxHaloSpan = 16;    // max (largest - smallest) tap offset sharing one tile
+constexpr int kMaxHaloTaps = 4;
+constexpr int kMaxHaloGroups = 160;
+struct HaloGroup {
+  int32_t src;                  // index into a_maps
+  int32_t col;                  // first column of the 64-column block in the source
+  int32_t rowoff;               // smallest tap offset of the group (row coordinate of the tile = m0 + rowoff)
+  int32_t ntaps;
+  int32_t k16;                  // 16-column K steps with real columns
+  int32_t shift[kMaxHaloTaps];  // tap offset - rowoff (rows into the tile)
+  int32_t wkb[kMaxHaloTaps];    // 64-column block index of the tap's weights in Wp
+};
+struct TdnnGemmHaloArgs {
+  CUtensorMap a_maps[kMaxASources];  // box 64 x a_box_rows
+  CUtensorMap b_map_pair;            // box 64 x b_box_rows_pair
+  CUtensorMap c_map;
+  HaloGroup groups[kMaxHaloGroups];
+  int32_t num_groups;
+  int32_t a_box_rows;       // 128 + span of this layer (<= 144)
+  int32_t b_box_rows_pair;
+  int32_t n_pad, n_mma, num_m_tiles, num_n_tiles;
+  const float2* post;
+  int32_t relu, ab_format, out_f32;
+};
+cudaError_t LaunchTdnnGemmHalo(const TdnnGemmHaloArgs& args, int num_sms, cudaStream_t stream);
+
 // fp32 CUDA-core version of the same contraction (CVX_PRECISION_FP32; validation aid).
 struct TdnnGemmSimtArgs {
   const float* a_src[kMaxASources];

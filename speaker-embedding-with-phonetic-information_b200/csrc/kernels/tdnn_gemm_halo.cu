@@ -1,0 +1,317 @@
+// K1 (production variant) -- CTA-pair TDNN implicit GEMM with tap-halo reuse.
+//
+// A spliced layer Append(Offset(x,o_1..o_n)) reads, for one 64-column block of x, the
+// row windows [m0+o_t, m0+o_t+128) -- n nearly identical activation tiles.  This kernel
+// loads ONE tile of 128+span rows (span = max o - min o <= 16) per column block and
+// issues the MMAs of every tap from it: tap t reads rows [o_t - o_min, +128) of the tile
+// through a shared-memory descriptor whose start address is advanced by whole 128-byte
+// rows and whose base_offset field carries (rows mod 8), the swizzle phase of a start that
+// is not 1024-byte aligned.  Activation-tile traffic (L2 -> SM and smem fill) drops by
+// the tap count; weight half-tiles stream through their own ring.
+//
+//   A ring   4 slots x (144 rows x 128 B)   one activation tile per (source, column block)
+//   B ring   7 slots x (128 rows x 128 B)   this CTA's half of one W tile per (group, tap)
+//   both CTAs of the pair: warp 0 = TMA producer (A tile, then its taps' W tiles, in
+//   consumption order); leader CTA warp 1 = MMA issuer (tcgen05.mma.cta_group::2, M=256);
+//   warps 2-9 = epilogue (see tdnn_gemm_pair.cu, unchanged).
+#include "kernels.h"
+#include "ptx.cuh"
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+namespace cvx {
+namespace {
+
+constexpr int kAStages = 4;
+constexpr int kBStages = 7;
+constexpr int kASlotBytes = (kGemmBlockM + kMaxHaloSpan) * 128;  // 18432
+constexpr int kBSlotBytes = (kGemmBlockN / 2) * 128;             // 16384
+constexpr int kCWarpBytes = 32 * 128;
+constexpr int kSmemA = 0;
+constexpr int kSmemB = kSmemA + kAStages * kASlotBytes;  // 73728
+constexpr int kSmemC = kSmemB + kBStages * kBSlotBytes;  // 188416
+constexpr int kSmemPost = kSmemC + 8 * kCWarpBytes;      // 221184
+constexpr int kSmemBars = kSmemPost + kGemmBlockN * 8;   // 223232
+constexpr int kNumBars = 2 * kAStages + 2 * kBStages + 4;
+constexpr int kSmemTmemPtr = kSmemBars + kNumBars * 8;
+constexpr int kSmemTotal = kSmemTmemPtr + 32;
+constexpr int kTmemCols = 512;
+constexpr int kThreads = 320;
+constexpr int kEpilogueThreads = 256;
+constexpr int kEpilogueWarps = 8;
+static_assert(kASlotBytes % 1024 == 0 && kSmemB % 1024 == 0 && kSmemC % 1024 == 0, "swizzle alignment");
+static_assert(kSmemTotal <= 232448, "shared memory budget");
+
+template <bool kBF16>
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  if constexpr (kBF16) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+  } else {
+    uint32_t r;  // saturating: a finite fp32 never becomes an fp16 infinity
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+  }
+}
+
+template <bool kBF16, bool kOutF32>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+    tdnn_gemm_halo_kernel(const __grid_constant__ TdnnGemmHaloArgs args) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* smem_a = smem + kSmemA;
+  uint8_t* smem_b = smem + kSmemB;
+  uint8_t* smem_c = smem + kSmemC;
+  float2* smem_post = reinterpret_cast<float2*>(smem + kSmemPost);
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + kSmemBars);  // leader's are used
+  uint64_t* a_empty = a_full + kAStages;                             // per CTA
+  uint64_t* b_full = a_empty + kAStages;                             // leader's are used
+  uint64_t* b_empty = b_full + kBStages;                             // per CTA
+  uint64_t* tmem_full_bar = b_empty + kBStages;                      // per CTA
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;                      // leader's are used
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + kSmemTmemPtr);
+
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x) >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+
+  if (threadIdx.x == 0) {
+    if (ptx::smem_u32(smem) & 1023u) __trap();
+    for (int i = 0; i < kAStages; ++i) {
+      ptx::mbar_init(&a_full[i], 2);
+      ptx::mbar_init(&a_empty[i], 1);
+    }
+    for (int i = 0; i < kBStages; ++i) {
+      ptx::mbar_init(&b_full[i], 2);
+      ptx::mbar_init(&b_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&tmem_full_bar[i], 1);
+      ptx::mbar_init(&tmem_empty_bar[i], 2 * kEpilogueWarps);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&args.b_map_pair);
+    ptx::prefetch_tensormap(&args.c_map);
+    ptx::prefetch_tensormap(&args.a_maps[0]);
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc_pair(tmem_ptr, kTmemCols);
+    ptx::tmem_relinquish_pair();
+  }
+  ptx::tcgen05_fence_before();
+  ptx::cluster_sync_all();
+  ptx::tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int num_n_tiles = args.num_n_tiles;
+  const int num_tiles = ((args.num_m_tiles + 1) >> 1) * num_n_tiles;  // 256-row tiles
+  const int num_groups = args.num_groups;
+  const int first_tile = blockIdx.x >> 1;
+  const int tile_step = gridDim.x >> 1;
+
+  if (warp == 0) {
+    // ------------------------------------------------------ TMA producer --
+    int sa = 0, sb = 0;
+    uint32_t pa = 0, pb = 0;
+    const uint32_t a_bytes = static_cast<uint32_t>(args.a_box_rows) * 128u;
+    const uint32_t b_bytes = static_cast<uint32_t>(args.b_box_rows_pair) * 128u;
+    for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+      const int m0 = (tile / num_n_tiles) * (2 * kGemmBlockM) + static_cast<int>(rank) * kGemmBlockM;
+      const int n0 = (tile % num_n_tiles) * kGemmBlockN;
+      const int n_cols = min(kGemmBlockN, args.n_mma - n0);
+      const int nb0 = n0 + static_cast<int>(rank) * (n_cols >> 1);  // this CTA's half of the W tile
+      for (int g = 0; g < num_groups; ++g) {
+        const HaloGroup& grp = args.groups[g];
+        ptx::mbar_wait(&a_empty[sa], pa ^ 1);
+        if (ptx::elect_one_sync()) {
+          ptx::mbar_arrive_expect_tx_cluster(&a_full[sa], a_bytes, 0);
+          ptx::tma_load_2d_pair(smem_a + sa * kASlotBytes, &args.a_maps[grp.src], &a_full[sa], 0, grp.col,
+                                m0 + grp.rowoff);
+        }
+        __syncwarp();
+        if (++sa == kAStages) {
+          sa = 0;
+          pa ^= 1;
+        }
+        for (int t = 0; t < grp.ntaps; ++t) {
+          ptx::mbar_wait(&b_empty[sb], pb ^ 1);
+          if (ptx::elect_one_sync()) {
+            ptx::mbar_arrive_expect_tx_cluster(&b_full[sb], b_bytes, 0);
+            ptx::tma_load_2d_pair(smem_b + sb * kBSlotBytes, &args.b_map_pair, &b_full[sb], 0,
+                                  grp.wkb[t] * kGemmBlockK, nb0);
+          }
+          __syncwarp();
+          if (++sb == kBStages) {
+            sb = 0;
+            pb ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------- MMA issuer (leader CTA) --
+    if (rank == 0) {
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      int it = 0;
+      for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
+        const int n0 = (tile % num_n_tiles) * kGemmBlockN;
+        const int n_cols = min(kGemmBlockN, args.n_mma - n0);  // multiple of 16
+        const uint32_t idesc = ptx::make_idesc_f16(kBF16 ? 1u : 0u, 2 * kGemmBlockM, n_cols);
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        ptx::mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
+        ptx::tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + as * kGemmBlockN;
+        uint32_t first = 0;  // becomes non-zero after the first MMA of the tile
+        for (int g = 0; g < num_groups; ++g) {
+          const HaloGroup& grp = args.groups[g];
+          ptx::mbar_wait(&a_full[sa], pa);
+          const uint32_t a_addr = ptx::smem_u32(smem_a + sa * kASlotBytes);
+          for (int t = 0; t < grp.ntaps; ++t) {
+            ptx::mbar_wait(&b_full[sb], pb);
+            ptx::tcgen05_fence_after();
+            // tap t: rows [shift, shift+128) of the halo tile; base_offset = swizzle phase of the start row
+            const uint32_t shift = static_cast<uint32_t>(grp.shift[t]);
+            const uint64_t a_desc = ptx::make_umma_desc_sw128(a_addr + shift * 128u) | (static_cast<uint64_t>(shift & 7u) << 49);
+            const uint64_t b_desc = ptx::make_umma_desc_sw128(ptx::smem_u32(smem_b + sb * kBSlotBytes));
+            if (ptx::elect_one_sync()) {
+#pragma unroll
+              for (int k = 0; k < kGemmBlockK / 16; ++k) {
+                if (k < grp.k16) {
+                  ptx::umma_f16_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, first | static_cast<uint32_t>(k));
+                }
+              }
+              ptx::umma_commit_pair_mc(&b_empty[sb], 0x3);                          // W slot free in both CTAs
+              if (t == grp.ntaps - 1) ptx::umma_commit_pair_mc(&a_empty[sa], 0x3);  // activation slot free
+              if (t == grp.ntaps - 1 && g == num_groups - 1) ptx::umma_commit_pair_mc(&tmem_full_bar[as], 0x3);
+            }
+            __syncwarp();
+            first = 1;
+            if (++sb == kBStages) {
+              sb = 0;
+              pb ^= 1;
+            }
+          }
+          if (++sa == kAStages) {
+            sa = 0;
+            pa ^= 1;
+          }
+        }
+      }
+    }
+  } else {
+    // ---------------------------------------------------------- epilogue --
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;  // which of the quarter's two warps: takes chunks c % 2 == half
+    const int et = threadIdx.x - 64;
+    uint8_t* buf = smem_c + (warp - 2) * kCWarpBytes;
+    int it = 0;
+    for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
+      const int m0 = (tile / num_n_tiles) * (2 * kGemmBlockM) + static_cast<int>(rank) * kGemmBlockM;
+      const int n0 = (tile % num_n_tiles) * kGemmBlockN;
+      constexpr int kChunkCols = kOutF32 ? 32 : 64;  // 128 bytes of output per row and chunk
+      const int n_chunks = (min(kGemmBlockN, args.n_mma - n0) + kChunkCols - 1) / kChunkCols;
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpilogueThreads) : "memory");  // previous tile's params no longer read
+      for (int j = et; j < kGemmBlockN; j += kEpilogueThreads)
+        smem_post[j] = (n0 + j < args.n_pad) ? __ldg(&args.post[n0 + j]) : make_float2(0.f, 0.f);
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpilogueThreads) : "memory");
+
+      ptx::mbar_wait(&tmem_full_bar[as], aphase);
+      ptx::tcgen05_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kGemmBlockN;
+
+      for (int c = half; c < n_chunks; c += 2) {
+        if (ptx::elect_one_sync()) ptx::tma_store_wait_read<0>();  // this warp's previous store is done with `buf`
+        __syncwarp();
+        if constexpr (kOutF32) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32b_x32(t_row + c * 32, r);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float v[4];
+#pragma unroll
+            for (int e = 0; e < 4; e += 2) {
+              const float4 p = *reinterpret_cast<const float4*>(&smem_post[c * 32 + j + e]);
+              v[e] = __uint_as_float(r[j + e]) + p.x;
+              v[e + 1] = __uint_as_float(r[j + e + 1]) + p.z;
+              if (args.relu) {
+                v[e] = fmaxf(v[e], 0.f);
+                v[e + 1] = fmaxf(v[e + 1], 0.f);
+              }
+              v[e] += p.y;
+              v[e + 1] += p.w;
+            }
+            const int unit = j >> 2;  // 16-byte unit (4 floats) inside the 128-byte row
+            *reinterpret_cast<float4*>(buf + lane * 128 + ((unit ^ (lane & 7)) << 4)) = make_float4(v[0], v[1], v[2], v[3]);
+          }
+        } else {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint32_t r[32];
+            ptx::tmem_ld_32x32b_x32(t_row + c * 64 + h * 32, r);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint32_t pk[4];
+#pragma unroll
+              for (int e = 0; e < 8; e += 2) {
+                const float4 p = *reinterpret_cast<const float4*>(&smem_post[c * 64 + h * 32 + j + e]);
+                float v0 = __uint_as_float(r[j + e]) + p.x;
+                float v1 = __uint_as_float(r[j + e + 1]) + p.z;
+                if (args.relu) {
+                  v0 = fmaxf(v0, 0.f);
+                  v1 = fmaxf(v1, 0.f);
+                }
+                pk[e >> 1] = pack2<kBF16>(v0 + p.y, v1 + p.w);
+              }
+              const int unit = h * 4 + (j >> 3);  // 16-byte unit inside the 128-byte row
+              *reinterpret_cast<uint4*>(buf + lane * 128 + ((unit ^ (lane & 7)) << 4)) =
+                  make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+          }
+        }
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (ptx::elect_one_sync()) {
+          ptx::tma_store_2d(&args.c_map, buf, n0 + c * kChunkCols, m0 + q * 32);
+          ptx::tma_store_commit();
+        }
+      }
+      ptx::tcgen05_fence_before();
+      __syncwarp();
+      if (ptx::elect_one_sync()) ptx::mbar_arrive_cluster(&tmem_empty_bar[as], 0);
+    }
+    if (ptx::elect_one_sync()) ptx::tma_store_wait<0>();
+  }
+
+  ptx::tcgen05_fence_before();
+  ptx::cluster_sync_all();  // the peer may still be reading this CTA's smem / arriving on its barriers
+  if (warp == 1) {
+    ptx::tcgen05_fence_after();
+    ptx::tmem_dealloc_pair(tmem_base, kTmemCols);
+  }
+}
+
+}  // namespace
+
+cudaError_t LaunchTdnnGemmHalo(const TdnnGemmHaloArgs& args, int num_sms, cudaStream_t stream) {
+  const bool bf16 = args.ab_format == 1;
+  auto kern = args.out_f32 ? (bf16 ? tdnn_gemm_halo_kernel<true, true> : tdnn_gemm_halo_kernel<false, true>)
+                           : (bf16 ? tdnn_gemm_halo_kernel<true, false> : tdnn_gemm_halo_kernel<false, false>);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
+  if (e != cudaSuccess) return e;
+  const int tiles = ((args.num_m_tiles + 1) / 2) * args.num_n_tiles;
+  if (tiles <= 0) return cudaSuccess;
+  const int clusters = tiles < num_sms / 2 ? tiles : num_sms / 2;
+  kern<<<2 * clusters, kThreads, kSmemTotal, stream>>>(args);
+  return cudaGetLastError();
+}
+
+}  // namespace cvx
