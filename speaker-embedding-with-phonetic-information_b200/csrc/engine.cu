@@ -481,6 +481,7 @@ void Engine::BuildHaloArgs(FrameOp& op) {
   h.relu = a.relu;
   h.ab_format = a.ab_format;
   h.out_f32 = 0;
+  if (const char* env = std::getenv("CVX_HALO_BASEOFF")) h.base_offset_mode = env[0] == '1';
   op.halo_ok = true;
 }
 

@@ -79,6 +79,7 @@ struct TdnnGemmHaloArgs {
   int32_t n_pad, n_mma, num_m_tiles, num_n_tiles;
   const float2* post;
   int32_t relu, ab_format, out_f32;
+  int32_t base_offset_mode;  // test aid: also set the descriptor's base_offset to (shift & 7)
 };
 cudaError_t LaunchTdnnGemmHalo(const TdnnGemmHaloArgs& args, int num_sms, cudaStream_t stream);
 

@@ -5,8 +5,7 @@
 // loads ONE tile of 128+span rows (span = max o - min o <= 16) per column block and
 // issues the MMAs of every tap from it: tap t reads rows [o_t - o_min, +128) of the tile
 // through a shared-memory descriptor whose start address is advanced by whole 128-byte
-// rows and whose base_offset field carries (rows mod 8), the swizzle phase of a start that
-// is not 1024-byte aligned.  Activation-tile traffic (L2 -> SM and smem fill) drops by
+// rows (the swizzle phase follows the absolute address, as it does for the 32-byte K steps).  Activation-tile traffic (L2 -> SM and smem fill) drops by
 // the tap count; weight half-tiles stream through their own ring.
 //
 //   A ring   4 slots x (144 rows x 128 B)   one activation tile per (source, column block)
@@ -175,7 +174,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
             ptx::tcgen05_fence_after();
             // tap t: rows [shift, shift+128) of the halo tile; base_offset = swizzle phase of the start row
             const uint32_t shift = static_cast<uint32_t>(grp.shift[t]);
-            const uint64_t a_desc = ptx::make_umma_desc_sw128(a_addr + shift * 128u) | (static_cast<uint64_t>(shift & 7u) << 49);
+            // (the 128-byte swizzle is a function of the absolute smem address bits, which TMA and the
+            // MMA unit both see, so a start address advanced by whole rows needs no base_offset;
+            // args.base_offset_mode = 1 sets the descriptor's base_offset field instead -- test aid)
+            const uint64_t a_desc = ptx::make_umma_desc_sw128(a_addr + shift * 128u) |
+                                    (args.base_offset_mode ? (static_cast<uint64_t>(shift & 7u) << 49) : 0ull);
             const uint64_t b_desc = ptx::make_umma_desc_sw128(ptx::smem_u32(smem_b + sb * kBSlotBytes));
             if (ptx::elect_one_sync()) {
 #pragma unroll
