@@ -482,7 +482,11 @@ void Engine::BuildHaloArgs(FrameOp& op) {
   h.ab_format = a.ab_format;
   h.out_f32 = 0;
   if (const char* env = std::getenv("CVX_HALO_BASEOFF")) h.base_offset_mode = env[0] == '1';
-  op.halo_ok = true;
+  // single-tap layers gain nothing from the halo tile and prefer the deeper 6-stage ring of the
+  // plain CTA-pair kernel
+  bool multi = false;
+  for (const HaloGroup& g : groups) multi = multi || g.ntaps > 1;
+  op.halo_ok = multi;
 }
 
 // ------------------------------------------------------------- profile ----
