@@ -44,7 +44,7 @@ EncodeTiledFn GetEncodeTiled() {
 // 2-D map over a row-major [rows, ld] matrix of 2-byte elements, box = box_cols x box_rows,
 // 128-byte swizzle (box_cols * 2 bytes == 128), out-of-bounds reads give zeros.
 void Encode2D(CUtensorMap* map, int32_t elem, void* base, int64_t rows, int64_t ld, uint32_t box_cols,
-              uint32_t box_rows, int64_t cols = -1) {
+              uint32_t box_rows, int64_t cols = -1, bool swizzle = true) {
   cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols < 0 ? ld : cols), static_cast<cuuint64_t>(rows)};
   cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * ElemSize(elem)};
   cuuint32_t box[2] = {box_cols, box_rows};
@@ -54,7 +54,7 @@ void Encode2D(CUtensorMap* map, int32_t elem, void* base, int64_t rows, int64_t 
                                                 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   CUresult r = GetEncodeTiled()(map, dt, 2,
                                 base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) throw CudaError("cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r)));
 }
@@ -399,11 +399,16 @@ void Engine::EncodeMaps() {
     Encode2D(&a.b_map_pair, elem_, op.d_w, op.n_pad, op.k_pad, kGemmBlockK, a.b_box_rows_pair);
     const Buffer& ob = buffers_[op.out_buffer];
     Encode2D(&a.c_map, elem_, ob.ptr, rows_cap_, ob.ld, 64, 32);
+    Encode2D(&a.c_map_half, elem_, ob.ptr, rows_cap_, ob.ld, 32, 32, -1, /*swizzle=*/false);
     a.num_kb = static_cast<int32_t>(op.kb.size());
     for (size_t i = 0; i < op.kb.size(); ++i) a.kb[i] = op.kb[i];
     a.n_pad = op.n_pad;
-    a.n_mma = RoundUp(plan_.frame[op.layer].out_dim, 16);
-    a.num_n_tiles = (op.n_pad + kGemmBlockN - 1) / kGemmBlockN;
+    a.n_mma = RoundUp(plan_.frame[op.layer].out_dim, 32);
+    {  // equal N tiles (e.g. 672 = 3 x 224 instead of 256 + 256 + 160): narrow tiles are operand-read bound
+      const int32_t nt = (a.n_mma + kGemmBlockN - 1) / kGemmBlockN;
+      a.tile_n = RoundUp((a.n_mma + nt - 1) / nt, 32);
+    }
+    a.num_n_tiles = (a.n_mma + a.tile_n - 1) / a.tile_n;
     a.post = op.d_post;
     a.relu = plan_.frame[op.layer].relu ? 1 : 0;
     a.ab_format = elem_ == kBF16 ? 1 : 0;
@@ -476,6 +481,8 @@ void Engine::BuildHaloArgs(FrameOp& op) {
   h.b_box_rows_pair = a.b_box_rows_pair;
   h.n_pad = a.n_pad;
   h.n_mma = a.n_mma;
+  h.tile_n = a.tile_n;
+  h.c_map_half = a.c_map_half;
   h.num_n_tiles = a.num_n_tiles;
   h.post = a.post;
   h.relu = a.relu;
@@ -557,6 +564,22 @@ void Engine::RunFrames(const float* const* dev_feats, int64_t rows, int64_t src_
       a.feat_dim[i] = plan_.input_dims[i];
     }
     a.colmap = s.d_colmap;
+    // tiled fast path: one stream, |offset| <= 16, narrow rows (the shared-memory tile stays < 48 KB)
+    a.tile_stream = -1;
+    if (!s.taps.empty()) {
+      int32_t lo = s.taps[0].offset, hi = s.taps[0].offset;
+      bool one = true;
+      for (const StageTap& t : s.taps) {
+        one = one && t.stream == s.taps[0].stream;
+        lo = std::min(lo, t.offset);
+        hi = std::max(hi, t.offset);
+      }
+      if (one && lo >= -16 && hi <= 16 && plan_.input_dims[s.taps[0].stream] <= 64) {
+        a.tile_stream = s.taps[0].stream;
+        a.off_min = lo;
+        a.off_max = hi;
+      }
+    }
     a.out = buffers_[s.buffer].ptr;
     a.ld_out = buffers_[s.buffer].ld;
     a.elem = elem_;
@@ -867,7 +890,9 @@ void Engine::Extract(const float* const* feats, int32_t num_streams, int64_t tot
           a.num_kb = static_cast<int32_t>(s.kb.size());
           for (size_t i = 0; i < s.kb.size(); ++i) a.kb[i] = s.kb[i];
           a.n_pad = s.n_pad;
-          a.n_mma = RoundUp(s.out_dim, 16);
+          a.n_mma = RoundUp(s.out_dim, 32);
+          a.tile_n = kGemmBlockN;
+          a.c_map_half = a.c_map;
           a.num_m_tiles = static_cast<int32_t>((pending + kGemmBlockM - 1) / kGemmBlockM);
           a.num_n_tiles = (a.n_mma + kGemmBlockN - 1) / kGemmBlockN;
           a.post = s.d_post;

@@ -33,10 +33,12 @@ struct TdnnGemmArgs {
   CUtensorMap b_map;                 // Wp [n_pad, k_pad], box 64 x 256, SWIZZLE_128B
   CUtensorMap b_map_pair;            // same matrix, box 64 x 128 (one CTA's half of a W tile, cta_group::2)
   CUtensorMap c_map;                 // out [rows_cap, ld_out], box 64 x 32, SWIZZLE_128B
+  CUtensorMap c_map_half;            // same matrix, box 32 x 32, no swizzle (last half chunk of a tile)
   KBlockDesc kb[kMaxKBlocks];
   int32_t num_kb;
   int32_t n_pad;          // output row pitch, multiple of 64
-  int32_t n_mma;          // roundup(out_dim, 16): columns the MMAs produce
+  int32_t n_mma;          // roundup(out_dim, 32): columns the MMAs produce
+  int32_t tile_n;         // N tile width: n_mma split into equal tiles, multiple of 32, <= 256
   int32_t num_m_tiles;    // ceil(rows / 128)
   int32_t num_n_tiles;    // ceil(n_pad / 256)
   int32_t b_box_rows;     // rows of the W box = min(256, n_pad)
@@ -72,11 +74,12 @@ struct TdnnGemmHaloArgs {
   CUtensorMap a_maps[kMaxASources];  // box 64 x a_box_rows
   CUtensorMap b_map_pair;            // box 64 x b_box_rows_pair
   CUtensorMap c_map;
+  CUtensorMap c_map_half;
   HaloGroup groups[kMaxHaloGroups];
   int32_t num_groups;
   int32_t a_box_rows;       // 128 + span of this layer (<= 144)
   int32_t b_box_rows_pair;
-  int32_t n_pad, n_mma, num_m_tiles, num_n_tiles;
+  int32_t n_pad, n_mma, tile_n, num_m_tiles, num_n_tiles;
   const float2* post;
   int32_t relu, ab_format, out_f32;
   int32_t base_offset_mode;  // test aid: also set the descriptor's base_offset to (shift & 7)
@@ -119,6 +122,9 @@ struct StageArgs {
   int32_t elem;
   int64_t rows;
   int64_t src_row_min, src_row_max;  // source rows that exist, relative to feats[] row 0
+  // tiled fast path: every mapped column reads stream `tile_stream` at offsets in [off_min, off_max]
+  int32_t tile_stream;               // -1: generic gather
+  int32_t off_min, off_max;
 };
 cudaError_t LaunchStageInput(const StageArgs& args, cudaStream_t stream);
 

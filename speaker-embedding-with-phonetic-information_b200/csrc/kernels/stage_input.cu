@@ -57,10 +57,62 @@ __global__ void __launch_bounds__(256) stage_input_kernel(const __grid_constant_
   *reinterpret_cast<uint4*>(static_cast<T*>(args.out) + row * args.ld_out + c0) = *reinterpret_cast<uint4*>(vals);
 }
 
+// Tiled variant for the common case (one stream, small offsets): a CTA first copies the
+// 128 + span source rows it needs into shared memory with fully coalesced loads (each feature
+// row is read from global memory once instead of once per tap), then gathers from there.
+constexpr int kStageTileRows = 128;
+
+template <typename T>
+__global__ void __launch_bounds__(256) stage_input_tiled_kernel(const __grid_constant__ StageArgs args) {
+  constexpr int kVec = 16 / sizeof(T);
+  extern __shared__ uint32_t s_mem[];
+  uint32_t* s_colmap = s_mem;
+  float* s_feat = reinterpret_cast<float*>(s_mem + args.ld_out);
+  const int dim = args.feat_dim[args.tile_stream];
+  const float* __restrict__ src = args.feats[args.tile_stream];
+  const int64_t r0 = static_cast<int64_t>(blockIdx.x) * kStageTileRows;
+  for (int c = threadIdx.x; c < args.ld_out; c += blockDim.x) s_colmap[c] = args.colmap[c];
+  const int n_src = (kStageTileRows + args.off_max - args.off_min) * dim;
+  const int64_t first = (r0 + args.off_min) * dim;
+  const int64_t lo = args.src_row_min * dim, hi = args.src_row_max * dim;
+  for (int i = threadIdx.x; i < n_src; i += blockDim.x) {
+    const int64_t g = first + i;
+    s_feat[i] = (g >= lo && g < hi) ? __ldg(src + g) : 0.f;
+  }
+  __syncthreads();
+  const int groups = args.ld_out / kVec;
+  for (int u = threadIdx.x; u < kStageTileRows * groups; u += blockDim.x) {
+    const int row = u / groups;
+    if (r0 + row >= args.rows) break;
+    const int c0 = (u % groups) * kVec;
+    alignas(16) T vals[kVec];
+#pragma unroll
+    for (int e = 0; e < kVec; ++e) {
+      const uint32_t m = s_colmap[c0 + e];
+      float v = 0.f;
+      if (m & 0x80000000u) {
+        const int off = static_cast<int>((m >> 16) & 0xFFF) - 2048;
+        v = s_feat[(row + off - args.off_min) * dim + (m & 0xFFFF)];
+      }
+      vals[e] = to_elem<T>(v);
+    }
+    *reinterpret_cast<uint4*>(static_cast<T*>(args.out) + (r0 + row) * args.ld_out + c0) = *reinterpret_cast<uint4*>(vals);
+  }
+}
+
 }  // namespace
 
 cudaError_t LaunchStageInput(const StageArgs& args, cudaStream_t stream) {
   if (args.rows <= 0) return cudaSuccess;
+  if (args.tile_stream >= 0) {
+    const unsigned tgrid = static_cast<unsigned>((args.rows + kStageTileRows - 1) / kStageTileRows);
+    const size_t tsmem = static_cast<size_t>(args.ld_out) * 4 +
+                         static_cast<size_t>(kStageTileRows + args.off_max - args.off_min) * args.feat_dim[args.tile_stream] * 4;
+    if (args.elem == kF16) stage_input_tiled_kernel<__half><<<tgrid, 256, tsmem, stream>>>(args);
+    else if (args.elem == kBF16) stage_input_tiled_kernel<__nv_bfloat16><<<tgrid, 256, tsmem, stream>>>(args);
+    else stage_input_tiled_kernel<float><<<tgrid, 256, tsmem, stream>>>(args);
+    return cudaGetLastError();
+  }
   const int vec = 16 / static_cast<int>(ElemSize(args.elem));
   const int64_t total = args.rows * (args.ld_out / vec);
   const unsigned grid = static_cast<unsigned>((total + 255) / 256);

@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(kThreads, 1) tdnn_gemm_kernel(const __grid_con
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m0 = (tile / num_n_tiles) * kGemmBlockM;
-        const int n0 = (tile % num_n_tiles) * kGemmBlockN;
+        const int n0 = (tile % num_n_tiles) * args.tile_n;
         for (int kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           if (ptx::elect_one_sync()) {
@@ -133,8 +133,8 @@ __global__ void __launch_bounds__(kThreads, 1) tdnn_gemm_kernel(const __grid_con
       uint32_t phase = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-        const int n0 = (tile % num_n_tiles) * kGemmBlockN;
-        const int n_cols = min(kGemmBlockN, args.n_mma - n0);  // multiple of 16
+        const int n0 = (tile % num_n_tiles) * args.tile_n;
+        const int n_cols = min(args.tile_n, args.n_mma - n0);  // multiple of 16
         const uint32_t idesc = ptx::make_idesc_f16(kBF16 ? 1u : 0u, kGemmBlockM, n_cols);
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
@@ -173,8 +173,9 @@ __global__ void __launch_bounds__(kThreads, 1) tdnn_gemm_kernel(const __grid_con
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m0 = (tile / num_n_tiles) * kGemmBlockM;
-      const int n0 = (tile % num_n_tiles) * kGemmBlockN;
-      const int n_chunks = (min(kGemmBlockN, args.n_mma - n0) + 63) >> 6;
+      const int n0 = (tile % num_n_tiles) * args.tile_n;
+      const int n_cols = min(args.tile_n, args.n_mma - n0);  // multiple of 32
+      const int n_chunks = (n_cols + 63) >> 6;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
 
@@ -190,8 +191,10 @@ __global__ void __launch_bounds__(kThreads, 1) tdnn_gemm_kernel(const __grid_con
       for (int c = half; c < n_chunks; c += 2) {
         if (ptx::elect_one_sync()) ptx::tma_store_wait_read<0>();  // this warp's previous store is done with `buf`
         __syncwarp();
+        const bool half_chunk = (n_cols - c * 64) < 64;  // see tdnn_gemm_pair.cu
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
+          if (h == 1 && half_chunk) break;
           uint32_t r[32];
           ptx::tmem_ld_32x32b_x32(t_row + c * 64 + h * 32, r);
           ptx::tmem_ld_wait();
@@ -210,14 +213,14 @@ __global__ void __launch_bounds__(kThreads, 1) tdnn_gemm_kernel(const __grid_con
               pk[e >> 1] = pack2<kBF16>(v0 + p.y, v1 + p.w);
             }
             const int unit = h * 4 + (j >> 3);  // 16-byte unit inside the 128-byte row
-            *reinterpret_cast<uint4*>(buf + lane * 128 + ((unit ^ (lane & 7)) << 4)) =
-                make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            uint8_t* dst = half_chunk ? buf + lane * 64 + (unit << 4) : buf + lane * 128 + ((unit ^ (lane & 7)) << 4);
+            *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           }
         }
         ptx::fence_proxy_async_smem();
         __syncwarp();
         if (ptx::elect_one_sync()) {
-          ptx::tma_store_2d(&args.c_map, buf, n0 + c * 64, m0 + q * 32);
+          ptx::tma_store_2d(half_chunk ? &args.c_map_half : &args.c_map, buf, n0 + c * 64, m0 + q * 32);
           ptx::tma_store_commit();
         }
       }

@@ -118,8 +118,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     const uint32_t b_bytes = static_cast<uint32_t>(args.b_box_rows_pair) * 128u;
     for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
       const int m0 = (tile / num_n_tiles) * (2 * kGemmBlockM) + static_cast<int>(rank) * kGemmBlockM;
-      const int n0 = (tile % num_n_tiles) * kGemmBlockN;
-      const int n_cols = min(kGemmBlockN, args.n_mma - n0);
+      const int n0 = (tile % num_n_tiles) * args.tile_n;
+      const int n_cols = min(args.tile_n, args.n_mma - n0);
       const int nb0 = n0 + static_cast<int>(rank) * (n_cols >> 1);  // this CTA's half of the W tile
       for (int g = 0; g < num_groups; ++g) {
         const HaloGroup& grp = args.groups[g];
@@ -156,8 +156,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       uint32_t pa = 0, pb = 0;
       int it = 0;
       for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
-        const int n0 = (tile % num_n_tiles) * kGemmBlockN;
-        const int n_cols = min(kGemmBlockN, args.n_mma - n0);  // multiple of 16
+        const int n0 = (tile % num_n_tiles) * args.tile_n;
+        const int n_cols = min(args.tile_n, args.n_mma - n0);  // multiple of 16
         const uint32_t idesc = ptx::make_idesc_f16(kBF16 ? 1u : 0u, 2 * kGemmBlockM, n_cols);
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
@@ -214,9 +214,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     int it = 0;
     for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
       const int m0 = (tile / num_n_tiles) * (2 * kGemmBlockM) + static_cast<int>(rank) * kGemmBlockM;
-      const int n0 = (tile % num_n_tiles) * kGemmBlockN;
+      const int n0 = (tile % num_n_tiles) * args.tile_n;
       constexpr int kChunkCols = kOutF32 ? 32 : 64;  // 128 bytes of output per row and chunk
-      const int n_chunks = (min(kGemmBlockN, args.n_mma - n0) + kChunkCols - 1) / kChunkCols;
+      const int n_cols = min(args.tile_n, args.n_mma - n0);  // multiple of 32
+      const int n_chunks = (n_cols + kChunkCols - 1) / kChunkCols;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
 
@@ -255,8 +256,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
             *reinterpret_cast<float4*>(buf + lane * 128 + ((unit ^ (lane & 7)) << 4)) = make_float4(v[0], v[1], v[2], v[3]);
           }
         } else {
+          // a tile whose width is an odd multiple of 32 ends in a half chunk: 32 columns, stored
+          // through the un-swizzled 32-column map (rows 64 bytes apart in `buf`)
+          const bool half_chunk = (n_cols - c * 64) < 64;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
+            if (h == 1 && half_chunk) break;
             uint32_t r[32];
             ptx::tmem_ld_32x32b_x32(t_row + c * 64 + h * 32, r);
             ptx::tmem_ld_wait();
@@ -275,9 +280,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                 pk[e >> 1] = pack2<kBF16>(v0 + p.y, v1 + p.w);
               }
               const int unit = h * 4 + (j >> 3);  // 16-byte unit inside the 128-byte row
-              *reinterpret_cast<uint4*>(buf + lane * 128 + ((unit ^ (lane & 7)) << 4)) =
-                  make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              uint8_t* dst = half_chunk ? buf + lane * 64 + (unit << 4) : buf + lane * 128 + ((unit ^ (lane & 7)) << 4);
+              *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             }
+          }
+          if (half_chunk) {
+            ptx::fence_proxy_async_smem();
+            __syncwarp();
+            if (ptx::elect_one_sync()) {
+              ptx::tma_store_2d(&args.c_map_half, buf, n0 + c * 64, m0 + q * 32);
+              ptx::tma_store_commit();
+            }
+            continue;
           }
         }
         ptx::fence_proxy_async_smem();
