@@ -278,6 +278,16 @@ Engine::Engine(const Plan& plan, const cvx_engine_options& opts) : plan_(plan), 
     }
     seg_ops_.push_back(s);
   }
+
+  // Fused pooling: possible when the pooled layer feeds nothing but the pooling, runs on the plain
+  // CTA-pair kernel (single-tap sources) and the tensor path is in use.  CVX_FUSED_POOL=0 keeps the
+  // stand-alone pooling kernels (whose slabs are cut relative to each chunk, so per-chunk results
+  // do not depend on where a chunk sits in the batch).
+  fused_pool_ = elem_ != kF32 && !(debug_ & kDebugSingleCtaGemm) && plan_.pool_output_stddevs;
+  for (const Layer& L : plan_.frame)
+    for (const Tap& t : L.taps) fused_pool_ = fused_pool_ && t.src != plan_.pool_src;
+  for (const Tap& t : plan_.frame[plan_.pool_src].taps) fused_pool_ = fused_pool_ && t.offset == 0;
+  if (const char* env = std::getenv("CVX_FUSED_POOL")) fused_pool_ = fused_pool_ && env[0] != '0';
 }
 
 Engine::~Engine() {
@@ -296,6 +306,9 @@ Engine::~Engine() {
   }
   void* pre_scratch[] = {d_prefix_, d_pre_utt_start_, d_pre_kept_utt_, d_pre_keep_};
   for (void* p : pre_scratch) cudaFree(p);
+  cudaFree(d_pool_meta_);
+  cudaFree(d_slot_n_);
+  cudaFree(d_slot_begin_);
   cudaFree(d_seg_hi_);
   cudaFree(d_seg_lo_);
   for (SegOp& s : seg_ops_) {
@@ -555,7 +568,8 @@ void Engine::ResetProfile() {
 }
 
 // ---------------------------------------------------------- frame pass ----
-void Engine::RunFrames(const float* const* dev_feats, int64_t rows, int64_t src_row_min, int64_t src_row_max) {
+void Engine::RunFrames(const float* const* dev_feats, int64_t rows, int64_t src_row_min, int64_t src_row_max,
+                       const PoolGroupMeta* pool_meta) {
   for (const Staging& s : stagings_) {
     StageArgs a;
     std::memset(&a, 0, sizeof(a));
@@ -615,7 +629,13 @@ void Engine::RunFrames(const float* const* dev_feats, int64_t rows, int64_t src_
       CVX_CUDA_CHECK(LaunchTdnnGemmSimt(a, compute_));
     } else {
       op.targs.num_m_tiles = static_cast<int32_t>((rows + kGemmBlockM - 1) / kGemmBlockM);
-      if (debug_ & kDebugSingleCtaGemm) {
+      if (pool_meta && op.layer == plan_.pool_src) {
+        TdnnGemmArgs fa = op.targs;  // same layer, epilogue reduces instead of storing
+        fa.pool_meta = pool_meta;
+        fa.pool_partials = static_cast<float*>(d_partials_);
+        fa.pool_ld = buffers_[op.out_buffer].ld;
+        CVX_CUDA_CHECK(LaunchTdnnGemmPair(fa, num_sms_, compute_));
+      } else if (debug_ & kDebugSingleCtaGemm) {
         CVX_CUDA_CHECK(LaunchTdnnGemm(op.targs, num_sms_, compute_));
       } else if (op.halo_ok && !(debug_ & kDebugNoHaloGemm)) {
         op.hargs.num_m_tiles = op.targs.num_m_tiles;
@@ -758,6 +778,49 @@ void Engine::Extract(const float* const* feats, int32_t num_streams, int64_t tot
       batches.push_back(b);
     }
   }
+  // ---- fused pooling tables: per batch, per 32-row group the (at most two) runs of valid rows ----
+  bool fused = fused_pool_;
+  std::vector<PoolGroupMeta> pool_meta;            // all batches, batch bi starts at meta_pos[bi]
+  std::vector<int32_t> slot_n, slot_begin_packed;  // per batch: slots / [nchunks + 1] offsets
+  std::vector<int64_t> meta_pos(batches.size()), slot_pos(batches.size()), slot_begin_pos(batches.size());
+  int64_t max_slots = 0;
+  for (size_t bi = 0; bi < batches.size() && fused; ++bi) {
+    const Batch& b = batches[bi];
+    const int64_t rows = b.row1 - b.row0;
+    const int64_t ngroups = (rows + 2 * kGemmBlockM - 1) / (2 * kGemmBlockM) * (2 * kGemmBlockM) / 32;
+    meta_pos[bi] = static_cast<int64_t>(pool_meta.size());
+    slot_pos[bi] = static_cast<int64_t>(slot_n.size());
+    slot_begin_pos[bi] = static_cast<int64_t>(slot_begin_packed.size());
+    pool_meta.resize(pool_meta.size() + ngroups, PoolGroupMeta{0, 0, 0, 0, 0});
+    PoolGroupMeta* gm = pool_meta.data() + meta_pos[bi];
+    int32_t nslots = 0;
+    for (int64_t c = b.c0; c < b.c1 && fused; ++c) {
+      slot_begin_packed.push_back(nslots);
+      const int64_t lo = chunk_start[c] - b.row0 + L;
+      const int64_t hi = chunk_start[c] - b.row0 + std::min<int64_t>(chunk_len[c] - 1 - R, rc);  // inclusive
+      for (int64_t g = lo / 32; g <= hi / 32; ++g) {
+        const int32_t f = static_cast<int32_t>(std::max<int64_t>(lo, g * 32) - g * 32);
+        const int32_t e = static_cast<int32_t>(std::min<int64_t>(hi + 1, g * 32 + 32) - g * 32);
+        PoolGroupMeta& m = gm[g];
+        if (m.a1 <= m.a0 && m.b1 <= m.b0) {  // first run of this group
+          m.slot = nslots;
+          m.a0 = static_cast<uint8_t>(f);
+          m.a1 = static_cast<uint8_t>(e);
+        } else if (m.b1 <= m.b0 && m.slot == nslots - 1) {  // second run: the slot right after the first
+          m.b0 = static_cast<uint8_t>(f);
+          m.b1 = static_cast<uint8_t>(e);
+        } else {
+          fused = false;  // three runs in one group (tiny chunks): use the stand-alone pooling kernels
+          break;
+        }
+        slot_n.push_back(e - f);
+        ++nslots;
+      }
+    }
+    slot_begin_packed.push_back(nslots);
+    max_slots = std::max<int64_t>(max_slots, nslots);
+  }
+
   // chunk_slab_off is stored per batch as [c1-c0+1] entries relative to the batch's first slab
   std::vector<int32_t> slab_off_packed;
   std::vector<int64_t> slab_off_pos(batches.size());
@@ -782,7 +845,12 @@ void Engine::Extract(const float* const* feats, int32_t num_streams, int64_t tot
   Grow(&d_chunk_slab_off_, &chunk_slab_off_cap_, slab_off_packed.size() * 4);
   Grow(&d_weights_, &weights_cap_, weights.size() * 4);
   Grow(&d_utt_off_, &utt_off_cap_, utt_off.size() * 8);
-  Grow(&d_partials_, &partials_cap_, static_cast<size_t>(max_slabs) * 2 * pool_buf.ld * 4);
+  Grow(&d_partials_, &partials_cap_, static_cast<size_t>(std::max(max_slabs, fused ? max_slots : 0)) * 2 * pool_buf.ld * 4);
+  if (fused) {
+    Grow(&d_pool_meta_, &pool_meta_cap_, pool_meta.size() * sizeof(PoolGroupMeta));
+    Grow(&d_slot_n_, &slot_n_cap_, std::max<size_t>(slot_n.size(), 1) * 4);
+    Grow(&d_slot_begin_, &slot_begin_cap_, slot_begin_packed.size() * 4);
+  }
   // pooled statistics of several device batches are collected and the segment layers run on
   // up to kSegFlushChunks chunks at once (a [few chunks, 3000] GEMM per batch is latency bound)
   constexpr int64_t kSegFlushChunks = 16384;
@@ -810,6 +878,11 @@ void Engine::Extract(const float* const* feats, int32_t num_streams, int64_t tot
   CVX_CUDA_CHECK(cudaMemcpyAsync(d_slabs_, slabs.data(), slabs.size() * sizeof(PoolSlab), cudaMemcpyHostToDevice, compute_));
   CVX_CUDA_CHECK(cudaMemcpyAsync(d_chunk_slab_off_, slab_off_packed.data(), slab_off_packed.size() * 4,
                                  cudaMemcpyHostToDevice, compute_));
+  if (fused) {
+    CVX_CUDA_CHECK(cudaMemcpyAsync(d_pool_meta_, pool_meta.data(), pool_meta.size() * sizeof(PoolGroupMeta), cudaMemcpyHostToDevice, compute_));
+    CVX_CUDA_CHECK(cudaMemcpyAsync(d_slot_n_, slot_n.data(), slot_n.size() * 4, cudaMemcpyHostToDevice, compute_));
+    CVX_CUDA_CHECK(cudaMemcpyAsync(d_slot_begin_, slot_begin_packed.data(), slot_begin_packed.size() * 4, cudaMemcpyHostToDevice, compute_));
+  }
   CVX_CUDA_CHECK(cudaMemcpyAsync(d_weights_, weights.data(), weights.size() * 4, cudaMemcpyHostToDevice, compute_));
   CVX_CUDA_CHECK(cudaMemcpyAsync(d_utt_off_, utt_off.data(), utt_off.size() * 8, cudaMemcpyHostToDevice, compute_));
   // the pageable host vectors above must stay alive until these copies ran
@@ -841,7 +914,7 @@ void Engine::Extract(const float* const* feats, int32_t num_streams, int64_t tot
       src_min = 0;
       src_max = rows;
     }
-    RunFrames(dev, rows, src_min, src_max);
+    RunFrames(dev, rows, src_min, src_max, fused ? static_cast<const PoolGroupMeta*>(d_pool_meta_) + meta_pos[bi] : nullptr);
     if (!dev_in) CVX_CUDA_CHECK(cudaEventRecord(feat_free_[fb], compute_));
 
     const int32_t nslabs = static_cast<int32_t>(b.slab1 - b.slab0);
@@ -849,16 +922,28 @@ void Engine::Extract(const float* const* feats, int32_t num_streams, int64_t tot
     const PoolSlab* dsl = static_cast<const PoolSlab*>(d_slabs_) + b.slab0;
     double pooled_rows = 0;
     for (int64_t s = b.slab0; s < b.slab1; ++s) pooled_rows += slabs[s].nrows;
-    ProfBegin(kProfPool, 0, pooled_rows * D * ElemSize(elem_));
-    CVX_CUDA_CHECK(LaunchStatsPoolPartial(pool_buf.ptr, elem_, pool_buf.ld, dsl, nslabs,
-                                          static_cast<float*>(d_partials_), compute_));
-    ProfEnd();
-    ProfBegin(kProfPoolFin, 0, static_cast<double>(nslabs) * 2 * D * 4 + static_cast<double>(nchunks) * pooled * 4);
-    CVX_CUDA_CHECK(LaunchStatsPoolFinalize(static_cast<const float*>(d_partials_), pool_buf.ld, dsl,
-                                           static_cast<const int32_t*>(d_chunk_slab_off_) + slab_off_pos[bi], nchunks, D,
-                                           plan_.pool_output_stddevs ? 1 : 0, plan_.pool_variance_floor,
-                                           static_cast<float*>(d_stats_) + pending * pooled, pooled, compute_));
-    ProfEnd();
+    if (fused) {
+      // the pooled layer's epilogue already left per-slot sums in d_partials_
+      const int32_t bslots = slot_begin_packed[slot_begin_pos[bi] + nchunks];
+      ProfBegin(kProfPoolFin, 0, static_cast<double>(bslots) * 2 * D * 4 + static_cast<double>(nchunks) * pooled * 4);
+      CVX_CUDA_CHECK(LaunchStatsPoolFinalizeFused(static_cast<const float*>(d_partials_), pool_buf.ld,
+                                                  static_cast<const int32_t*>(d_slot_begin_) + slot_begin_pos[bi],
+                                                  static_cast<const int32_t*>(d_slot_n_) + slot_pos[bi], nchunks, D, 1,
+                                                  plan_.pool_variance_floor,
+                                                  static_cast<float*>(d_stats_) + pending * pooled, pooled, compute_));
+      ProfEnd();
+    } else {
+      ProfBegin(kProfPool, 0, pooled_rows * D * ElemSize(elem_));
+      CVX_CUDA_CHECK(LaunchStatsPoolPartial(pool_buf.ptr, elem_, pool_buf.ld, dsl, nslabs,
+                                            static_cast<float*>(d_partials_), compute_));
+      ProfEnd();
+      ProfBegin(kProfPoolFin, 0, static_cast<double>(nslabs) * 2 * D * 4 + static_cast<double>(nchunks) * pooled * 4);
+      CVX_CUDA_CHECK(LaunchStatsPoolFinalize(static_cast<const float*>(d_partials_), pool_buf.ld, dsl,
+                                             static_cast<const int32_t*>(d_chunk_slab_off_) + slab_off_pos[bi], nchunks, D,
+                                             plan_.pool_output_stddevs ? 1 : 0, plan_.pool_variance_floor,
+                                             static_cast<float*>(d_stats_) + pending * pooled, pooled, compute_));
+      ProfEnd();
+    }
 
     pending += nchunks;
     const bool last_batch = bi + 1 == batches.size();

@@ -115,7 +115,9 @@ class Engine {
   void EnsureRows(int64_t rows);
   void EncodeMaps();
   void BuildHaloArgs(FrameOp& op);
-  void RunFrames(const float* const* dev_feats, int64_t rows, int64_t src_row_min, int64_t src_row_max);
+  // pool_meta != NULL: the pooled layer runs with the fused-pooling epilogue (partials -> d_partials_)
+  void RunFrames(const float* const* dev_feats, int64_t rows, int64_t src_row_min, int64_t src_row_max,
+                 const PoolGroupMeta* pool_meta = nullptr);
   void ProfBegin(int cls, double flops, double bytes);
   void ProfEnd();
   void ProfResolve();
@@ -151,6 +153,9 @@ class Engine {
   size_t seg_hi_cap_ = 0, seg_lo_cap_ = 0;
   int64_t seg_split_rows_ = 0;
   int64_t last_num_chunks_ = 0;
+  bool fused_pool_ = false;  // pooled layer's activations are reduced in its GEMM epilogue
+  void *d_pool_meta_ = nullptr, *d_slot_n_ = nullptr, *d_slot_begin_ = nullptr;
+  size_t pool_meta_cap_ = 0, slot_n_cap_ = 0, slot_begin_cap_ = 0;
   void RunPrestep(int32_t s, int32_t dim, const float* host_raw, const cvx_prestep& pre, int64_t total_raw_rows,
                   const int64_t* utt_raw_start, const int32_t* keep, const int64_t* utt_kept_start, int32_t num_utts);
   void *d_raw_[kMaxASources] = {}, *d_sel_[kMaxASources] = {};

@@ -28,6 +28,15 @@ struct KBlockDesc {
   int32_t k16;     // 16-column K steps of this block that hold real columns (1..4)
 };
 
+// Fused pooling (pair kernel, pooled layer only): the epilogue reduces each 32-row group of the
+// output tile over its valid rows instead of storing the activations.  A group holds at most two
+// runs of valid rows (tail of one chunk, head of the next): rows [a0, a1) -> slot, rows [b0, b1)
+// -> the following slot.  Empty runs have a1 <= a0 / b1 <= b0.
+struct PoolGroupMeta {
+  int32_t slot;
+  uint8_t a0, a1, b0, b1;
+};
+
 struct TdnnGemmArgs {
   CUtensorMap a_maps[kMaxASources];  // [rows_cap, ld] activations, box 64 x 128, SWIZZLE_128B
   CUtensorMap b_map;                 // Wp [n_pad, k_pad], box 64 x 256, SWIZZLE_128B
@@ -48,6 +57,9 @@ struct TdnnGemmArgs {
   int32_t ab_format;      // 0 = fp16, 1 = bf16 (UMMA F16F32Format)
   int32_t out_f32;        // pair kernel only: write fp32 output (c_map is an fp32 map with 32-column boxes)
   int32_t c_row0;         // row offset added to every output store (segment layers write into a slice)
+  const PoolGroupMeta* pool_meta;  // non-NULL: fused pooling (see PoolGroupMeta), no activation store
+  float* pool_partials;            // [slots][2][pool_ld]: sum x, sum x^2 per slot and column
+  int32_t pool_ld;
   int32_t num_stages;     // smem ring depth actually used (<= the kernel's maximum; tuning aid)
 };
 
@@ -147,6 +159,12 @@ cudaError_t LaunchStatsPoolFinalize(const float* partials, int32_t ld, const Poo
 // fp32 [m, k] -> fp16 hi / lo split (x = hi + lo to ~2^-22), pad columns [k, ld_out) zeroed
 cudaError_t LaunchSplitF32(const float* in, int32_t ld_in, int64_t m, int32_t k, void* hi, void* lo,
                            int32_t ld_out, int32_t elem, cudaStream_t stream);
+
+// fused-pooling finalize: chunk c owns slots [slot_begin[c], slot_begin[c+1]) with slot_n[] valid rows each
+cudaError_t LaunchStatsPoolFinalizeFused(const float* partials, int32_t ld, const int32_t* slot_begin,
+                                         const int32_t* slot_n, int32_t num_chunks, int32_t dim,
+                                         int32_t output_stddevs, float variance_floor, float* stats,
+                                         int32_t ld_stats, cudaStream_t stream);
 
 // ---- K3: segment-level affine and per-utterance weighted average ----------
 cudaError_t LaunchSegmentAffine(const float* in, int32_t ld_in, int64_t m, int32_t k, const float* w,

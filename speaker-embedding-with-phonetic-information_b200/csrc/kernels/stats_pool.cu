@@ -181,7 +181,46 @@ __global__ void __launch_bounds__(256) stats_pool_finalize_kernel(const float* _
   if (output_stddevs) out[dim + j] = sqrtf(fmaxf(m2 / n, floor_));
 }
 
+// Finalize for the fused path: slots hold plain sums (sum x, sum x^2) over n valid rows.
+__global__ void __launch_bounds__(256) stats_pool_finalize_fused_kernel(const float* __restrict__ partials, int ld,
+                                                                         const int32_t* __restrict__ slot_begin,
+                                                                         const int32_t* __restrict__ slot_n, int dim,
+                                                                         int output_stddevs, float floor_,
+                                                                         float* __restrict__ stats, int ld_stats) {
+  const int chunk = blockIdx.x;
+  const int j = blockIdx.y * blockDim.x + threadIdx.x;
+  if (j >= dim) return;
+  const int s0 = slot_begin[chunk], s1 = slot_begin[chunk + 1];
+  float n = 0.f, mean = 0.f, m2 = 0.f;
+  for (int s = s0; s < s1; ++s) {
+    const float nb = static_cast<float>(slot_n[s]);
+    const float sx = partials[static_cast<int64_t>(s) * 2 * ld + j];
+    const float sxx = partials[static_cast<int64_t>(s) * 2 * ld + ld + j];
+    const float mb = sx / nb;
+    const float m2b = fmaxf(sxx - sx * mb, 0.f);
+    const float tot = n + nb;
+    const float delta = mb - mean;
+    mean += delta * (nb / tot);
+    m2 += m2b + delta * delta * (n * nb / tot);
+    n = tot;
+  }
+  float* out = stats + static_cast<int64_t>(chunk) * ld_stats;
+  out[j] = mean;
+  if (output_stddevs) out[dim + j] = sqrtf(fmaxf(m2 / n, floor_));
+}
+
 }  // namespace
+
+cudaError_t LaunchStatsPoolFinalizeFused(const float* partials, int32_t ld, const int32_t* slot_begin,
+                                         const int32_t* slot_n, int32_t num_chunks, int32_t dim,
+                                         int32_t output_stddevs, float variance_floor, float* stats,
+                                         int32_t ld_stats, cudaStream_t stream) {
+  if (num_chunks <= 0) return cudaSuccess;
+  dim3 grid(num_chunks, (dim + 255) / 256);
+  stats_pool_finalize_fused_kernel<<<grid, 256, 0, stream>>>(partials, ld, slot_begin, slot_n, dim, output_stddevs,
+                                                             variance_floor, stats, ld_stats);
+  return cudaGetLastError();
+}
 
 cudaError_t LaunchStatsPoolPartial(const void* act, int32_t elem, int32_t ld, const PoolSlab* slabs,
                                    int32_t num_slabs, float* partials, cudaStream_t stream) {

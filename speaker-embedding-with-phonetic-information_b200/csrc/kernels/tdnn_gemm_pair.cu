@@ -53,9 +53,27 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   }
 }
 
+// Sum over the 32 lanes of a warp of 32 per-lane values: afterwards s[0] of lane l holds the
+// total of element l (butterfly transpose-reduce, 31 shuffles).
+__device__ __forceinline__ void warp_transpose_reduce(float (&s)[32], int lane) {
+#pragma unroll
+  for (int n = 16; n >= 1; n >>= 1) {
+    const bool up = (lane & n) != 0;
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      const float send = up ? s[i] : s[i + n];
+      const float recv = __shfl_xor_sync(0xffffffffu, send, n);
+      s[i] = (up ? s[i + n] : s[i]) + recv;
+    }
+  }
+}
+
 // kOutF32: the epilogue writes fp32 (32-column chunks) instead of the operand type -- used for
 // the segment-level layers, whose fp32 inputs/weights are fed as fp16 hi/lo splits.
-template <bool kBF16, bool kOutF32>
+// kPool:   fused statistics pooling -- the epilogue of the pooled layer rounds its outputs to the
+// operand type (as if stored) and reduces sum x / sum x^2 over the valid rows of each 32-row
+// group (PoolGroupMeta) into per-slot partials; the [rows, 1500] activation is never written.
+template <bool kBF16, bool kOutF32, bool kPool>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     tdnn_gemm_pair_kernel(const __grid_constant__ TdnnGemmArgs args) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -197,7 +215,60 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       ptx::tcgen05_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kGemmBlockN;
 
+      PoolGroupMeta meta{};
+      if constexpr (kPool) meta = args.pool_meta[(m0 + q * 32) >> 5];
       for (int c = half; c < n_chunks; c += 2) {
+        if constexpr (kPool) {
+          const bool has_a = meta.a1 > meta.a0, has_b = meta.b1 > meta.b0;
+          if (!has_a && !has_b) break;  // no valid row in this 32-row group (edge / gap rows)
+          const bool half_chunk = (n_cols - c * 64) < 64;
+#pragma unroll 1
+          for (int h = 0; h < 2; ++h) {
+            if (h == 1 && half_chunk) break;
+            uint32_t r[32];
+            ptx::tmem_ld_32x32b_x32(t_row + c * 64 + h * 32, r);
+            ptx::tmem_ld_wait();
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              const float4 p = *reinterpret_cast<const float4*>(&smem_post[c * 64 + h * 32 + j]);
+              float v0 = __uint_as_float(r[j]) + p.x;
+              float v1 = __uint_as_float(r[j + 1]) + p.z;
+              if (args.relu) {
+                v0 = fmaxf(v0, 0.f);
+                v1 = fmaxf(v1, 0.f);
+              }
+              const uint32_t pk = pack2<kBF16>(v0 + p.y, v1 + p.w);  // the value a consumer would read
+              if constexpr (kBF16) {
+                v[j] = __uint_as_float(pk << 16);
+                v[j + 1] = __uint_as_float(pk & 0xffff0000u);
+              } else {
+                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&pk));
+                v[j] = f.x;
+                v[j + 1] = f.y;
+              }
+            }
+#pragma unroll 1
+            for (int seg = 0; seg < 2; ++seg) {
+              const int lo = seg ? meta.b0 : meta.a0, hi = seg ? meta.b1 : meta.a1;
+              if (hi <= lo) continue;
+              const bool on = lane >= lo && lane < hi;
+              float s[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) s[j] = on ? v[j] : 0.f;
+              warp_transpose_reduce(s, lane);
+              const float sx = s[0];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) s[j] = on ? v[j] * v[j] : 0.f;
+              warp_transpose_reduce(s, lane);
+              const int slot = meta.slot + ((seg && has_a) ? 1 : 0);
+              float* out = args.pool_partials + static_cast<int64_t>(slot) * 2 * args.pool_ld + n0 + c * 64 + h * 32 + lane;
+              out[0] = sx;
+              out[args.pool_ld] = s[0];
+            }
+          }
+          continue;
+        }
         if (ptx::elect_one_sync()) ptx::tma_store_wait_read<0>();  // this warp's previous store is done with `buf`
         __syncwarp();
         if constexpr (kOutF32) {
@@ -287,8 +358,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 
 cudaError_t LaunchTdnnGemmPair(const TdnnGemmArgs& args, int num_sms, cudaStream_t stream) {
   const bool bf16 = args.ab_format == 1;
-  auto kern = args.out_f32 ? (bf16 ? tdnn_gemm_pair_kernel<true, true> : tdnn_gemm_pair_kernel<false, true>)
-                           : (bf16 ? tdnn_gemm_pair_kernel<true, false> : tdnn_gemm_pair_kernel<false, false>);
+  auto kern = args.pool_meta ? (bf16 ? tdnn_gemm_pair_kernel<true, false, true> : tdnn_gemm_pair_kernel<false, false, true>)
+              : args.out_f32 ? (bf16 ? tdnn_gemm_pair_kernel<true, true, false> : tdnn_gemm_pair_kernel<false, true, false>)
+                             : (bf16 ? tdnn_gemm_pair_kernel<true, false, false> : tdnn_gemm_pair_kernel<false, false, false>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
   if (e != cudaSuccess) return e;
   const int tiles = ((args.num_m_tiles + 1) / 2) * args.num_n_tiles;
