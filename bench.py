@@ -271,6 +271,23 @@ def main() -> None:
         g = prof["tdnn_gemm"]
         gemm_tflops = g["flops"] / (g["total_ms"] * 1e-3) / 1e12
         pl = prof["stats_pool_partial"]
+        pool_note = "stand-alone pooling kernel inside the timed steps"
+        if pl["launches"] == 0:
+            # default path: pooling is fused into the pooled layer's GEMM epilogue.  The stand-alone
+            # HBM-bound kernel (CVX_FUSED_POOL=0) is measured in a separate, untimed pass.
+            os.environ["CVX_FUSED_POOL"] = "0"
+            ex2 = cvx.Extractor(model, device=local_rank, precision=args.precision, max_batch_rows=args.max_batch_rows,
+                                profile=True)
+            for i in range(3):
+                if i == 1:
+                    ex2.reset_profile()
+                ex2.extract_chunks(dptrs, total_rows, starts, lens, utts, None, n_utts, out=np.zeros_like(out),
+                                   flags=cvx.FLAG_DEVICE_INPUT)
+            pl = {p["name"]: p for p in ex2.profile()}["stats_pool_partial"]
+            ex2.close()
+            del os.environ["CVX_FUSED_POOL"]
+            pool_note = ("pooling is fused into the pooled layer's GEMM epilogue on the timed path; this is the "
+                         "stand-alone kernel (CVX_FUSED_POOL=0) measured in a separate pass of the same workload")
         pool_gbs = pl["bytes"] / (pl["total_ms"] * 1e-3) / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
@@ -299,7 +316,7 @@ def main() -> None:
                          "launches": int(g["launches"]), "avg_launch_ms": g["total_ms"] / max(g["launches"], 1)},
             "roofline_pool": {"kernel": "stats_pool_partial", "bound": "hbm", "achieved": pool_gbs, "peak": pk["hbm"],
                               "unit": "GB/s", "frac": pool_gbs / pk["hbm"], "traffic": None,
-                              "launches": int(pl["launches"])},
+                              "launches": int(pl["launches"]), "note": pool_note},
         }
         if world == 1 and not args.no_cpu_baseline:
             from oracle import cpu_baseline
