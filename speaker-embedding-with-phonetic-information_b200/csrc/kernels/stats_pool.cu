@@ -181,32 +181,63 @@ __global__ void __launch_bounds__(256) stats_pool_finalize_kernel(const float* _
   if (output_stddevs) out[dim + j] = sqrtf(fmaxf(m2 / n, floor_));
 }
 
-// Finalize for the fused path: slots hold plain sums (sum x, sum x^2) over n valid rows.
+// Finalize for the fused path: slots hold plain sums (sum x, sum x^2) over n <= 32 valid rows.
+// CTA = (chunk, 64 columns) x 4 slot lanes: each lane walks a contiguous quarter of the chunk's
+// slots, adding 8 slots (<= 256 rows, like a stand-alone slab) before each Chan merge; the four
+// lanes are then merged in order through shared memory (deterministic).
 __global__ void __launch_bounds__(256) stats_pool_finalize_fused_kernel(const float* __restrict__ partials, int ld,
                                                                          const int32_t* __restrict__ slot_begin,
                                                                          const int32_t* __restrict__ slot_n, int dim,
                                                                          int output_stddevs, float floor_,
                                                                          float* __restrict__ stats, int ld_stats) {
+  __shared__ float sh[3][4][64];
   const int chunk = blockIdx.x;
-  const int j = blockIdx.y * blockDim.x + threadIdx.x;
-  if (j >= dim) return;
+  const int cl = threadIdx.x & 63, part = threadIdx.x >> 6;
+  const int j = blockIdx.y * 64 + cl;
   const int s0 = slot_begin[chunk], s1 = slot_begin[chunk + 1];
+  const int per = (s1 - s0 + 3) / 4;
+  const int a = s0 + part * per, b = min(s1, a + per);
   float n = 0.f, mean = 0.f, m2 = 0.f;
-  for (int s = s0; s < s1; ++s) {
-    const float nb = static_cast<float>(slot_n[s]);
-    const float sx = partials[static_cast<int64_t>(s) * 2 * ld + j];
-    const float sxx = partials[static_cast<int64_t>(s) * 2 * ld + ld + j];
-    const float mb = sx / nb;
-    const float m2b = fmaxf(sxx - sx * mb, 0.f);
-    const float tot = n + nb;
-    const float delta = mb - mean;
-    mean += delta * (nb / tot);
-    m2 += m2b + delta * delta * (n * nb / tot);
-    n = tot;
+  if (j < dim) {
+    for (int s = a; s < b; s += 8) {
+      float nb = 0.f, sx = 0.f, sxx = 0.f;
+      const int e = min(b, s + 8);
+#pragma unroll 4
+      for (int t = s; t < e; ++t) {
+        nb += static_cast<float>(slot_n[t]);
+        sx += partials[static_cast<int64_t>(t) * 2 * ld + j];
+        sxx += partials[static_cast<int64_t>(t) * 2 * ld + ld + j];
+      }
+      const float mb = sx / nb;
+      const float m2b = fmaxf(sxx - sx * mb, 0.f);
+      const float tot = n + nb;
+      const float delta = mb - mean;
+      mean += delta * (nb / tot);
+      m2 += m2b + delta * delta * (n * nb / tot);
+      n = tot;
+    }
   }
-  float* out = stats + static_cast<int64_t>(chunk) * ld_stats;
-  out[j] = mean;
-  if (output_stddevs) out[dim + j] = sqrtf(fmaxf(m2 / n, floor_));
+  sh[0][part][cl] = n;
+  sh[1][part][cl] = mean;
+  sh[2][part][cl] = m2;
+  __syncthreads();
+  if (part == 0 && j < dim) {
+    n = 0.f, mean = 0.f, m2 = 0.f;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const float nb = sh[0][p][cl];
+      if (nb > 0.f) {
+        const float tot = n + nb;
+        const float delta = sh[1][p][cl] - mean;
+        mean += delta * (nb / tot);
+        m2 += sh[2][p][cl] + delta * delta * (n * nb / tot);
+        n = tot;
+      }
+    }
+    float* out = stats + static_cast<int64_t>(chunk) * ld_stats;
+    out[j] = mean;
+    if (output_stddevs) out[dim + j] = sqrtf(fmaxf(m2 / n, floor_));
+  }
 }
 
 }  // namespace
@@ -216,7 +247,7 @@ cudaError_t LaunchStatsPoolFinalizeFused(const float* partials, int32_t ld, cons
                                          int32_t output_stddevs, float variance_floor, float* stats,
                                          int32_t ld_stats, cudaStream_t stream) {
   if (num_chunks <= 0) return cudaSuccess;
-  dim3 grid(num_chunks, (dim + 255) / 256);
+  dim3 grid(num_chunks, (dim + 63) / 64);
   stats_pool_finalize_fused_kernel<<<grid, 256, 0, stream>>>(partials, ld, slot_begin, slot_n, dim, output_stddevs,
                                                              variance_floor, stats, ld_stats);
   return cudaGetLastError();

@@ -53,26 +53,12 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   }
 }
 
-// Sum over the 32 lanes of a warp of 32 per-lane values: afterwards s[0] of lane l holds the
-// total of element l (butterfly transpose-reduce, 31 shuffles).
-__device__ __forceinline__ void warp_transpose_reduce(float (&s)[32], int lane) {
-#pragma unroll
-  for (int n = 16; n >= 1; n >>= 1) {
-    const bool up = (lane & n) != 0;
-#pragma unroll
-    for (int i = 0; i < n; ++i) {
-      const float send = up ? s[i] : s[i + n];
-      const float recv = __shfl_xor_sync(0xffffffffu, send, n);
-      s[i] = (up ? s[i + n] : s[i]) + recv;
-    }
-  }
-}
-
 // kOutF32: the epilogue writes fp32 (32-column chunks) instead of the operand type -- used for
 // the segment-level layers, whose fp32 inputs/weights are fed as fp16 hi/lo splits.
 // kPool:   fused statistics pooling -- the epilogue of the pooled layer rounds its outputs to the
 // operand type (as if stored) and reduces sum x / sum x^2 over the valid rows of each 32-row
-// group (PoolGroupMeta) into per-slot partials; the [rows, 1500] activation is never written.
+// group (PoolGroupMeta) into per-slot partials through a swizzled smem transpose; the
+// [rows, 1500] activation is never written.
 template <bool kBF16, bool kOutF32, bool kPool>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     tdnn_gemm_pair_kernel(const __grid_constant__ TdnnGemmArgs args) {
@@ -248,23 +234,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                 v[j + 1] = f.y;
               }
             }
+            // transpose through this warp's (otherwise unused) staging buffer: lane = row writes its 32
+            // columns, then lane = column sums the valid rows; (col ^ row) keeps both phases conflict-free
+            float* tile = reinterpret_cast<float*>(buf);
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) tile[lane * 32 + (j ^ lane)] = v[j];
+            __syncwarp();
 #pragma unroll 1
             for (int seg = 0; seg < 2; ++seg) {
               const int lo = seg ? meta.b0 : meta.a0, hi = seg ? meta.b1 : meta.a1;
               if (hi <= lo) continue;
-              const bool on = lane >= lo && lane < hi;
-              float s[32];
-#pragma unroll
-              for (int j = 0; j < 32; ++j) s[j] = on ? v[j] : 0.f;
-              warp_transpose_reduce(s, lane);
-              const float sx = s[0];
-#pragma unroll
-              for (int j = 0; j < 32; ++j) s[j] = on ? v[j] * v[j] : 0.f;
-              warp_transpose_reduce(s, lane);
+              float sx = 0.f, sxx = 0.f;
+#pragma unroll 4
+              for (int r = lo; r < hi; ++r) {
+                const float x = tile[r * 32 + (lane ^ r)];
+                sx += x;
+                sxx = fmaf(x, x, sxx);
+              }
               const int slot = meta.slot + ((seg && has_a) ? 1 : 0);
               float* out = args.pool_partials + static_cast<int64_t>(slot) * 2 * args.pool_ld + n0 + c * 64 + h * 32 + lane;
               out[0] = sx;
-              out[args.pool_ld] = s[0];
+              out[args.pool_ld] = sxx;
             }
           }
           continue;
