@@ -928,7 +928,7 @@ void Engine::Extract(const float* const* feats, int32_t num_streams, int64_t tot
       ProfBegin(kProfPoolFin, 0, static_cast<double>(bslots) * 2 * D * 4 + static_cast<double>(nchunks) * pooled * 4);
       CVX_CUDA_CHECK(LaunchStatsPoolFinalizeFused(static_cast<const float*>(d_partials_), pool_buf.ld,
                                                   static_cast<const int32_t*>(d_slot_begin_) + slot_begin_pos[bi],
-                                                  static_cast<const int32_t*>(d_slot_n_) + slot_pos[bi], nchunks, D, 1,
+                                                  static_cast<const int32_t*>(d_slot_n_) + slot_pos[bi], nchunks, bslots, D, 1,
                                                   plan_.pool_variance_floor,
                                                   static_cast<float*>(d_stats_) + pending * pooled, pooled, compute_));
       ProfEnd();

@@ -162,8 +162,8 @@ cudaError_t LaunchSplitF32(const float* in, int32_t ld_in, int64_t m, int32_t k,
 
 // fused-pooling finalize: chunk c owns slots [slot_begin[c], slot_begin[c+1]) with slot_n[] valid rows each
 cudaError_t LaunchStatsPoolFinalizeFused(const float* partials, int32_t ld, const int32_t* slot_begin,
-                                         const int32_t* slot_n, int32_t num_chunks, int32_t dim,
-                                         int32_t output_stddevs, float variance_floor, float* stats,
+                                         const int32_t* slot_n, int32_t num_chunks, int32_t total_slots,
+                                         int32_t dim, int32_t output_stddevs, float variance_floor, float* stats,
                                          int32_t ld_stats, cudaStream_t stream);
 
 // ---- K3: segment-level affine and per-utterance weighted average ----------

@@ -182,31 +182,40 @@ __global__ void __launch_bounds__(256) stats_pool_finalize_kernel(const float* _
 }
 
 // Finalize for the fused path: slots hold plain sums (sum x, sum x^2) over n <= 32 valid rows.
-// CTA = (chunk, 64 columns) x 4 slot lanes: each lane walks a contiguous quarter of the chunk's
-// slots, adding 8 slots (<= 256 rows, like a stand-alone slab) before each Chan merge; the four
-// lanes are then merged in order through shared memory (deterministic).
+// CTA = (chunk, 256 / kLanes columns) x kLanes slot lanes: each lane walks a contiguous part of the
+// chunk's slots, adding 8 slots (<= 256 rows, like a stand-alone slab; independent loads) before
+// each Chan merge; the lanes are then merged in order through shared memory (deterministic).
+// kLanes = 4 for long chunks (hundreds of slots), 1 for short segments (a handful of slots).
+template <int kLanes>
 __global__ void __launch_bounds__(256) stats_pool_finalize_fused_kernel(const float* __restrict__ partials, int ld,
                                                                          const int32_t* __restrict__ slot_begin,
                                                                          const int32_t* __restrict__ slot_n, int dim,
                                                                          int output_stddevs, float floor_,
                                                                          float* __restrict__ stats, int ld_stats) {
-  __shared__ float sh[3][4][64];
+  constexpr int kCols = 256 / kLanes;
+  __shared__ float sh[3][kLanes][kCols];
   const int chunk = blockIdx.x;
-  const int cl = threadIdx.x & 63, part = threadIdx.x >> 6;
-  const int j = blockIdx.y * 64 + cl;
+  const int cl = threadIdx.x % kCols, part = threadIdx.x / kCols;
+  const int j = blockIdx.y * kCols + cl;
   const int s0 = slot_begin[chunk], s1 = slot_begin[chunk + 1];
-  const int per = (s1 - s0 + 3) / 4;
+  const int per = (s1 - s0 + kLanes - 1) / kLanes;
   const int a = s0 + part * per, b = min(s1, a + per);
   float n = 0.f, mean = 0.f, m2 = 0.f;
   if (j < dim) {
     for (int s = a; s < b; s += 8) {
       float nb = 0.f, sx = 0.f, sxx = 0.f;
-      const int e = min(b, s + 8);
-#pragma unroll 4
-      for (int t = s; t < e; ++t) {
-        nb += static_cast<float>(slot_n[t]);
-        sx += partials[static_cast<int64_t>(t) * 2 * ld + j];
-        sxx += partials[static_cast<int64_t>(t) * 2 * ld + ld + j];
+      float vx[8], vxx[8];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const bool on = s + t < b;
+        vx[t] = on ? partials[static_cast<int64_t>(s + t) * 2 * ld + j] : 0.f;
+        vxx[t] = on ? partials[static_cast<int64_t>(s + t) * 2 * ld + ld + j] : 0.f;
+        nb += on ? static_cast<float>(slot_n[s + t]) : 0.f;
+      }
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        sx += vx[t];
+        sxx += vxx[t];
       }
       const float mb = sx / nb;
       const float m2b = fmaxf(sxx - sx * mb, 0.f);
@@ -217,14 +226,15 @@ __global__ void __launch_bounds__(256) stats_pool_finalize_fused_kernel(const fl
       n = tot;
     }
   }
-  sh[0][part][cl] = n;
-  sh[1][part][cl] = mean;
-  sh[2][part][cl] = m2;
-  __syncthreads();
-  if (part == 0 && j < dim) {
+  if constexpr (kLanes > 1) {
+    sh[0][part][cl] = n;
+    sh[1][part][cl] = mean;
+    sh[2][part][cl] = m2;
+    __syncthreads();
+    if (part != 0) return;
     n = 0.f, mean = 0.f, m2 = 0.f;
 #pragma unroll
-    for (int p = 0; p < 4; ++p) {
+    for (int p = 0; p < kLanes; ++p) {
       const float nb = sh[0][p][cl];
       if (nb > 0.f) {
         const float tot = n + nb;
@@ -234,6 +244,8 @@ __global__ void __launch_bounds__(256) stats_pool_finalize_fused_kernel(const fl
         n = tot;
       }
     }
+  }
+  if (j < dim) {
     float* out = stats + static_cast<int64_t>(chunk) * ld_stats;
     out[j] = mean;
     if (output_stddevs) out[dim + j] = sqrtf(fmaxf(m2 / n, floor_));
@@ -243,13 +255,19 @@ __global__ void __launch_bounds__(256) stats_pool_finalize_fused_kernel(const fl
 }  // namespace
 
 cudaError_t LaunchStatsPoolFinalizeFused(const float* partials, int32_t ld, const int32_t* slot_begin,
-                                         const int32_t* slot_n, int32_t num_chunks, int32_t dim,
+                                         const int32_t* slot_n, int32_t num_chunks, int32_t total_slots, int32_t dim,
                                          int32_t output_stddevs, float variance_floor, float* stats,
                                          int32_t ld_stats, cudaStream_t stream) {
   if (num_chunks <= 0) return cudaSuccess;
-  dim3 grid(num_chunks, (dim + 63) / 64);
-  stats_pool_finalize_fused_kernel<<<grid, 256, 0, stream>>>(partials, ld, slot_begin, slot_n, dim, output_stddevs,
-                                                             variance_floor, stats, ld_stats);
+  if (total_slots / num_chunks >= 32) {  // long chunks: split each chunk's slots over 4 lanes
+    dim3 grid(num_chunks, (dim + 63) / 64);
+    stats_pool_finalize_fused_kernel<4><<<grid, 256, 0, stream>>>(partials, ld, slot_begin, slot_n, dim, output_stddevs,
+                                                                  variance_floor, stats, ld_stats);
+  } else {
+    dim3 grid(num_chunks, (dim + 255) / 256);
+    stats_pool_finalize_fused_kernel<1><<<grid, 256, 0, stream>>>(partials, ld, slot_begin, slot_n, dim, output_stddevs,
+                                                                  variance_floor, stats, ld_stats);
+  }
   return cudaGetLastError();
 }
 
