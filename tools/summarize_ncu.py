@@ -76,12 +76,14 @@ def kernel_report(name, title, note=""):
              "| launch | " + " | ".join(c.replace("sm__", "").replace(".avg", "").replace("pct_of_peak_sustained_", "%") for c in cols) + " |",
              "|---|" + "---|" * len(cols)]
     traffic = []
+    kn = idx.get("Kernel Name")
     for i, r in enumerate(data):
         vals = []
         for c in cols:
             v, u = r[idx[c]], units[idx[c]]
             vals.append(f"{v} {u}".strip())
-        lines.append(f"| {i} | " + " | ".join(vals) + " |")
+        tagname = (r[kn].split("<")[0].split("::")[-1] if kn is not None else "")
+        lines.append(f"| {i} {tagname} | " + " | ".join(vals) + " |")
         traffic.append(to_bytes(r[idx["dram__bytes_read.sum"]], units[idx["dram__bytes_read.sum"]]) +
                        to_bytes(r[idx["dram__bytes_write.sum"]], units[idx["dram__bytes_write.sum"]]))
     open(os.path.join(P, f"{tag}_{name}.md"), "w").write("\n".join(lines) + "\n")
@@ -90,11 +92,13 @@ def kernel_report(name, title, note=""):
 
 os.makedirs(P, exist_ok=True)
 launch_list()
-t_gemm = kernel_report("gemm", "tdnn_gemm_pair_kernel, 10 consecutive launches = the 10 frame layers of one 343k-row batch "
-                       "(v5 c-vector: tdnn1_share, tdnn2-4_xvec, AM tdnn1-5, tdnn5_xvec)",
-                       "Command: `ncu --set full --clock-control none --import-source on -k regex:tdnn_gemm -s 21 -c 10 python bench.py "
+t_gemm = kernel_report("gemm", "TDNN GEMM kernels, 10 consecutive launches = the 10 frame layers of one 524k-row batch "
+                       "(v5 c-vector, plan order: tdnn1_share, tdnn2-4_xvec, AM tdnn1-5, tdnn5_xvec = pooled layer with the "
+                       "fused-pooling epilogue; multi-tap layers run tdnn_gemm_halo_kernel, the others tdnn_gemm_pair_kernel)",
+                       "Command: `ncu --set full --clock-control none --import-source on -k regex:tdnn_gemm -s 20 -c 10 python bench.py "
                        "--steps 1 --warmup 3 --utts-per-gpu 60 --no-cpu-baseline`")
-t_pool = kernel_report("pool", "stats_pool_partial_kernel<__half>", "Command: `ncu --set full ... -k regex:stats_pool_partial -s 2 -c 2 ...`")
+t_pool = kernel_report("pool", "stats_pool_partial_kernel<__half> (stand-alone pooling, CVX_FUSED_POOL=0)",
+                       "Command: `CVX_FUSED_POOL=0 ncu --set full ... -k regex:stats_pool_partial -s 2 -c 2 ...`")
 kernel_report("stage", "stage_input_kernel<__half>", "Command: `ncu --set full ... -k regex:stage_input -s 2 -c 1 ...`")
 out = {}
 if t_gemm:
