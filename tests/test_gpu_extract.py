@@ -199,3 +199,101 @@ def test_fused_pooling_matches_standalone_kernels(cvx, synth, model_dir, require
         out[fused], ok = ex.extract(feats, lengths, chunk_size=100, min_chunk_size=25)
         assert ok.all()
     assert np.max(np.abs(out["0"] - out["1"])) <= 2e-5 * np.max(np.abs(out["0"]))
+
+
+def test_model_from_plan_abi(cvx, synth, require_gpu):
+    """level-0 ABI: a host that already holds the network hands over a cvx_plan
+    (cvx_model_from_plan) instead of a file; same embeddings as the file route."""
+    import ctypes as C
+    from oracle.nnet3_oracle import Oracle, extract_all, parity_metrics
+
+    class Tap(C.Structure):
+        _fields_ = [("src", C.c_int32), ("offset", C.c_int32)]
+
+    class Layer(C.Structure):
+        _fields_ = [("name", C.c_char_p), ("num_taps", C.c_int32), ("taps", C.POINTER(Tap)), ("in_dim", C.c_int32),
+                    ("out_dim", C.c_int32), ("weight", C.POINTER(C.c_float)), ("bias", C.POINTER(C.c_float)),
+                    ("relu", C.c_int32), ("scale", C.POINTER(C.c_float)), ("offset", C.POINTER(C.c_float))]
+
+    class Plan(C.Structure):
+        _fields_ = [("num_inputs", C.c_int32), ("input_names", C.POINTER(C.c_char_p)), ("input_dims", C.POINTER(C.c_int32)),
+                    ("num_frame_layers", C.c_int32), ("frame_layers", C.POINTER(Layer)), ("pool_src", C.c_int32),
+                    ("pool_left_context", C.c_int32), ("pool_right_context", C.c_int32),
+                    ("pool_output_stddevs", C.c_int32), ("pool_variance_floor", C.c_float),
+                    ("num_segment_layers", C.c_int32), ("segment_layers", C.POINTER(Layer))]
+
+    m = synth.make_tiny_model(feat_dim=5, hidden=16, pooled=24, emb=8)
+    keep = []
+
+    def fptr(a):
+        a = np.ascontiguousarray(a, np.float32)
+        keep.append(a)
+        return a.ctypes.data_as(C.POINTER(C.c_float))
+
+    def layer(name, taps, bn=True, relu=True):
+        f = m.components[name + ".affine"].fields
+        W, b = f["LinearParams"], f["BiasParams"]
+        t = (Tap * max(len(taps), 1))(*[Tap(s, o) for s, o in taps])
+        keep.append(t)
+        L = Layer(name.encode(), len(taps), t, W.shape[1], W.shape[0], fptr(W), fptr(b), int(relu), None, None)
+        if bn:
+            g = m.components[name + ".batchnorm"].fields
+            s = np.float32(g["TargetRms"]) * (np.maximum(g["StatsVar"], 0) + np.float32(g["Epsilon"])) ** np.float32(-0.5)
+            L.scale, L.offset = fptr(s), fptr(-g["StatsMean"] * s)
+        return L
+
+    frames = (Layer * 3)(layer("tdnn1", [(-1, o) for o in (-2, -1, 0, 1, 2)]), layer("tdnn2", [(0, -2), (0, 0), (0, 2)]),
+                         layer("tdnn3", [(1, 0)]))
+    segs = (Layer * 1)(layer("tdnn6", [], bn=False, relu=False))
+    names = (C.c_char_p * 1)(b"input")
+    dims = (C.c_int32 * 1)(5)
+    plan = Plan(1, names, dims, 3, frames, 2, 0, 10000, 1, 1e-10, 1, segs)
+    lib = cvx.load_library()
+    h = C.c_void_p()
+    lib.cvx_model_from_plan.argtypes = [C.POINTER(Plan), C.POINTER(C.c_void_p)]
+    assert lib.cvx_model_from_plan(C.byref(plan), C.byref(h)) == 0, lib.cvx_last_error()
+    mod = cvx.Model.__new__(cvx.Model)
+    mod._lib, mod._h = lib, h
+    info = cvx.ModelInfo()
+    assert lib.cvx_model_get_info(h, C.byref(info)) == 0
+    mod.info, mod.input_names, mod.input_dims = info, ["input"], [5]
+    assert (info.left_context, info.right_context, info.embedding_dim) == (4, 4, 8)
+    lengths = [40, 100, 25]
+    feats = {"input": synth.make_features(lengths, 5, 3)}
+    got, ok = cvx.Extractor(mod, precision="fp32").extract(feats, lengths, chunk_size=60, min_chunk_size=25)
+    ref, _ = extract_all(Oracle(m, "tdnn6.affine", np.float64), feats, lengths, chunk_size=60, min_chunk_size=25)
+    r, c = parity_metrics(got[ok], ref[ok])
+    assert r <= 2e-5, r
+    # malformed plans are refused with a message, not a crash
+    plan.pool_src = 7
+    assert lib.cvx_model_from_plan(C.byref(plan), C.byref(h)) == -1 and b"pool_src" in lib.cvx_last_error()
+
+
+def test_cli_reads_compressed_feature_archives(cvx, kf, synth, model_dir, require_gpu, tmp_path):
+    """feats.scp archives written by steps/make_mfcc.sh hold CompressedMatrix entries
+    (CM2 here: uint16 per value, global min/range header); the reader decodes them."""
+    import os
+    import struct
+    import subprocess
+    from oracle.nnet3_oracle import Oracle, extract_all, parity_metrics
+    path, model = model_dir("v2_xvector")
+    lengths = [120, 300]
+    x = synth.make_features(lengths, 23, 9)
+    lo, rng = float(x.min()), float(x.max() - x.min())
+    q = np.clip(np.round((x - lo) / rng * 65535.0), 0, 65535).astype("<u2")
+    deq = (lo + rng * (1.0 / 65535.0) * q.astype(np.float32)).astype(np.float32)
+    with open(tmp_path / "cm.ark", "wb") as f, open(tmp_path / "cm.scp", "w") as scp:
+        r = 0
+        for k, T in zip(synth.utt_keys(2), lengths):
+            f.write(k.encode() + b" ")
+            scp.write(f"{k} {tmp_path}/cm.ark:{f.tell()}\n")
+            f.write(b"\0BCM2 " + struct.pack("<ffii", lo, rng, T, 23) + q[r:r + T].tobytes())
+            r += T
+    exe = os.path.join(cvx.BIN_DIR, "nnet3-xvector-compute")
+    res = subprocess.run([exe, "--min-chunk-size=25", "--chunk-size=200", "--output-node=tdnn6.affine", path,
+                          f"scp:{tmp_path}/cm.scp", f"ark:{tmp_path}/o.ark"], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr
+    got = np.stack([v for _, v in kf.read_ark(str(tmp_path / "o.ark"))])
+    ref, ok = extract_all(Oracle(model, "tdnn6.affine", np.float64), {"input": deq}, lengths, chunk_size=200, min_chunk_size=25)
+    rr, cc = parity_metrics(got, ref[ok])
+    assert rr <= TOL_REL and cc >= TOL_COS, (rr, cc)
