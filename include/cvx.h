@@ -102,6 +102,15 @@ typedef struct cvx_model cvx_model;
  * SetDropoutTestMode + CollapseModel in nnet3-xvector-compute.cc. */
 int cvx_model_load(const char* rxfilename, const char* output_node, cvx_model** out);
 
+/* The same for the frame-level program nnet3-compute: the output is a layer of the
+ * network evaluated at every frame, e.g. the phonetic bottleneck `tdnn5.batchnorm` or the
+ * log-posteriors `output.log-softmax`
+ * (egs/sre/v5/sid/nnet3_cvector/cvector/extract_am_embedding.sh:56-85,
+ *  egs/sre/v5/sid/nnet3_cvector/cvector/extract_log_post.sh:68-85).  Engines of such a model
+ * serve cvx_compute_frames only; cvx_model_info.pooled_dim is 0 and embedding_dim is the
+ * output dimension. */
+int cvx_model_load_frames(const char* rxfilename, const char* output_node, cvx_model** out);
+
 /* Deep-copies a caller-built plan. */
 int cvx_model_from_plan(const cvx_plan* plan, cvx_model** out);
 
@@ -190,6 +199,18 @@ int cvx_extract_raw(cvx_engine* engine, const float* const* raw_feats, const cvx
                     const int32_t* keep, const int64_t* utt_kept_start, int32_t num_utts,
                     const int64_t* chunk_start, const int32_t* chunk_len, const int32_t* chunk_utt,
                     const float* chunk_weight, int64_t num_chunks, float* out, uint32_t flags);
+
+/* ------------------------------------------------- frame-level outputs --
+ * Replaces DecodableNnetSimple::GetOutput over a whole utterance as nnet3-compute uses it
+ * [UPSTREAM-RECALL nnet3/nnet-am-decodable-simple.cc]: utterance u owns rows
+ * [utt_start[u], utt_start[u+1]) of feats[s]; out [total_rows, embedding_dim] receives one output
+ * row per input frame.  Frames the network needs beyond either end of an utterance are copies
+ * of its first / last frame (upstream's edge rule).  CVX_FLAG_APPLY_EXP exponentiates the result
+ * (nnet3-compute --apply-exp).  Only for engines of a cvx_model_load_frames model. */
+#define CVX_FLAG_APPLY_EXP 4u
+int cvx_compute_frames(cvx_engine* engine, const float* const* feats, int32_t num_streams,
+                       int64_t total_rows, const int64_t* utt_start, int32_t num_utts, float* out,
+                       uint32_t flags);
 
 /* Test entry: the pre-step alone on one stream; out = [total_kept, dim] fp32 host. */
 int cvx_test_prestep(cvx_engine* engine, const float* raw, int32_t dim, const cvx_prestep* prestep,

@@ -199,6 +199,30 @@ class Oracle:
 
     # -- graph evaluation: returns (values[t_lo..t_hi], t_lo) -------------
     def forward_chunk(self, inputs: Dict[str, np.ndarray]) -> np.ndarray:
+        y, lo, fl = self._evaluate(inputs)
+        if fl:
+            raise ValueError("requested output is frame-level; the extraction path expects one vector per chunk")
+        return y[0]
+
+    def forward_frames(self, inputs: Dict[str, np.ndarray]) -> np.ndarray:
+        """Frame-level output at every input frame: what `nnet3-compute` writes for one
+        utterance (R/egs/sre/v5/sid/nnet3_cvector/cvector/extract_am_embedding.sh:79-85,
+        extract_log_post.sh:80-85).  Frames beyond the ends of the input are copies of the
+        first / last frame -- upstream's DecodableNnetSimple edge rule [UPSTREAM-RECALL
+        nnet3/nnet-am-decodable-simple.cc; not in the reference tree]."""
+        left, right = self.frame_context()
+        padded = {}
+        for n, x in inputs.items():
+            x = np.asarray(x)
+            padded[n] = np.concatenate([np.repeat(x[:1], left, axis=0), x, np.repeat(x[-1:], right, axis=0)], axis=0)
+        y, lo, fl = self._evaluate(padded)
+        if not fl:
+            raise ValueError("requested output is segment-level")
+        T = next(iter(inputs.values())).shape[0]
+        assert lo == left and y.shape[0] == T, (lo, left, y.shape, T)
+        return y
+
+    def _evaluate(self, inputs: Dict[str, np.ndarray]):
         T = None
         for n in self.g.input_names:
             if n in inputs:
@@ -233,6 +257,13 @@ class Oracle:
                     y = self._batchnorm(nd.component, x)
                     if self.quant is not None and fl:
                         y = self.quant(y)
+                elif ct == "LogSoftmaxComponent":
+                    if not fl:
+                        raise ValueError("log-softmax of a segment-level node")
+                    m = x.max(axis=1, keepdims=True)
+                    y = x - m - np.log(np.exp(x - m).sum(axis=1, keepdims=True))
+                elif ct in ("NoOpComponent", "DropoutComponent", "GeneralDropoutComponent"):
+                    y = x                                       # test mode
                 elif ct == "StatisticsExtractionComponent":
                     f = comp.fields
                     if int(f["InputPeriod"]) != 1 or int(f["OutputPeriod"]) != 1:
@@ -294,12 +325,25 @@ class Oracle:
                         parts[0][2])
             raise ValueError(d)
 
-        y, lo, fl = ev_node("output")
-        if fl:
-            raise ValueError("requested output is frame-level; the extraction path expects one vector per chunk")
-        return y[0]
+        return ev_node("output")
 
     # -- context ----------------------------------------------------------
+    def frame_context(self) -> Tuple[int, int]:
+        """(left, right) context of a frame-level output node."""
+        def walk(d) -> Tuple[int, int]:
+            if d[0] == "node":
+                nd = self.g.nodes[d[1]]
+                return (0, 0) if nd.kind == "input" else walk(nd.desc)
+            if d[0] == "Offset":
+                l, r = walk(d[1])
+                return l - d[2], r + d[2]
+            if d[0] == "Round":
+                return walk(d[1])
+            ls, rs = zip(*[walk(a) for a in d[1]])
+            return max(ls), max(rs)
+        l, r = walk(self.g.nodes["output"].desc)
+        return max(l, 0), max(r, 0)
+
     def context(self) -> Tuple[int, int]:
         """(left, right) context of the pooling input, by probing (N_valid = T-L-R)."""
         def walk(d) -> Tuple[int, int]:

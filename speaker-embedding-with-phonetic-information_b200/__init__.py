@@ -25,6 +25,7 @@ BIN_DIR = os.path.join(_HERE, "bin")
 PRECISION = {"fp16": 0, "bf16": 1, "fp32": 2}
 FLAG_DEVICE_INPUT = 1
 FLAG_DEVICE_OUTPUT = 2
+FLAG_APPLY_EXP = 4
 
 
 class CvxError(RuntimeError):
@@ -51,10 +52,10 @@ class KernelProfile(C.Structure):
 
 #: every symbol include/cvx.h declares (tests check the library exports them all)
 ABI_SYMBOLS = [
-    "cvx_last_error", "cvx_version", "cvx_model_load", "cvx_model_from_plan", "cvx_model_free",
+    "cvx_last_error", "cvx_version", "cvx_model_load", "cvx_model_load_frames", "cvx_model_from_plan", "cvx_model_free",
     "cvx_model_get_info", "cvx_model_input_name", "cvx_model_input_dim", "cvx_model_describe",
     "cvx_engine_options_default", "cvx_engine_create", "cvx_engine_destroy", "cvx_extract",
-    "cvx_engine_last_chunk_embeddings", "cvx_extract_raw", "cvx_test_prestep", "cvx_host_alloc", "cvx_host_free", "cvx_device_alloc",
+    "cvx_engine_last_chunk_embeddings", "cvx_extract_raw", "cvx_compute_frames", "cvx_test_prestep", "cvx_host_alloc", "cvx_host_free", "cvx_device_alloc",
     "cvx_device_free", "cvx_memcpy_h2d", "cvx_device_count", "cvx_engine_get_profile",
     "cvx_engine_reset_profile", "cvx_engine_launch_count", "cvx_engine_last_extract_ms", "cvx_test_tdnn_layer", "cvx_test_tdnn_layer_bench", "cvx_test_stats_pool",
 ]
@@ -83,6 +84,7 @@ def load_library() -> C.CDLL:
     lib.cvx_last_error.restype = C.c_char_p
     lib.cvx_version.restype = C.c_char_p
     lib.cvx_model_load.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(C.c_void_p)]
+    lib.cvx_model_load_frames.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(C.c_void_p)]
     lib.cvx_model_free.argtypes = [C.c_void_p]
     lib.cvx_model_get_info.argtypes = [C.c_void_p, C.POINTER(ModelInfo)]
     lib.cvx_model_input_name.argtypes = [C.c_void_p, C.c_int32]
@@ -95,6 +97,8 @@ def load_library() -> C.CDLL:
     lib.cvx_engine_destroy.argtypes = [C.c_void_p]
     lib.cvx_extract.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_int64, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_uint32]
+    lib.cvx_compute_frames.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_int64, C.c_void_p, C.c_int32,
+                                       C.c_void_p, C.c_uint32]
     lib.cvx_engine_last_chunk_embeddings.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
     lib.cvx_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
     lib.cvx_host_free.argtypes = [C.c_void_p]
@@ -160,13 +164,15 @@ class PinnedArray:
 
 
 class Model:
-    """nnet3 raw model lowered to the extraction plan (cvx_model_load)."""
+    """nnet3 raw model lowered to the extraction plan (cvx_model_load), or with
+    ``frames=True`` to the frame-output plan nnet3-compute runs (cvx_model_load_frames)."""
 
-    def __init__(self, rxfilename: str, output_node: Optional[str] = None):
+    def __init__(self, rxfilename: str, output_node: Optional[str] = None, frames: bool = False):
         self._lib = load_library()
         h = C.c_void_p()
-        _check(self._lib.cvx_model_load(rxfilename.encode(), output_node.encode() if output_node else None,
-                                        C.byref(h)))
+        load = self._lib.cvx_model_load_frames if frames else self._lib.cvx_model_load
+        _check(load(rxfilename.encode(), output_node.encode() if output_node else None, C.byref(h)))
+        self.frames = frames
         self._h = h
         info = ModelInfo()
         _check(self._lib.cvx_model_get_info(h, C.byref(info)))
@@ -303,6 +309,24 @@ class Extractor:
         out = self.extract_chunks(mats, total, np.array(starts, np.int64), np.array(lens, np.int32),
                                   np.array(utts, np.int32), np.array(wts, np.float32), len(lengths))
         return out, ok
+
+    def compute_frames(self, feats: Dict[str, np.ndarray], lengths: Sequence[int], apply_exp: bool = False,
+                       flags: int = 0) -> np.ndarray:
+        """Frame-output models: the output layer at every frame of every utterance, what
+        `nnet3-compute [--apply-exp=true]` writes row for row (cvx_compute_frames).
+        feats: input-node name -> packed fp32 rows; lengths: rows per utterance."""
+        names = self.model.input_names
+        mats = [np.ascontiguousarray(feats[n], dtype=np.float32) for n in names]
+        start = np.zeros(len(lengths) + 1, dtype=np.int64)
+        np.cumsum(np.asarray(lengths, dtype=np.int64), out=start[1:])
+        total = int(start[-1])
+        ptrs = (C.c_void_p * len(mats))()
+        for i, m in enumerate(mats):
+            ptrs[i] = m.ctypes.data
+        out = np.zeros((total, self.model.info.embedding_dim), dtype=np.float32)
+        _check(self._lib.cvx_compute_frames(self._h, ptrs, len(mats), total, _ptr(start), len(lengths), _ptr(out),
+                                            flags | (FLAG_APPLY_EXP if apply_exp else 0)))
+        return out
 
     def last_chunk_embeddings(self, num_chunks: int) -> np.ndarray:
         out = np.zeros((num_chunks, self.model.info.embedding_dim), dtype=np.float32)

@@ -78,6 +78,8 @@ struct HostBatch {
   }
 };
 
+}  // namespace
+
 std::string ReadOutputNodeFromConfig(const std::string& path) {
   // accepts the one-line extract.config written by run_xvector_new.sh:123 /
   // extract_xvectors_new.sh:58: "output-node name=output input=<descriptor>"
@@ -99,8 +101,6 @@ std::string ReadOutputNodeFromConfig(const std::string& path) {
   }
   throw KaldiError("no 'output-node name=output input=...' line in " + path);
 }
-
-}  // namespace
 
 int ExtractMain(int argc, const char* const* argv, bool multiple_input) {
   try {

@@ -2,7 +2,13 @@
 #ifndef CVX_BIN_EXTRACT_MAIN_H_
 #define CVX_BIN_EXTRACT_MAIN_H_
 
+#include <string>
+
 namespace cvx {
+// The descriptor of "output-node name=output input=<descriptor>" in an extract.config-style file.
+std::string ReadOutputNodeFromConfig(const std::string& path);
+// nnet3-compute <raw-nnet-in> <features-rspecifier> <matrix-wspecifier>  (compute_main.cc)
+int ComputeMain(int argc, const char* const* argv);
 // multiple_input = false: nnet3-xvector-compute       <nnet> <feats-rspecifier> <vector-wspecifier>
 // multiple_input = true : nnet3-cvector-compute-multiple-input --name=a,b <n> <nnet> <feats1> .. <featsn> <vector-wspecifier>
 int ExtractMain(int argc, const char* const* argv, bool multiple_input);

@@ -91,6 +91,16 @@ int cvx_model_load(const char* rxfilename, const char* output_node, cvx_model** 
   });
 }
 
+int cvx_model_load_frames(const char* rxfilename, const char* output_node, cvx_model** out) {
+  if (!rxfilename || !out) return Fail(CVX_ERR_INVALID, "cvx_model_load_frames: NULL argument");
+  *out = nullptr;
+  return Guard([&] {
+    std::unique_ptr<cvx_model> m(new cvx_model);
+    m->plan = cvx::LoadNnet3Plan(rxfilename, output_node ? output_node : "", /*frame_output=*/true);
+    *out = m.release();
+  });
+}
+
 int cvx_model_from_plan(const cvx_plan* p, cvx_model** out) {
   if (!p || !out) return Fail(CVX_ERR_INVALID, "cvx_model_from_plan: NULL argument");
   *out = nullptr;
@@ -122,8 +132,9 @@ int cvx_model_get_info(const cvx_model* model, cvx_model_info* info) {
   const cvx::Plan& p = model->plan;
   info->num_inputs = static_cast<int32_t>(p.input_dims.size());
   info->embedding_dim = p.EmbeddingDim();
-  info->left_context = p.frame[p.pool_src].left;
-  info->right_context = p.frame[p.pool_src].right;
+  const int32_t ctx_layer = p.FrameOutput() ? p.frame_out : p.pool_src;
+  info->left_context = p.frame[ctx_layer].left;
+  info->right_context = p.frame[ctx_layer].right;
   info->pooled_dim = p.PooledDim();
   info->num_frame_layers = static_cast<int32_t>(p.frame.size());
   info->num_segment_layers = static_cast<int32_t>(p.segment.size());
@@ -187,6 +198,13 @@ int cvx_extract_raw(cvx_engine* engine, const float* const* raw_feats, const cvx
     engine->impl->ExtractRaw(raw_feats, prestep, num_streams, total_raw_rows, utt_raw_start, keep, utt_kept_start,
                              num_utts, chunk_start, chunk_len, chunk_utt, chunk_weight, num_chunks, out, flags);
   });
+}
+
+int cvx_compute_frames(cvx_engine* engine, const float* const* feats, int32_t num_streams, int64_t total_rows,
+                       const int64_t* utt_start, int32_t num_utts, float* out, uint32_t flags) {
+  if (!engine) return Fail(CVX_ERR_INVALID, "cvx_compute_frames: NULL engine");
+  if (num_utts > 0 && (!feats || !utt_start || !out)) return Fail(CVX_ERR_INVALID, "cvx_compute_frames: NULL argument");
+  return Guard([&] { engine->impl->ComputeFrames(feats, num_streams, total_rows, utt_start, num_utts, out, flags); });
 }
 
 int cvx_test_prestep(cvx_engine* engine, const float* raw, int32_t dim, const cvx_prestep* prestep,

@@ -283,10 +283,11 @@ Engine::Engine(const Plan& plan, const cvx_engine_options& opts) : plan_(plan), 
   // CTA-pair kernel (single-tap sources) and the tensor path is in use.  CVX_FUSED_POOL=0 keeps the
   // stand-alone pooling kernels (whose slabs are cut relative to each chunk, so per-chunk results
   // do not depend on where a chunk sits in the batch).
-  fused_pool_ = elem_ != kF32 && !(debug_ & kDebugSingleCtaGemm) && plan_.pool_output_stddevs;
+  fused_pool_ = !plan_.FrameOutput() && elem_ != kF32 && !(debug_ & kDebugSingleCtaGemm) && plan_.pool_output_stddevs;
   for (const Layer& L : plan_.frame)
     for (const Tap& t : L.taps) fused_pool_ = fused_pool_ && t.src != plan_.pool_src;
-  for (const Tap& t : plan_.frame[plan_.pool_src].taps) fused_pool_ = fused_pool_ && t.offset == 0;
+  if (!plan_.FrameOutput())
+    for (const Tap& t : plan_.frame[plan_.pool_src].taps) fused_pool_ = fused_pool_ && t.offset == 0;
   if (const char* env = std::getenv("CVX_FUSED_POOL")) fused_pool_ = fused_pool_ && env[0] != '0';
 }
 
@@ -569,7 +570,7 @@ void Engine::ResetProfile() {
 
 // ---------------------------------------------------------- frame pass ----
 void Engine::RunFrames(const float* const* dev_feats, int64_t rows, int64_t src_row_min, int64_t src_row_max,
-                       const PoolGroupMeta* pool_meta) {
+                       const PoolGroupMeta* pool_meta, float* f32_out, int32_t f32_ld) {
   for (const Staging& s : stagings_) {
     StageArgs a;
     std::memset(&a, 0, sizeof(a));
@@ -634,6 +635,16 @@ void Engine::RunFrames(const float* const* dev_feats, int64_t rows, int64_t src_
         fa.pool_meta = pool_meta;
         fa.pool_partials = static_cast<float*>(d_partials_);
         fa.pool_ld = buffers_[op.out_buffer].ld;
+        CVX_CUDA_CHECK(LaunchTdnnGemmPair(fa, num_sms_, compute_));
+      } else if (f32_out && &op == &frame_ops_.back()) {
+        // frame-output mode: the last layer's epilogue writes fp32 rows (no 16-bit rounding of the result);
+        // rows beyond `rows` and columns beyond out_dim are clipped by the map
+        TdnnGemmArgs fa = op.targs;
+        Encode2D(&fa.c_map, kF32, f32_out, rows, f32_ld, 32, 32, L.out_dim);
+        fa.c_map_half = fa.c_map;
+        fa.tile_n = kGemmBlockN;
+        fa.num_n_tiles = (fa.n_mma + kGemmBlockN - 1) / kGemmBlockN;
+        fa.out_f32 = 1;
         CVX_CUDA_CHECK(LaunchTdnnGemmPair(fa, num_sms_, compute_));
       } else if (debug_ & kDebugSingleCtaGemm) {
         CVX_CUDA_CHECK(LaunchTdnnGemm(op.targs, num_sms_, compute_));
@@ -703,6 +714,8 @@ void Engine::Extract(const float* const* feats, int32_t num_streams, int64_t tot
   if (num_streams != static_cast<int32_t>(plan_.input_dims.size()))
     throw InvalidArgument("model has " + std::to_string(plan_.input_dims.size()) + " input stream(s), got " +
                           std::to_string(num_streams));
+  if (plan_.FrameOutput())
+    throw InvalidArgument("this engine was built from a frame-output model (cvx_model_load_frames); use cvx_compute_frames");
   if (num_utts < 0 || num_chunks < 0 || total_rows < 0) throw InvalidArgument("negative size");
   if (!out && num_utts > 0) throw InvalidArgument("out is NULL");
   const int32_t E = plan_.EmbeddingDim();
@@ -1010,6 +1023,102 @@ void Engine::Extract(const float* const* feats, int32_t num_streams, int64_t tot
   CVX_CUDA_CHECK(cudaEventElapsedTime(&last_call_ms_, call_begin_, call_end_));
   ProfResolve();
   last_num_chunks_ = num_chunks;
+}
+
+// -------------------------------------------------------- frame outputs ----
+// nnet3-compute's product: the output layer at every frame of every utterance.
+// Utterances are packed back to back with `left` + `right` replicated edge frames each, so every
+// real frame is an interior row of its padded utterance and one frame pass serves the whole batch.
+void Engine::ComputeFrames(const float* const* feats, int32_t num_streams, int64_t total_rows, const int64_t* utt_start,
+                           int32_t num_utts, float* out, uint32_t flags) {
+  CVX_CUDA_CHECK(cudaSetDevice(opts_.device));
+  if (!plan_.FrameOutput())
+    throw InvalidArgument("this engine was built from an extraction model; load it with cvx_model_load_frames");
+  if (num_streams != static_cast<int32_t>(plan_.input_dims.size()))
+    throw InvalidArgument("model has " + std::to_string(plan_.input_dims.size()) + " input stream(s), got " +
+                          std::to_string(num_streams));
+  if (num_utts < 0 || total_rows < 0) throw InvalidArgument("negative size");
+  if (num_utts == 0) return;
+  if (utt_start[0] < 0 || utt_start[num_utts] > total_rows) throw InvalidArgument("utt_start outside [0, total_rows]");
+  for (int32_t u = 0; u < num_utts; ++u)
+    if (utt_start[u + 1] <= utt_start[u]) throw InvalidArgument("utterance " + std::to_string(u) + " has no frames");
+  for (int32_t s = 0; s < num_streams; ++s)
+    if (!feats[s]) throw InvalidArgument("feats[" + std::to_string(s) + "] is NULL");
+  const bool dev_in = (flags & CVX_FLAG_DEVICE_INPUT) != 0, dev_out = (flags & CVX_FLAG_DEVICE_OUTPUT) != 0;
+  const Layer& OL = plan_.frame[plan_.frame_out];
+  const int32_t left = OL.left, right = OL.right, pad = left + right, E = OL.out_dim;
+  const int32_t ld32 = RoundUp(E, 4);
+  // batch = whole utterances; padded rows per batch bounded by max_batch_rows and by 4 GB of fp32 output
+  int64_t cap = std::min<int64_t>(max_batch_rows_, std::max<int64_t>((int64_t{1} << 30) / ld32, kGemmBlockM));
+  CVX_CUDA_CHECK(cudaEventRecord(call_begin_, compute_));
+  int32_t u0 = 0;
+  while (u0 < num_utts) {
+    int32_t u1 = u0;
+    int64_t rows_p = 0;
+    while (u1 < num_utts) {
+      const int64_t add = utt_start[u1 + 1] - utt_start[u1] + pad;
+      if (u1 > u0 && rows_p + add > cap) break;
+      rows_p += add;
+      ++u1;
+    }
+    const int32_t nu = u1 - u0;
+    const int64_t r0 = utt_start[u0], rows_c = utt_start[u1] - r0;
+    EnsureRows(rows_p);
+    std::vector<int64_t> rel(nu + 1);
+    for (int32_t u = 0; u <= nu; ++u) rel[u] = utt_start[u0 + u] - r0;
+    Grow(&d_utt_off_, &utt_off_cap_, rel.size() * 8);
+    CVX_CUDA_CHECK(cudaMemcpyAsync(d_utt_off_, rel.data(), rel.size() * 8, cudaMemcpyHostToDevice, compute_));
+    const float* dev[kMaxASources] = {};
+    for (int32_t s = 0; s < num_streams; ++s) {
+      const int32_t dim = plan_.input_dims[s];
+      const float* src = feats[s] + r0 * dim;
+      if (!dev_in) {
+        Grow(&d_feat_[0][s], &d_feat_cap_[0][s], static_cast<size_t>(rows_c) * dim * 4);
+        CVX_CUDA_CHECK(cudaMemcpyAsync(d_feat_[0][s], src, static_cast<size_t>(rows_c) * dim * 4, cudaMemcpyHostToDevice, compute_));
+        src = static_cast<const float*>(d_feat_[0][s]);
+      }
+      if (pad > 0) {
+        Grow(&d_sel_[s], &sel_cap_[s], static_cast<size_t>(rows_p) * dim * 4);
+        ProfBegin(kProfStage, 0, static_cast<double>(rows_c + rows_p) * dim * 4.0);
+        CVX_CUDA_CHECK(LaunchPadEdges(src, dim, static_cast<const int64_t*>(d_utt_off_), nu, left, right, rows_p,
+                                      static_cast<float*>(d_sel_[s]), compute_));
+        ProfEnd();
+        src = static_cast<const float*>(d_sel_[s]);
+      }
+      dev[s] = src;
+    }
+    const float* act = nullptr;
+    int32_t act_ld = 0;
+    if (elem_ == kF32) {
+      RunFrames(dev, rows_p, 0, rows_p);
+      const Buffer& b = buffers_[frame_ops_.back().out_buffer];
+      act = static_cast<const float*>(b.ptr);
+      act_ld = b.ld;
+    } else {
+      Grow(&d_stats_, &stats_cap_, static_cast<size_t>(rows_p) * ld32 * 4);
+      RunFrames(dev, rows_p, 0, rows_p, nullptr, static_cast<float*>(d_stats_), ld32);
+      act = static_cast<const float*>(d_stats_);
+      act_ld = ld32;
+    }
+    float* dst = out + r0 * E;
+    if (!dev_out) {
+      Grow(&d_out_, &out_cap_, static_cast<size_t>(rows_c) * E * 4);
+      dst = static_cast<float*>(d_out_);
+    }
+    ProfBegin(kProfAverage, 0, static_cast<double>(rows_c) * E * 8.0);
+    CVX_CUDA_CHECK(LaunchFrameOutput(act, act_ld, E, static_cast<const int64_t*>(d_utt_off_), nu, left, right, rows_c,
+                                     plan_.frame_log_softmax ? 1 : 0, (flags & CVX_FLAG_APPLY_EXP) ? 1 : 0, dst, compute_));
+    ProfEnd();
+    if (!dev_out)
+      CVX_CUDA_CHECK(cudaMemcpyAsync(out + r0 * E, d_out_, static_cast<size_t>(rows_c) * E * 4, cudaMemcpyDeviceToHost, compute_));
+    // the next batch reuses d_utt_off_ / d_feat_ / d_out_: finish this one first
+    CVX_CUDA_CHECK(cudaStreamSynchronize(compute_));
+    u0 = u1;
+  }
+  CVX_CUDA_CHECK(cudaEventRecord(call_end_, compute_));
+  CVX_CUDA_CHECK(cudaStreamSynchronize(compute_));
+  CVX_CUDA_CHECK(cudaEventElapsedTime(&last_call_ms_, call_begin_, call_end_));
+  ProfResolve();
 }
 
 // ------------------------------------------------------------ pre-step ----

@@ -48,6 +48,9 @@ class Engine {
                const int32_t* chunk_len, const int32_t* chunk_utt, const float* chunk_weight, int64_t num_chunks,
                int32_t num_utts, float* out, uint32_t flags);
   void LastChunkEmbeddings(float* out, int64_t num_chunks);
+  // Frame-output models (Plan::frame_out >= 0): the output layer at every frame, edges replicated.
+  void ComputeFrames(const float* const* feats, int32_t num_streams, int64_t total_rows, const int64_t* utt_start,
+                     int32_t num_utts, float* out, uint32_t flags);
   // Extract() preceded by the device pre-step (sliding CMN + frame selection) on raw features.
   void ExtractRaw(const float* const* raw, const cvx_prestep* pre, int32_t num_streams, int64_t total_raw_rows,
                   const int64_t* utt_raw_start, const int32_t* keep, const int64_t* utt_kept_start, int32_t num_utts,
@@ -117,7 +120,7 @@ class Engine {
   void BuildHaloArgs(FrameOp& op);
   // pool_meta != NULL: the pooled layer runs with the fused-pooling epilogue (partials -> d_partials_)
   void RunFrames(const float* const* dev_feats, int64_t rows, int64_t src_row_min, int64_t src_row_max,
-                 const PoolGroupMeta* pool_meta = nullptr);
+                 const PoolGroupMeta* pool_meta = nullptr, float* f32_out = nullptr, int32_t f32_ld = 0);
   void ProfBegin(int cls, double flops, double bytes);
   void ProfEnd();
   void ProfResolve();

@@ -472,22 +472,30 @@ void WriteVector(Output& out, bool binary, const float* v, int32_t n) {
 }
 
 void WriteMatrix(Output& out, bool binary, const Matrix& m) {
+  WriteMatrix(out, binary, m.Data(), m.rows, m.cols);
+}
+
+void WriteMatrix(Output& out, bool binary, const float* data, int32_t rows, int32_t cols) {
   if (binary) {
     out.Write("FM ", 3);
-    WriteInt32Binary(out, m.rows);
-    WriteInt32Binary(out, m.cols);
-    out.Write(m.data.data(), m.data.size() * 4);
+    WriteInt32Binary(out, rows);
+    WriteInt32Binary(out, cols);
+    out.Write(data, static_cast<size_t>(rows) * cols * 4);
   } else {
-    if (m.rows == 0) {
+    if (rows == 0) {
       out.Write(" [ ]\n");
       return;
     }
     std::string s = " [";
-    for (int32_t r = 0; r < m.rows; ++r) {
+    for (int32_t r = 0; r < rows; ++r) {
       s += "\n  ";
-      for (int32_t c = 0; c < m.cols; ++c) {
-        AppendFloatText(&s, m.Row(r)[c]);
+      for (int32_t c = 0; c < cols; ++c) {
+        AppendFloatText(&s, data[static_cast<size_t>(r) * cols + c]);
         s.push_back(' ');
+      }
+      if (s.size() > (1u << 20)) {  // keep the text buffer bounded for long utterances
+        out.Write(s);
+        s.clear();
       }
     }
     s += "]\n";
@@ -607,6 +615,34 @@ void VectorWriter::Write(const std::string& key, const float* v, int32_t n) {
     ark_.Flush();
     if (spec_.is_scp) scp_.Flush();
   }
+}
+
+MatrixWriter::MatrixWriter(const std::string& wspecifier) : spec_(ParseWspecifier(wspecifier)) {
+  if (spec_.is_ark) ark_.Open(spec_.ark_name);
+  if (spec_.is_scp) scp_.Open(spec_.scp_name);
+  if (spec_.is_scp && !spec_.is_ark)
+    throw KaldiError("writing an scp without an ark is not supported: " + wspecifier);
+}
+
+void MatrixWriter::Write(const std::string& key, const float* data, int32_t rows, int32_t cols) {
+  ark_.Write(key);
+  ark_.Write(" ", 1);
+  int64_t off = ark_.Tell();
+  if (!spec_.text) ark_.Write("\0B", 2);
+  WriteMatrix(ark_, !spec_.text, data, rows, cols);
+  if (spec_.is_scp) {
+    std::string line = key + " " + spec_.ark_name + ":" + std::to_string(off) + "\n";
+    scp_.Write(line);
+  }
+  if (spec_.flush) {
+    ark_.Flush();
+    if (spec_.is_scp) scp_.Flush();
+  }
+}
+
+void MatrixWriter::Close() {
+  if (ark_.IsOpen() && ark_.Close() != 0) throw KaldiError("error closing " + spec_.ark_name);
+  if (scp_.IsOpen() && scp_.Close() != 0) throw KaldiError("error closing " + spec_.scp_name);
 }
 
 void VectorWriter::Close() {

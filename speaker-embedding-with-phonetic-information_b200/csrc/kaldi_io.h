@@ -133,6 +133,7 @@ void ReadVectorOrMatrix(Input& in, bool binary, Matrix* m, bool* was_vector);
 void WriteToken(Output& out, const std::string& tok);
 void WriteVector(Output& out, bool binary, const float* v, int32_t n);
 void WriteMatrix(Output& out, bool binary, const Matrix& m);
+void WriteMatrix(Output& out, bool binary, const float* data, int32_t rows, int32_t cols);
 
 // ----------------------------------------------------------------- tables --
 struct TableSpec {
@@ -171,6 +172,19 @@ class VectorWriter {
  public:
   explicit VectorWriter(const std::string& wspecifier);
   void Write(const std::string& key, const float* v, int32_t n);
+  void Close();
+
+ private:
+  TableSpec spec_;
+  Output ark_;
+  Output scp_;
+};
+
+// Table of float matrices (what nnet3-compute writes): ark, ark,t and ark,scp.
+class MatrixWriter {
+ public:
+  explicit MatrixWriter(const std::string& wspecifier);
+  void Write(const std::string& key, const float* data, int32_t rows, int32_t cols);
   void Close();
 
  private:

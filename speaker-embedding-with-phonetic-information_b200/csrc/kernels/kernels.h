@@ -182,5 +182,13 @@ cudaError_t LaunchCmnSelect(const float* x, int32_t dim, const int64_t* utt_star
                             const int32_t* keep, int64_t total_kept, const double* prefix, int32_t cmn_window,
                             int32_t center, int32_t min_window, float* out, cudaStream_t stream);
 
+// ---- frame-level outputs (frame_output.cu): edge replication in, compaction (+log-softmax) out ----
+// utt_start [num_utts + 1] in compact rows; utterance u owns padded rows from utt_start[u] + u * (left + right)
+cudaError_t LaunchPadEdges(const float* src, int32_t dim, const int64_t* utt_start, int32_t num_utts, int32_t left,
+                           int32_t right, int64_t padded_rows, float* dst, cudaStream_t stream);
+cudaError_t LaunchFrameOutput(const float* act, int32_t ld, int32_t dim, const int64_t* utt_start, int32_t num_utts,
+                              int32_t left, int32_t right, int64_t rows, int32_t log_softmax, int32_t apply_exp,
+                              float* out, cudaStream_t stream);
+
 }  // namespace cvx
 #endif  // CVX_KERNELS_KERNELS_H_

@@ -365,7 +365,7 @@ struct Sym {
 
 class Lowerer {
  public:
-  Lowerer(const Nnet& net, Plan* plan) : net_(net), plan_(plan) {}
+  Lowerer(const Nnet& net, Plan* plan, bool frame_output) : net_(net), plan_(plan), frame_output_(frame_output) {}
 
   void Run() {
     auto it = net_.node_index.find("output");
@@ -374,11 +374,29 @@ class Lowerer {
     if (out.kind != Node::kOutput) throw FormatError("'output' is not an output-node");
     for (const Node& n : net_.nodes)
       if (n.kind == Node::kInput) inputs_.push_back(n.name);
-    Ref r = Flatten1(out.desc, "output");
-    if (!r.segment) throw UnsupportedError("the requested output is frame-level; this path produces one vector per chunk");
-    if (r.kind != Ref::kSegLayer && r.kind != Ref::kPool)
-      throw UnsupportedError("unsupported output expression");
-    if (plan_->pool_src < 0) throw UnsupportedError("no StatisticsPooling on the path to the output");
+    if (frame_output_) {
+      // nnet3-compute form: the output is a frame-level layer, optionally behind a LogSoftmax
+      const Desc* d = &out.desc;
+      if (d->kind == Desc::kNode) {
+        const Node& n = NodeByName(d->node);
+        if (n.kind == Node::kComponent && Comp(n).type == "LogSoftmaxComponent") {
+          plan_->frame_log_softmax = true;
+          d = &n.desc;
+        }
+      }
+      Ref r = Flatten1(*d, "output");
+      if (r.segment) throw UnsupportedError("the requested output is segment-level; use the extraction entry points");
+      if (r.kind != Ref::kFrameLayer) throw UnsupportedError("the output must be a layer of the network, not an input");
+      if (r.index != static_cast<int32_t>(plan_->frame.size()) - 1)
+        throw UnsupportedError("internal: output layer is not the last lowered layer");
+      plan_->frame_out = r.index;
+    } else {
+      Ref r = Flatten1(out.desc, "output");
+      if (!r.segment)
+        throw UnsupportedError("the requested output is frame-level; this path produces one vector per chunk");
+      if (r.kind != Ref::kSegLayer && r.kind != Ref::kPool) throw UnsupportedError("unsupported output expression");
+      if (plan_->pool_src < 0) throw UnsupportedError("no StatisticsPooling on the path to the output");
+    }
     // keep only the inputs that are reachable, in file order
     std::vector<std::string> names;
     std::vector<int32_t> dims, remap(inputs_.size(), -1);
@@ -651,11 +669,12 @@ class Lowerer {
   std::set<std::string> in_progress_;
   std::map<std::string, Ref> layer_memo_;
   bool include_variance_ = true;
+  bool frame_output_ = false;
 };
 
 }  // namespace
 
-Plan LoadNnet3Plan(const std::string& rxfilename, const std::string& output_node) {
+Plan LoadNnet3Plan(const std::string& rxfilename, const std::string& output_node, bool frame_output) {
   Nnet net = ReadNnet(rxfilename);
   if (!output_node.empty()) {
     Node nd;
@@ -670,7 +689,7 @@ Plan LoadNnet3Plan(const std::string& rxfilename, const std::string& output_node
     }
   }
   Plan plan;
-  Lowerer(net, &plan).Run();
+  Lowerer(net, &plan, frame_output).Run();
   plan.Finalize();
   return plan;
 }

@@ -47,8 +47,13 @@ void Plan::Finalize() {
     if (l.scale.size() != l.offset.size() || (!l.scale.empty() && static_cast<int32_t>(l.scale.size()) != l.out_dim))
       fail("frame layer " + l.name + ": scale/offset size");
   }
-  if (pool_src < 0 || pool_src >= static_cast<int32_t>(frame.size())) fail("pool_src out of range");
-  if (pool_left_context < 0 || pool_right_context < 0) fail("negative pooling context");
+  if (FrameOutput()) {
+    if (frame_out != static_cast<int32_t>(frame.size()) - 1) fail("frame_out must be the last frame layer");
+    if (pool_src >= 0 || !segment.empty()) fail("frame-output plans have no pooling or segment layers");
+  } else {
+    if (pool_src < 0 || pool_src >= static_cast<int32_t>(frame.size())) fail("pool_src out of range");
+    if (pool_left_context < 0 || pool_right_context < 0) fail("negative pooling context");
+  }
   int32_t d = PooledDim();
   for (Layer& l : segment) {
     if (l.in_dim != d) fail("segment layer " + l.name + ": in_dim " + std::to_string(l.in_dim) + " != " + std::to_string(d));
@@ -73,7 +78,10 @@ void Plan::Finalize() {
     }
     os << "}" << (l.relu ? " relu" : "") << (l.scale.empty() ? "" : " bn") << " ctx=" << l.left << "/" << l.right << "\n";
   }
-  os << "pool src=L" << pool_src << " window=[-" << pool_left_context << ",+" << pool_right_context << "] "
+  if (FrameOutput())
+    os << "frame output L" << frame_out << (frame_log_softmax ? " log-softmax" : "") << "\n";
+  else
+    os << "pool src=L" << pool_src << " window=[-" << pool_left_context << ",+" << pool_right_context << "] "
      << (pool_output_stddevs ? "mean+stddev" : "mean") << " floor=" << pool_variance_floor << "\n";
   for (size_t i = 0; i < segment.size(); ++i) {
     const Layer& l = segment[i];

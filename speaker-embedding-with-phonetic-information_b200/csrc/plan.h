@@ -36,11 +36,19 @@ struct Plan {
   bool pool_output_stddevs = true;
   float pool_variance_floor = 1e-10f;
   std::vector<Layer> segment;   // chain; taps unused
+  // Frame-output mode (nnet3-compute): no pooling; the result is frame layer
+  // `frame_out` at every frame of the utterance, optionally through a row-wise log-softmax.
+  int32_t frame_out = -1;
+  bool frame_log_softmax = false;
   std::string description;
 
   int32_t SrcDim(int32_t src) const { return src >= 0 ? frame[src].out_dim : input_dims[-1 - src]; }
-  int32_t PooledDim() const { return frame[pool_src].out_dim * (pool_output_stddevs ? 2 : 1); }
-  int32_t EmbeddingDim() const { return segment.empty() ? PooledDim() : segment.back().out_dim; }
+  bool FrameOutput() const { return frame_out >= 0; }
+  int32_t PooledDim() const { return FrameOutput() ? 0 : frame[pool_src].out_dim * (pool_output_stddevs ? 2 : 1); }
+  int32_t EmbeddingDim() const {
+    if (FrameOutput()) return frame[frame_out].out_dim;
+    return segment.empty() ? PooledDim() : segment.back().out_dim;
+  }
   int64_t MacPerFrame() const;
   int64_t MacPerChunk() const;
   // Validates indices/dims, fills Layer::left/right and `description`; throws std::runtime_error.

@@ -210,7 +210,9 @@ class _Builder:
     def output_layer(self, name: str, dim: int, input: str = "[-1]") -> None:
         desc = normalize_descriptor(input, self.prev, self.outs)
         in_dim = self._desc_dim(desc)
-        self._affine(f"{name}.affine", in_dim, dim, zero=True)   # param-stddev=0 bias-stddev=0
+        # xconfig initialises output layers with param-stddev=0 bias-stddev=0; random_outputs gives
+        # trained-looking heads for the frame-level (nnet3-compute) tests
+        self._affine(f"{name}.affine", in_dim, dim, zero=not getattr(self, "random_outputs", False))
         self.lines.append(f"component-node name={name}.affine component={name}.affine input={desc}")
         self.comps[f"{name}.log-softmax"] = Component("LogSoftmaxComponent", OrderedDict([
             ("Dim", dim), ("ValueAvg", np.zeros(0, np.float32)), ("DerivAvg", np.zeros(0, np.float32)),
@@ -264,13 +266,15 @@ SEGMENT_MAC_PER_CHUNK = 3000 * 512
 
 def make_model(topology: str, seed: int = 42, feat_dim: int = 23, am_feat_dim: int = 40,
                num_speakers: int = 64, num_senones: int = 96, max_chunk: int = 10000,
-               hidden: int = 512, stats_dim: int = 1500, am_hidden: int = 650, am_bottleneck: int = 128) -> Nnet3Model:
+               hidden: int = 512, stats_dim: int = 1500, am_hidden: int = 650, am_bottleneck: int = 128,
+               random_outputs: bool = False) -> Nnet3Model:
     """Random-init model file content for one of TOPOLOGIES (W~N(0,1/K),
     b~N(0,0.1^2), BN mean~N(0.3,0.1^2), var~U(0.05,0.5), count=1e5, eps=1e-3).
     hidden / stats_dim / am_* default to the reference's sizes; smaller values give
     same-shaped nets for small committed fixtures."""
     rng = np.random.default_rng(seed)
     b = _Builder(rng)
+    b.random_outputs = random_outputs
     H, S = hidden, stats_dim
     am = dict(hidden=am_hidden, bottleneck=am_bottleneck)
     if topology == "v2_xvector":

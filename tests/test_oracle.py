@@ -255,3 +255,23 @@ def test_prestep_oracle_window_rule():
     assert select_voiced(x, v).shape == (30, 3) and np.array_equal(select_voiced(x, v)[1], x[2])
     with pytest.raises(ValueError):
         select_voiced(x, v[:-1])
+
+
+def test_forward_frames_edges_and_interior(synth):
+    """forward_frames: interior frames equal the plain evaluation of the un-padded input, edge
+    frames equal the evaluation of an explicitly replicated input; log-softmax rows normalise."""
+    from oracle.nnet3_oracle import Oracle
+    m = synth.make_model("v4_cvector", seed=9, hidden=64, stats_dim=96, am_hidden=80, am_bottleneck=16,
+                         num_senones=40, random_outputs=True)
+    x = synth.make_features([60], 23, 4)
+    orc = Oracle(m, "tdnn5.batchnorm")
+    y = orc.forward_frames({"input": x})
+    L, R = orc.frame_context()
+    assert (L, R) == (13, 7) and y.shape == (60, 16)
+    inner, lo, fl = orc._evaluate({"input": x})
+    assert fl and lo == L and np.allclose(y[L:60 - R], inner)
+    xp = np.concatenate([np.repeat(x[:1], 20, 0), x, np.repeat(x[-1:], 20, 0)])
+    wide, lo2, _ = orc._evaluate({"input": xp})
+    assert np.allclose(wide[20 - lo2:20 - lo2 + 60], y)
+    lp = Oracle(m, "output_am.log-softmax").forward_frames({"input": x})
+    assert lp.shape == (60, 40) and np.allclose(np.exp(lp).sum(axis=1), 1.0)
