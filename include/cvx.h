@@ -200,6 +200,33 @@ int cvx_extract_raw(cvx_engine* engine, const float* const* raw_feats, const cvx
                     const int64_t* chunk_start, const int32_t* chunk_len, const int32_t* chunk_utt,
                     const float* chunk_weight, int64_t num_chunks, float* out, uint32_t flags);
 
+/* ------------------------------------------------- embedding post-step --
+ * Optional: the step immediately after the hot path in the reference's back-end
+ * (egs/sre/v5/run_sre10.sh:118-129), done on the device instead of by three more processes:
+ *   ivector-subtract-global-mean mean.vec ... | transform-vec transform.mat ... |
+ *   ivector-normalize-length ...
+ * y = T (v - mean) (or T [v - mean; 1] when transform_cols == dim + 1), then
+ * y *= sqrt(rows) / ||y||  (scaleup = 1, upstream's default) or 1 / ||y|| (scaleup = 0). */
+typedef struct cvx_vector_chain {
+  const float* mean;        /* [dim] host, or NULL: nothing subtracted */
+  const float* transform;   /* [transform_rows, transform_cols] row-major host, or NULL */
+  int32_t transform_rows, transform_cols;
+  int32_t normalize_length; /* ivector-normalize-length --normalize */
+  int32_t scaleup;          /* ivector-normalize-length --scaleup */
+} cvx_vector_chain;
+
+/* Installs (chain != NULL) or removes the post-step of an extraction engine: cvx_extract /
+ * cvx_extract_raw then return [num_utts, cvx_engine_output_dim()] vectors that went through
+ * the chain on the device (failed utterances stay all-zero).  mean / transform are copied. */
+int cvx_engine_set_vector_chain(cvx_engine* engine, const cvx_vector_chain* chain);
+int32_t cvx_engine_output_dim(const cvx_engine* engine);
+
+/* The chain alone on host vectors in [num_vectors, dim] -> out [num_vectors, transform ?
+ * transform_rows : dim]; ratios (may be NULL) receives per vector the factor
+ * ivector-normalize-length averages in its log (||y|| / sqrt(dim) with scaleup). */
+int cvx_transform_vectors(int32_t device, const float* in, int64_t num_vectors, int32_t dim,
+                          const cvx_vector_chain* chain, float* out, float* ratios);
+
 /* ------------------------------------------------- frame-level outputs --
  * Replaces DecodableNnetSimple::GetOutput over a whole utterance as nnet3-compute uses it
  * [UPSTREAM-RECALL nnet3/nnet-am-decodable-simple.cc]: utterance u owns rows

@@ -50,12 +50,36 @@ class KernelProfile(C.Structure):
                 ("flops", C.c_double), ("bytes", C.c_double)]
 
 
+class VectorChain(C.Structure):
+    _fields_ = [("mean", C.c_void_p), ("transform", C.c_void_p), ("transform_rows", C.c_int32),
+                ("transform_cols", C.c_int32), ("normalize_length", C.c_int32), ("scaleup", C.c_int32)]
+
+
+def _make_chain(mean, transform, normalize_length, scaleup):
+    """-> (VectorChain, keep-alive arrays)."""
+    ch = VectorChain()
+    keep = []
+    if mean is not None:
+        m = np.ascontiguousarray(mean, np.float32)
+        keep.append(m)
+        ch.mean = m.ctypes.data
+    if transform is not None:
+        t = np.ascontiguousarray(transform, np.float32)
+        keep.append(t)
+        ch.transform = t.ctypes.data
+        ch.transform_rows, ch.transform_cols = t.shape
+    ch.normalize_length = int(bool(normalize_length))
+    ch.scaleup = int(bool(scaleup))
+    return ch, keep
+
+
 #: every symbol include/cvx.h declares (tests check the library exports them all)
 ABI_SYMBOLS = [
     "cvx_last_error", "cvx_version", "cvx_model_load", "cvx_model_load_frames", "cvx_model_from_plan", "cvx_model_free",
     "cvx_model_get_info", "cvx_model_input_name", "cvx_model_input_dim", "cvx_model_describe",
     "cvx_engine_options_default", "cvx_engine_create", "cvx_engine_destroy", "cvx_extract",
-    "cvx_engine_last_chunk_embeddings", "cvx_extract_raw", "cvx_compute_frames", "cvx_test_prestep", "cvx_host_alloc", "cvx_host_free", "cvx_device_alloc",
+    "cvx_engine_last_chunk_embeddings", "cvx_extract_raw", "cvx_compute_frames", "cvx_engine_set_vector_chain", "cvx_engine_output_dim", "cvx_transform_vectors",
+    "cvx_test_prestep", "cvx_host_alloc", "cvx_host_free", "cvx_device_alloc",
     "cvx_device_free", "cvx_memcpy_h2d", "cvx_device_count", "cvx_engine_get_profile",
     "cvx_engine_reset_profile", "cvx_engine_launch_count", "cvx_engine_last_extract_ms", "cvx_test_tdnn_layer", "cvx_test_tdnn_layer_bench", "cvx_test_stats_pool",
 ]
@@ -99,6 +123,11 @@ def load_library() -> C.CDLL:
                                 C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_uint32]
     lib.cvx_compute_frames.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_int64, C.c_void_p, C.c_int32,
                                        C.c_void_p, C.c_uint32]
+    lib.cvx_engine_set_vector_chain.argtypes = [C.c_void_p, C.POINTER(VectorChain)]
+    lib.cvx_engine_output_dim.argtypes = [C.c_void_p]
+    lib.cvx_engine_output_dim.restype = C.c_int32
+    lib.cvx_transform_vectors.argtypes = [C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.POINTER(VectorChain), C.c_void_p,
+                                          C.c_void_p]
     lib.cvx_engine_last_chunk_embeddings.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
     lib.cvx_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
     lib.cvx_host_free.argtypes = [C.c_void_p]
@@ -237,6 +266,21 @@ class Extractor:
         except Exception:
             pass
 
+    # -- embedding post-step ----------------------------------------------
+    def set_vector_chain(self, mean=None, transform=None, normalize_length: bool = True, scaleup: bool = True,
+                         clear: bool = False) -> None:
+        """Install `ivector-subtract-global-mean | transform-vec | ivector-normalize-length` as a device
+        post-step of extract()/extract_chunks() (cvx_engine_set_vector_chain); clear=True removes it."""
+        if clear:
+            _check(self._lib.cvx_engine_set_vector_chain(self._h, None))
+            return
+        ch, keep = _make_chain(mean, transform, normalize_length, scaleup)
+        _check(self._lib.cvx_engine_set_vector_chain(self._h, C.byref(ch)))
+
+    @property
+    def output_dim(self) -> int:
+        return int(self._lib.cvx_engine_output_dim(self._h))
+
     # -- raw ABI call ------------------------------------------------------
     def extract_chunks(self, feats: Sequence, total_rows: int, chunk_start: np.ndarray, chunk_len: np.ndarray,
                        chunk_utt: np.ndarray, chunk_weight: Optional[np.ndarray], num_utts: int,
@@ -257,7 +301,7 @@ class Extractor:
         cl = np.ascontiguousarray(chunk_len, dtype=np.int32)
         cu = np.ascontiguousarray(chunk_utt, dtype=np.int32)
         cw = None if chunk_weight is None else np.ascontiguousarray(chunk_weight, dtype=np.float32)
-        E = self.model.info.embedding_dim
+        E = self.output_dim
         if out is None:
             out = np.zeros((num_utts, E), dtype=np.float32)
         out_ptr = out.ctypes.data_as(C.c_void_p) if isinstance(out, np.ndarray) else C.c_void_p(int(out))
@@ -376,6 +420,20 @@ def bench_tdnn_layer(rows: int, in_dim: int, offsets: Sequence[int], out_dim: in
     _check(lib.cvx_test_tdnn_layer_bench(device, PRECISION[precision], rows, in_dim, _ptr(offs), len(offs), out_dim,
                                          iters, C.byref(ms)))
     return ms.value
+
+
+def transform_vectors(vectors: np.ndarray, mean=None, transform=None, normalize_length: bool = True,
+                      scaleup: bool = True, device: int = 0) -> Tuple[np.ndarray, np.ndarray]:
+    """The back-end's per-vector chain on the device (cvx_transform_vectors):
+    subtract mean -> transform-vec -> ivector-normalize-length.  Returns (vectors, ratios)."""
+    lib = load_library()
+    v = np.ascontiguousarray(vectors, np.float32)
+    ch, keep = _make_chain(mean, transform, normalize_length, scaleup)
+    od = ch.transform_rows if transform is not None else v.shape[1]
+    out = np.zeros((v.shape[0], od), np.float32)
+    ratios = np.zeros(v.shape[0], np.float32)
+    _check(lib.cvx_transform_vectors(device, _ptr(v), v.shape[0], v.shape[1], C.byref(ch), _ptr(out), _ptr(ratios)))
+    return out, ratios
 
 
 def test_stats_pool(x: np.ndarray, begin: Sequence[int], end: Sequence[int], precision: str = "fp16",

@@ -127,6 +127,8 @@ int ExtractMain(int argc, const char* const* argv, bool multiple_input) {
     ParseOptions po(multiple_input ? usage_multi : usage_single);
 
     std::string use_gpu = "yes", output_node, nnet_config, precision = "fp16", names, vad_rspecifier;
+    std::string mean_vec, transform_mat;
+    bool normalize_length = false, scaleup = true;
     int32_t chunk_size = -1, min_chunk_size = 100, gpu_id = -1, cmn_window = 0, min_cmn_window = 100;
     bool cmn_center = true, cmn_norm_vars = false;
     int64_t batch_rows = 1 << 20, max_batch_rows = 0;
@@ -162,6 +164,14 @@ int ExtractMain(int argc, const char* const* argv, bool multiple_input) {
     po.Register("center", &cmn_center, "apply-cmvn-sliding --center");
     po.Register("min-cmn-window", &min_cmn_window, "apply-cmvn-sliding --min-cmn-window (only if --center=false)");
     po.Register("norm-vars", &cmn_norm_vars, "apply-cmvn-sliding --norm-vars (only false is supported)");
+    po.Register("mean-vec", &mean_vec,
+                "If set, subtract this vector from every embedding on the GPU (what piping the output through "
+                "ivector-subtract-global-mean <mean> does)");
+    po.Register("transform-mat", &transform_mat,
+                "If set, multiply every embedding by this matrix on the GPU, after --mean-vec (transform-vec, e.g. the LDA)");
+    po.Register("normalize-length", &normalize_length,
+                "If true, scale every embedding to length sqrt(dim) on the GPU, last (ivector-normalize-length)");
+    po.Register("scaleup", &scaleup, "ivector-normalize-length --scaleup");
     if (multiple_input) po.Register("name", &names, "Comma-separated input-node names, one per feature stream");
     po.Register("frame-subsampling-factor", &ign_i[0], "ignored");
     po.Register("extra-left-context", &ign_i[1], "ignored");
@@ -251,6 +261,31 @@ int ExtractMain(int argc, const char* const* argv, bool multiple_input) {
     cvx_engine* engine = nullptr;
     if (cvx_engine_create(model, &eo, &engine) != CVX_OK) throw KaldiError(std::string("creating the GPU engine: ") + cvx_last_error());
 
+    if (!mean_vec.empty() || !transform_mat.empty() || normalize_length) {
+      // the back-end's per-vector chain, applied before the embeddings leave the device
+      std::vector<float> mean;
+      Matrix tf;
+      cvx_vector_chain chain;
+      std::memset(&chain, 0, sizeof(chain));
+      if (!mean_vec.empty()) {
+        mean = ReadVectorFile(mean_vec);
+        if (static_cast<int32_t>(mean.size()) != info.embedding_dim)
+          throw KaldiError("--mean-vec has dim " + std::to_string(mean.size()) + ", the embeddings have dim " +
+                           std::to_string(info.embedding_dim));
+        chain.mean = mean.data();
+      }
+      if (!transform_mat.empty()) {
+        tf = ReadMatrixFile(transform_mat);
+        chain.transform = tf.Data();
+        chain.transform_rows = tf.rows;
+        chain.transform_cols = tf.cols;
+      }
+      chain.normalize_length = normalize_length ? 1 : 0;
+      chain.scaleup = scaleup ? 1 : 0;
+      if (cvx_engine_set_vector_chain(engine, &chain) != CVX_OK)
+        throw KaldiError(std::string("installing the vector post-step: ") + cvx_last_error());
+    }
+
     std::vector<std::unique_ptr<SequentialMatrixReader>> readers;
     for (int i = 0; i < num_inputs; ++i) readers.emplace_back(new SequentialMatrixReader(feat_rspecifiers[i]));
     VectorWriter writer(vector_wspecifier);
@@ -268,7 +303,7 @@ int ExtractMain(int argc, const char* const* argv, bool multiple_input) {
       // pin the whole batch up front: growing pinned memory step by step costs more than the I/O
       b.Reserve(batch_rows + batch_rows / 8 + 65536);
     }
-    const int32_t E = info.embedding_dim;
+    const int32_t E = cvx_engine_output_dim(engine);
     const int32_t ctx = info.left_context + info.right_context + 1;
     int64_t num_success = 0, num_fail = 0, frame_count = 0;
     auto t_start = std::chrono::steady_clock::now();

@@ -1,0 +1,4 @@
+// Drop-in for upstream Kaldi's ivector-normalize-length as called by egs/sre/v5/run_sre10.sh:107-129 and
+// egs/sre/v5/sid/nnet3/xvector/extract_xvectors_new.sh:102-108 (see vector_tools_main.cc).
+#include "extract_main.h"
+int main(int argc, char** argv) { return cvx::NormalizeLengthMain(argc, argv); }

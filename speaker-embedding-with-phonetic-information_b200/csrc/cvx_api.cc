@@ -200,6 +200,19 @@ int cvx_extract_raw(cvx_engine* engine, const float* const* raw_feats, const cvx
   });
 }
 
+int cvx_engine_set_vector_chain(cvx_engine* engine, const cvx_vector_chain* chain) {
+  if (!engine) return Fail(CVX_ERR_INVALID, "cvx_engine_set_vector_chain: NULL engine");
+  return Guard([&] { engine->impl->SetVectorChain(chain); });
+}
+
+int32_t cvx_engine_output_dim(const cvx_engine* engine) { return engine ? engine->impl->OutputDim() : -1; }
+
+int cvx_transform_vectors(int32_t device, const float* in, int64_t num_vectors, int32_t dim, const cvx_vector_chain* chain,
+                          float* out, float* ratios) {
+  if (!chain || (num_vectors > 0 && (!in || !out))) return Fail(CVX_ERR_INVALID, "cvx_transform_vectors: NULL argument");
+  return Guard([&] { cvx::TransformVectors(device, in, num_vectors, dim, *chain, out, ratios); });
+}
+
 int cvx_compute_frames(cvx_engine* engine, const float* const* feats, int32_t num_streams, int64_t total_rows,
                        const int64_t* utt_start, int32_t num_utts, float* out, uint32_t flags) {
   if (!engine) return Fail(CVX_ERR_INVALID, "cvx_compute_frames: NULL engine");

@@ -296,6 +296,9 @@ Engine::~Engine() {
   cudaDeviceSynchronize();
   for (Buffer& b : buffers_)
     if (b.ptr) cudaFree(b.ptr);
+  cudaFree(d_chain_mean_);
+  cudaFree(d_chain_tf_);
+  cudaFree(d_chain_out_);
   for (FrameOp& op : frame_ops_) {
     cudaFree(op.d_w);
     cudaFree(op.d_post);
@@ -722,8 +725,8 @@ void Engine::Extract(const float* const* feats, int32_t num_streams, int64_t tot
   const bool dev_in = (flags & CVX_FLAG_DEVICE_INPUT) != 0, dev_out = (flags & CVX_FLAG_DEVICE_OUTPUT) != 0;
   if (num_utts == 0) return;
   if (num_chunks == 0) {
-    if (dev_out) CVX_CUDA_CHECK(cudaMemset(out, 0, static_cast<size_t>(num_utts) * E * 4));
-    else std::memset(out, 0, static_cast<size_t>(num_utts) * E * 4);
+    if (dev_out) CVX_CUDA_CHECK(cudaMemset(out, 0, static_cast<size_t>(num_utts) * OutputDim() * 4));
+    else std::memset(out, 0, static_cast<size_t>(num_utts) * OutputDim() * 4);
     return;
   }
   for (int32_t s = 0; s < num_streams; ++s)
@@ -1014,15 +1017,109 @@ void Engine::Extract(const float* const* feats, int32_t num_streams, int64_t tot
   ProfBegin(kProfAverage, 0, static_cast<double>(num_chunks + num_utts) * E * 4);
   CVX_CUDA_CHECK(LaunchUttAverage(static_cast<const float*>(d_chunk_emb_), E, static_cast<const int64_t*>(d_utt_off_),
                                   static_cast<const float*>(d_weights_), num_utts,
-                                  dev_out ? out : static_cast<float*>(d_out_), compute_));
+                                  dev_out && !chain_on_ ? out : static_cast<float*>(d_out_), compute_));
   ProfEnd();
+  const void* result = d_out_;
+  if (chain_on_) {
+    // post-step on the device: the vectors leave as the back-end wants them
+    Grow(&d_chain_out_, &chain_out_cap_, static_cast<size_t>(num_utts) * chain_out_dim_ * 4);
+    float* dst = dev_out ? out : static_cast<float*>(d_chain_out_);
+    ProfBegin(kProfAverage, 0, static_cast<double>(num_utts) * (E + chain_out_dim_) * 4);
+    CVX_CUDA_CHECK(LaunchVectorChain(static_cast<const float*>(d_out_), num_utts, E, d_chain_mean_, d_chain_tf_,
+                                     chain_.transform_rows, chain_.transform_cols, chain_.normalize_length,
+                                     chain_.scaleup, /*keep_zero=*/1, dst, nullptr, compute_));
+    ProfEnd();
+    result = d_chain_out_;
+  }
   if (!dev_out)
-    CVX_CUDA_CHECK(cudaMemcpyAsync(out, d_out_, static_cast<size_t>(num_utts) * E * 4, cudaMemcpyDeviceToHost, compute_));
+    CVX_CUDA_CHECK(cudaMemcpyAsync(out, result, static_cast<size_t>(num_utts) * OutputDim() * 4, cudaMemcpyDeviceToHost, compute_));
   CVX_CUDA_CHECK(cudaEventRecord(call_end_, compute_));
   CVX_CUDA_CHECK(cudaStreamSynchronize(compute_));
   CVX_CUDA_CHECK(cudaEventElapsedTime(&last_call_ms_, call_begin_, call_end_));
   ProfResolve();
   last_num_chunks_ = num_chunks;
+}
+
+// ---------------------------------------------------------- post-step ----
+void ValidateVectorChain(const cvx_vector_chain& c, int32_t dim) {
+  if (c.transform) {
+    if (c.transform_rows <= 0) throw InvalidArgument("vector chain: transform_rows <= 0");
+    if (c.transform_cols != dim && c.transform_cols != dim + 1)
+      throw InvalidArgument("vector chain: the transform has " + std::to_string(c.transform_cols) + " columns, the vectors have dim " +
+                            std::to_string(dim) + " (expected dim or dim + 1)");
+  }
+  if (static_cast<size_t>(dim + (c.transform ? c.transform_rows : dim)) * 4 > 200 * 1024)
+    throw InvalidArgument("vector chain: dimensions too large");
+}
+
+void Engine::SetVectorChain(const cvx_vector_chain* chain) {
+  CVX_CUDA_CHECK(cudaSetDevice(opts_.device));
+  CVX_CUDA_CHECK(cudaStreamSynchronize(compute_));
+  if (plan_.FrameOutput()) throw InvalidArgument("the vector chain applies to extraction engines only");
+  cudaFree(d_chain_mean_);
+  cudaFree(d_chain_tf_);
+  d_chain_mean_ = d_chain_tf_ = nullptr;
+  chain_on_ = false;
+  if (!chain) return;
+  const int32_t E = plan_.EmbeddingDim();
+  ValidateVectorChain(*chain, E);
+  chain_ = *chain;
+  if (chain->mean) {
+    d_chain_mean_ = DevAlloc<float>(E);
+    CVX_CUDA_CHECK(cudaMemcpy(d_chain_mean_, chain->mean, static_cast<size_t>(E) * 4, cudaMemcpyHostToDevice));
+  }
+  if (chain->transform) {
+    const size_t n = static_cast<size_t>(chain->transform_rows) * chain->transform_cols;
+    d_chain_tf_ = DevAlloc<float>(n);
+    CVX_CUDA_CHECK(cudaMemcpy(d_chain_tf_, chain->transform, n * 4, cudaMemcpyHostToDevice));
+  }
+  chain_.mean = chain_.transform = nullptr;  // host pointers are not kept
+  chain_out_dim_ = chain->transform ? chain->transform_rows : E;
+  chain_on_ = true;
+}
+
+void TransformVectors(int32_t device, const float* in, int64_t n, int32_t dim, const cvx_vector_chain& c, float* out,
+                      float* ratios) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    throw CudaError("no usable CUDA device; this path has no CPU fallback");
+  if (device < 0 || device >= ndev) throw InvalidArgument("device ordinal out of range");
+  if (n < 0 || dim <= 0) throw InvalidArgument("bad vector count / dim");
+  if (n == 0) return;
+  ValidateVectorChain(c, dim);
+  CVX_CUDA_CHECK(cudaSetDevice(device));
+  const int32_t od = c.transform ? c.transform_rows : dim;
+  float *d_in = nullptr, *d_out = nullptr, *d_mean = nullptr, *d_tf = nullptr, *d_ratio = nullptr;
+  auto cleanup = [&] {
+    cudaFree(d_in);
+    cudaFree(d_out);
+    cudaFree(d_mean);
+    cudaFree(d_tf);
+    cudaFree(d_ratio);
+  };
+  try {
+    CVX_CUDA_CHECK(cudaMalloc(&d_in, static_cast<size_t>(n) * dim * 4));
+    CVX_CUDA_CHECK(cudaMalloc(&d_out, static_cast<size_t>(n) * od * 4));
+    CVX_CUDA_CHECK(cudaMemcpy(d_in, in, static_cast<size_t>(n) * dim * 4, cudaMemcpyHostToDevice));
+    if (c.mean) {
+      CVX_CUDA_CHECK(cudaMalloc(&d_mean, static_cast<size_t>(dim) * 4));
+      CVX_CUDA_CHECK(cudaMemcpy(d_mean, c.mean, static_cast<size_t>(dim) * 4, cudaMemcpyHostToDevice));
+    }
+    if (c.transform) {
+      const size_t sz = static_cast<size_t>(c.transform_rows) * c.transform_cols * 4;
+      CVX_CUDA_CHECK(cudaMalloc(&d_tf, sz));
+      CVX_CUDA_CHECK(cudaMemcpy(d_tf, c.transform, sz, cudaMemcpyHostToDevice));
+    }
+    if (ratios) CVX_CUDA_CHECK(cudaMalloc(&d_ratio, static_cast<size_t>(n) * 4));
+    CVX_CUDA_CHECK(LaunchVectorChain(d_in, n, dim, d_mean, d_tf, c.transform_rows, c.transform_cols, c.normalize_length,
+                                     c.scaleup, /*keep_zero=*/0, d_out, d_ratio, nullptr));
+    CVX_CUDA_CHECK(cudaMemcpy(out, d_out, static_cast<size_t>(n) * od * 4, cudaMemcpyDeviceToHost));
+    if (ratios) CVX_CUDA_CHECK(cudaMemcpy(ratios, d_ratio, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost));
+  } catch (...) {
+    cleanup();
+    throw;
+  }
+  cleanup();
 }
 
 // -------------------------------------------------------- frame outputs ----

@@ -67,6 +67,11 @@ class Engine {
   // repetitions of the frame pass on `rows` rows (CUDA events around each launch).
   double DebugBenchFrames(const float* const* feats, int64_t rows, int32_t iters);
 
+  // Post-step applied to the utterance embeddings on the device before they leave Extract()
+  // (subtract mean -> transform -> length normalisation); chain == NULL removes it.
+  void SetVectorChain(const cvx_vector_chain* chain);
+  int32_t OutputDim() const { return chain_on_ ? chain_out_dim_ : plan_.EmbeddingDim(); }
+
   int GetProfile(cvx_kernel_profile* recs, int32_t max_recs);
   void ResetProfile();
   int64_t launch_count() const { return launches_; }
@@ -168,6 +173,13 @@ class Engine {
   cudaEvent_t call_begin_ = nullptr, call_end_ = nullptr;
   float last_call_ms_ = 0.f;
 
+  bool chain_on_ = false;
+  cvx_vector_chain chain_ = {};
+  int32_t chain_out_dim_ = 0;
+  float *d_chain_mean_ = nullptr, *d_chain_tf_ = nullptr;
+  void* d_chain_out_ = nullptr;
+  size_t chain_out_cap_ = 0;
+
   bool profile_ = false;
   std::vector<PendingEvent> pending_;
   std::vector<cudaEvent_t> event_pool_;
@@ -175,6 +187,11 @@ class Engine {
   int64_t prof_launches_[kNumProf] = {};
   int64_t launches_ = 0;
 };
+
+// Stand-alone post-step on host vectors (cvx_transform_vectors).
+void TransformVectors(int32_t device, const float* in, int64_t num_vectors, int32_t dim, const cvx_vector_chain& chain,
+                      float* out, float* ratios);
+void ValidateVectorChain(const cvx_vector_chain& chain, int32_t dim);
 
 // Stand-alone pooling run for tests (cvx_test_stats_pool).
 void TestStatsPool(int32_t device, int32_t precision, const float* in, int64_t rows, int32_t dim, const int64_t* begin,

@@ -190,5 +190,11 @@ cudaError_t LaunchFrameOutput(const float* act, int32_t ld, int32_t dim, const i
                               int32_t left, int32_t right, int64_t rows, int32_t log_softmax, int32_t apply_exp,
                               float* out, cudaStream_t stream);
 
+// ---- embedding post-step (vector_chain.cu): subtract mean -> transform -> length normalisation ----
+// out [num_vectors, transform ? t_rows : dim]; ratios [num_vectors] or NULL
+cudaError_t LaunchVectorChain(const float* in, int64_t num_vectors, int32_t dim, const float* mean, const float* transform,
+                              int32_t t_rows, int32_t t_cols, int32_t normalize, int32_t scaleup, int32_t keep_zero,
+                              float* out, float* ratios, cudaStream_t stream);
+
 }  // namespace cvx
 #endif  // CVX_KERNELS_KERNELS_H_

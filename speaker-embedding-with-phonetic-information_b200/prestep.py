@@ -65,7 +65,7 @@ def extract_raw(ex: Extractor, raw: Dict[str, np.ndarray], lengths: Sequence[int
                 starts.append(int(kept_start[u]) + s); lens.append(n); utts.append(u)
                 ok[u] = True
     cs, cl, cu = np.array(starts, np.int64), np.array(lens, np.int32), np.array(utts, np.int32)
-    out = np.zeros((len(lengths), ex.model.info.embedding_dim), np.float32)
+    out = np.zeros((len(lengths), ex.output_dim), np.float32)
     _check(lib.cvx_extract_raw(ex._h, ptrs, pres, len(mats), mats[0].shape[0], _ptr(raw_start), _ptr(keep),
                                _ptr(kept_start), len(lengths), _ptr(cs), _ptr(cl), _ptr(cu), None, len(cs), _ptr(out), 0))
     return out, ok

@@ -275,3 +275,26 @@ def test_forward_frames_edges_and_interior(synth):
     assert np.allclose(wide[20 - lo2:20 - lo2 + 60], y)
     lp = Oracle(m, "output_am.log-softmax").forward_frames({"input": x})
     assert lp.shape == (60, 40) and np.allclose(np.exp(lp).sum(axis=1), 1.0)
+
+
+def test_backend_restatement_identities():
+    """oracle/backend_oracle.py: the chain composes its stages; lengths come out as sqrt(dim) / 1;
+    zero vectors are left alone; the affine transform form adds its last column."""
+    from oracle.backend_oracle import (normalize_length, speaker_means, subtract_global_mean, transform_vec,
+                                       vector_chain)
+    rng = np.random.default_rng(0)
+    v = rng.normal(0, 1, (9, 12))
+    mean, t = rng.normal(0, 1, 12), rng.normal(0, 1, (5, 12))
+    y, ratio = vector_chain(v, mean, t)
+    z, ratio2 = normalize_length(transform_vec(subtract_global_mean(v, mean), t))
+    assert np.allclose(y, z) and np.allclose(ratio, ratio2)
+    assert np.allclose(np.linalg.norm(y, axis=1), np.sqrt(5))
+    assert np.allclose(np.linalg.norm(normalize_length(v, scaleup=False)[0], axis=1), 1.0)
+    assert np.allclose(subtract_global_mean(v).mean(axis=0), 0)
+    ta = np.concatenate([t, np.ones((5, 1))], axis=1)
+    assert np.allclose(transform_vec(v, ta), transform_vec(v, t) + 1.0)
+    zz, rz = normalize_length(np.zeros((1, 4)))
+    assert np.all(zz == 0) and rz[0] == 0
+    means, counts, missing = speaker_means([("a", ["u0", "u1", "x"]), ("b", ["y"])], {"u0": v[0], "u1": v[1]})
+    assert [s for s, _ in means] == ["a"] and counts == [("a", 2)] and missing == 2
+    assert np.allclose(means[0][1], (v[0] + v[1]) / 2)
