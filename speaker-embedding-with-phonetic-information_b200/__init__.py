@@ -355,10 +355,11 @@ class Extractor:
         return out, ok
 
     def compute_frames(self, feats: Dict[str, np.ndarray], lengths: Sequence[int], apply_exp: bool = False,
-                       flags: int = 0) -> np.ndarray:
+                       flags: int = 0, out: Optional[np.ndarray] = None) -> np.ndarray:
         """Frame-output models: the output layer at every frame of every utterance, what
         `nnet3-compute [--apply-exp=true]` writes row for row (cvx_compute_frames).
-        feats: input-node name -> packed fp32 rows; lengths: rows per utterance."""
+        feats: input-node name -> packed fp32 rows; lengths: rows per utterance; out: optional
+        preallocated [rows, dim] fp32 result (a PinnedArray's .array for full PCIe speed)."""
         names = self.model.input_names
         mats = [np.ascontiguousarray(feats[n], dtype=np.float32) for n in names]
         start = np.zeros(len(lengths) + 1, dtype=np.int64)
@@ -367,7 +368,9 @@ class Extractor:
         ptrs = (C.c_void_p * len(mats))()
         for i, m in enumerate(mats):
             ptrs[i] = m.ctypes.data
-        out = np.zeros((total, self.model.info.embedding_dim), dtype=np.float32)
+        if out is None:
+            out = np.zeros((total, self.model.info.embedding_dim), dtype=np.float32)
+        assert out.dtype == np.float32 and out.flags.c_contiguous and out.shape == (total, self.model.info.embedding_dim)
         _check(self._lib.cvx_compute_frames(self._h, ptrs, len(mats), total, _ptr(start), len(lengths), _ptr(out),
                                             flags | (FLAG_APPLY_EXP if apply_exp else 0)))
         return out

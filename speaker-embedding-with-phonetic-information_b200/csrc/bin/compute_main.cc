@@ -28,7 +28,8 @@ struct FrameBatch {
   int32_t dim = 0;
   std::vector<std::string> keys;
   std::vector<int64_t> utt_start{0};
-  std::vector<float> out;
+  float* out = nullptr;  // pinned [out_cap]
+  size_t out_cap = 0;
 
   int64_t rows() const { return utt_start.back(); }
   void Reset() {
@@ -45,7 +46,19 @@ struct FrameBatch {
     feats = static_cast<float*>(p);
     cap_rows = ncap;
   }
-  ~FrameBatch() { cvx_host_free(feats); }
+  void ReserveOut(size_t n) {
+    if (n <= out_cap) return;
+    cvx_host_free(out);
+    out = nullptr;
+    void* p = nullptr;
+    if (cvx_host_alloc(&p, n * sizeof(float)) != CVX_OK) throw KaldiError(cvx_last_error());
+    out = static_cast<float*>(p);
+    out_cap = n;
+  }
+  ~FrameBatch() {
+    cvx_host_free(feats);
+    cvx_host_free(out);
+  }
 };
 
 }  // namespace
@@ -173,13 +186,13 @@ int ComputeMain(int argc, const char* const* argv) {
       worker = std::thread([&, which]() {
         try {
           FrameBatch& w = fb[which];
-          w.out.resize(static_cast<size_t>(w.rows()) * E);
+          w.ReserveOut(static_cast<size_t>(w.rows()) * E);
           const float* f[1] = {w.feats};
           if (cvx_compute_frames(engine, f, 1, w.rows(), w.utt_start.data(), static_cast<int32_t>(w.keys.size()),
-                                 w.out.data(), apply_exp ? CVX_FLAG_APPLY_EXP : 0) != CVX_OK)
+                                 w.out, apply_exp ? CVX_FLAG_APPLY_EXP : 0) != CVX_OK)
             throw KaldiError(std::string("cvx_compute_frames failed: ") + cvx_last_error());
           for (size_t u = 0; u < w.keys.size(); ++u)
-            writer.Write(w.keys[u], w.out.data() + static_cast<size_t>(w.utt_start[u]) * E,
+            writer.Write(w.keys[u], w.out + static_cast<size_t>(w.utt_start[u]) * E,
                          static_cast<int32_t>(w.utt_start[u + 1] - w.utt_start[u]), E);
         } catch (const std::exception& e) {
           worker_error = e.what();

@@ -299,6 +299,15 @@ Engine::~Engine() {
   cudaFree(d_chain_mean_);
   cudaFree(d_chain_tf_);
   cudaFree(d_chain_out_);
+  cudaFree(d_frame_out_[0]);
+  cudaFree(d_frame_out_[1]);
+  if (d2h_) {
+    cudaStreamDestroy(d2h_);
+    for (int i = 0; i < 2; ++i) {
+      cudaEventDestroy(out_ready_[i]);
+      cudaEventDestroy(out_free_[i]);
+    }
+  }
   for (FrameOp& op : frame_ops_) {
     cudaFree(op.d_w);
     cudaFree(op.d_post);
@@ -1146,10 +1155,16 @@ void Engine::ComputeFrames(const float* const* feats, int32_t num_streams, int64
   const int32_t left = OL.left, right = OL.right, pad = left + right, E = OL.out_dim;
   const int32_t ld32 = RoundUp(E, 4);
   // batch = whole utterances; padded rows per batch bounded by max_batch_rows and by 4 GB of fp32 output
-  int64_t cap = std::min<int64_t>(max_batch_rows_, std::max<int64_t>((int64_t{1} << 30) / ld32, kGemmBlockM));
-  CVX_CUDA_CHECK(cudaEventRecord(call_begin_, compute_));
-  int32_t u0 = 0;
-  while (u0 < num_utts) {
+  const int64_t cap = std::min<int64_t>(max_batch_rows_, std::max<int64_t>((int64_t{1} << 30) / ld32, kGemmBlockM));
+  struct FBatch {
+    int32_t u0, u1;
+    int64_t rows_c, rows_p;
+    size_t off_pos;  // position of its utt_start copy in `rel`
+  };
+  std::vector<FBatch> batches;
+  std::vector<int64_t> rel;  // per batch: utterance starts relative to the batch, n + 1 entries
+  int64_t max_c = 0, max_p = 0;
+  for (int32_t u0 = 0; u0 < num_utts;) {
     int32_t u1 = u0;
     int64_t rows_p = 0;
     while (u1 < num_utts) {
@@ -1158,62 +1173,100 @@ void Engine::ComputeFrames(const float* const* feats, int32_t num_streams, int64
       rows_p += add;
       ++u1;
     }
-    const int32_t nu = u1 - u0;
-    const int64_t r0 = utt_start[u0], rows_c = utt_start[u1] - r0;
-    EnsureRows(rows_p);
-    std::vector<int64_t> rel(nu + 1);
-    for (int32_t u = 0; u <= nu; ++u) rel[u] = utt_start[u0 + u] - r0;
-    Grow(&d_utt_off_, &utt_off_cap_, rel.size() * 8);
-    CVX_CUDA_CHECK(cudaMemcpyAsync(d_utt_off_, rel.data(), rel.size() * 8, cudaMemcpyHostToDevice, compute_));
+    FBatch fb{u0, u1, utt_start[u1] - utt_start[u0], rows_p, rel.size()};
+    for (int32_t u = u0; u <= u1; ++u) rel.push_back(utt_start[u] - utt_start[u0]);
+    max_c = std::max(max_c, fb.rows_c);
+    max_p = std::max(max_p, fb.rows_p);
+    batches.push_back(fb);
+    u0 = u1;
+  }
+  EnsureRows(max_p);
+  if (!d2h_) {
+    CVX_CUDA_CHECK(cudaStreamCreateWithFlags(&d2h_, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      CVX_CUDA_CHECK(cudaEventCreateWithFlags(&out_ready_[i], cudaEventDisableTiming));
+      CVX_CUDA_CHECK(cudaEventCreateWithFlags(&out_free_[i], cudaEventDisableTiming));
+    }
+  }
+  Grow(&d_utt_off_, &utt_off_cap_, rel.size() * 8);
+  CVX_CUDA_CHECK(cudaMemcpyAsync(d_utt_off_, rel.data(), rel.size() * 8, cudaMemcpyHostToDevice, compute_));
+  for (int32_t s = 0; s < num_streams; ++s) {
+    if (!dev_in)
+      for (int i = 0; i < 2; ++i) Grow(&d_feat_[i][s], &d_feat_cap_[i][s], static_cast<size_t>(max_c) * plan_.input_dims[s] * 4);
+    if (pad > 0) Grow(&d_sel_[s], &sel_cap_[s], static_cast<size_t>(max_p) * plan_.input_dims[s] * 4);
+  }
+  if (elem_ != kF32) Grow(&d_stats_, &stats_cap_, static_cast<size_t>(max_p) * ld32 * 4);
+  if (!dev_out)
+    for (int i = 0; i < 2; ++i) Grow(&d_frame_out_[i], &frame_out_cap_[i], static_cast<size_t>(max_c) * E * 4);
+  CVX_CUDA_CHECK(cudaStreamSynchronize(compute_));  // `rel` is pageable: its copy must have run
+
+  // Three streams: H2D of batch i+1 and D2H of batch i-1 overlap the frame pass of batch i.
+  CVX_CUDA_CHECK(cudaEventRecord(call_begin_, compute_));
+  for (size_t bi = 0; bi < batches.size(); ++bi) {
+    const FBatch& b = batches[bi];
+    const int slot = static_cast<int>(bi & 1);
+    const int32_t nu = b.u1 - b.u0;
+    const int64_t r0 = utt_start[b.u0];
+    const int64_t* d_rel = static_cast<const int64_t*>(d_utt_off_) + b.off_pos;
     const float* dev[kMaxASources] = {};
+    if (!dev_in) {
+      if (bi >= 2) CVX_CUDA_CHECK(cudaStreamWaitEvent(copy_, feat_free_[slot], 0));
+      for (int32_t s = 0; s < num_streams; ++s) {
+        const int32_t dim = plan_.input_dims[s];
+        CVX_CUDA_CHECK(cudaMemcpyAsync(d_feat_[slot][s], feats[s] + r0 * dim, static_cast<size_t>(b.rows_c) * dim * 4,
+                                       cudaMemcpyHostToDevice, copy_));
+      }
+      CVX_CUDA_CHECK(cudaEventRecord(feat_ready_[slot], copy_));
+      CVX_CUDA_CHECK(cudaStreamWaitEvent(compute_, feat_ready_[slot], 0));
+    }
     for (int32_t s = 0; s < num_streams; ++s) {
       const int32_t dim = plan_.input_dims[s];
-      const float* src = feats[s] + r0 * dim;
-      if (!dev_in) {
-        Grow(&d_feat_[0][s], &d_feat_cap_[0][s], static_cast<size_t>(rows_c) * dim * 4);
-        CVX_CUDA_CHECK(cudaMemcpyAsync(d_feat_[0][s], src, static_cast<size_t>(rows_c) * dim * 4, cudaMemcpyHostToDevice, compute_));
-        src = static_cast<const float*>(d_feat_[0][s]);
-      }
+      const float* src = dev_in ? feats[s] + r0 * dim : static_cast<const float*>(d_feat_[slot][s]);
       if (pad > 0) {
-        Grow(&d_sel_[s], &sel_cap_[s], static_cast<size_t>(rows_p) * dim * 4);
-        ProfBegin(kProfStage, 0, static_cast<double>(rows_c + rows_p) * dim * 4.0);
-        CVX_CUDA_CHECK(LaunchPadEdges(src, dim, static_cast<const int64_t*>(d_utt_off_), nu, left, right, rows_p,
-                                      static_cast<float*>(d_sel_[s]), compute_));
+        ProfBegin(kProfStage, 0, static_cast<double>(b.rows_c + b.rows_p) * dim * 4.0);
+        CVX_CUDA_CHECK(LaunchPadEdges(src, dim, d_rel, nu, left, right, b.rows_p, static_cast<float*>(d_sel_[s]), compute_));
         ProfEnd();
         src = static_cast<const float*>(d_sel_[s]);
       }
       dev[s] = src;
     }
+    // with padding the frame pass reads d_sel_, so the raw rows are free as soon as the pad kernels ran
+    if (!dev_in && pad > 0) CVX_CUDA_CHECK(cudaEventRecord(feat_free_[slot], compute_));
     const float* act = nullptr;
     int32_t act_ld = 0;
     if (elem_ == kF32) {
-      RunFrames(dev, rows_p, 0, rows_p);
-      const Buffer& b = buffers_[frame_ops_.back().out_buffer];
-      act = static_cast<const float*>(b.ptr);
-      act_ld = b.ld;
+      RunFrames(dev, b.rows_p, 0, b.rows_p);
+      const Buffer& ob = buffers_[frame_ops_.back().out_buffer];
+      act = static_cast<const float*>(ob.ptr);
+      act_ld = ob.ld;
     } else {
-      Grow(&d_stats_, &stats_cap_, static_cast<size_t>(rows_p) * ld32 * 4);
-      RunFrames(dev, rows_p, 0, rows_p, nullptr, static_cast<float*>(d_stats_), ld32);
+      RunFrames(dev, b.rows_p, 0, b.rows_p, nullptr, static_cast<float*>(d_stats_), ld32);
       act = static_cast<const float*>(d_stats_);
       act_ld = ld32;
     }
-    float* dst = out + r0 * E;
-    if (!dev_out) {
-      Grow(&d_out_, &out_cap_, static_cast<size_t>(rows_c) * E * 4);
-      dst = static_cast<float*>(d_out_);
-    }
-    ProfBegin(kProfAverage, 0, static_cast<double>(rows_c) * E * 8.0);
-    CVX_CUDA_CHECK(LaunchFrameOutput(act, act_ld, E, static_cast<const int64_t*>(d_utt_off_), nu, left, right, rows_c,
-                                     plan_.frame_log_softmax ? 1 : 0, (flags & CVX_FLAG_APPLY_EXP) ? 1 : 0, dst, compute_));
+    if (!dev_in && pad == 0) CVX_CUDA_CHECK(cudaEventRecord(feat_free_[slot], compute_));
+    float* dst = dev_out ? out + r0 * E : static_cast<float*>(d_frame_out_[slot]);
+    if (!dev_out && bi >= 2) CVX_CUDA_CHECK(cudaStreamWaitEvent(compute_, out_free_[slot], 0));
+    ProfBegin(kProfAverage, 0, static_cast<double>(b.rows_c) * E * 8.0);
+    CVX_CUDA_CHECK(LaunchFrameOutput(act, act_ld, E, d_rel, nu, left, right, b.rows_c, plan_.frame_log_softmax ? 1 : 0,
+                                     (flags & CVX_FLAG_APPLY_EXP) ? 1 : 0, dst, compute_));
     ProfEnd();
-    if (!dev_out)
-      CVX_CUDA_CHECK(cudaMemcpyAsync(out + r0 * E, d_out_, static_cast<size_t>(rows_c) * E * 4, cudaMemcpyDeviceToHost, compute_));
-    // the next batch reuses d_utt_off_ / d_feat_ / d_out_: finish this one first
-    CVX_CUDA_CHECK(cudaStreamSynchronize(compute_));
-    u0 = u1;
+    if (!dev_out) {
+      CVX_CUDA_CHECK(cudaEventRecord(out_ready_[slot], compute_));
+      CVX_CUDA_CHECK(cudaStreamWaitEvent(d2h_, out_ready_[slot], 0));
+      CVX_CUDA_CHECK(cudaMemcpyAsync(out + r0 * E, d_frame_out_[slot], static_cast<size_t>(b.rows_c) * E * 4,
+                                     cudaMemcpyDeviceToHost, d2h_));
+      CVX_CUDA_CHECK(cudaEventRecord(out_free_[slot], d2h_));
+    }
+  }
+  if (!dev_out) {  // the call ends when the last results are on the host
+    CVX_CUDA_CHECK(cudaEventRecord(out_ready_[0], d2h_));
+    CVX_CUDA_CHECK(cudaStreamWaitEvent(compute_, out_ready_[0], 0));
   }
   CVX_CUDA_CHECK(cudaEventRecord(call_end_, compute_));
   CVX_CUDA_CHECK(cudaStreamSynchronize(compute_));
+  CVX_CUDA_CHECK(cudaStreamSynchronize(copy_));
+  CVX_CUDA_CHECK(cudaStreamSynchronize(d2h_));
   CVX_CUDA_CHECK(cudaEventElapsedTime(&last_call_ms_, call_begin_, call_end_));
   ProfResolve();
 }

@@ -173,6 +173,12 @@ class Engine {
   cudaEvent_t call_begin_ = nullptr, call_end_ = nullptr;
   float last_call_ms_ = 0.f;
 
+  // frame-output mode: results leave on their own stream from two alternating buffers
+  cudaStream_t d2h_ = nullptr;
+  cudaEvent_t out_ready_[2] = {nullptr, nullptr}, out_free_[2] = {nullptr, nullptr};
+  void* d_frame_out_[2] = {nullptr, nullptr};
+  size_t frame_out_cap_[2] = {0, 0};
+
   bool chain_on_ = false;
   cvx_vector_chain chain_ = {};
   int32_t chain_out_dim_ = 0;
