@@ -10,13 +10,15 @@
 //
 // Chunking / averaging follows nnet3-xvector-compute.cc main();
 // the forward pass itself goes through the C ABI (include/cvx.h) to the CUDA side.
-// Utterances are packed into row batches; a worker thread runs cvx_extract on one
-// batch while the main thread keeps reading the feature pipe(s) into the other.
+// Utterances are packed into row batches; worker threads (one per GPU in use, --num-gpus) run
+// cvx_extract on full batches while the main thread keeps reading the feature pipe(s) into a
+// free one; results are written in launch order.
 #include "extract_main.h"
 
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <fstream>
 #include <memory>
 #include <thread>
@@ -129,7 +131,7 @@ int ExtractMain(int argc, const char* const* argv, bool multiple_input) {
     std::string use_gpu = "yes", output_node, nnet_config, precision = "fp16", names, vad_rspecifier;
     std::string mean_vec, transform_mat;
     bool normalize_length = false, scaleup = true;
-    int32_t chunk_size = -1, min_chunk_size = 100, gpu_id = -1, cmn_window = 0, min_cmn_window = 100;
+    int32_t chunk_size = -1, min_chunk_size = 100, gpu_id = -1, cmn_window = 0, min_cmn_window = 100, num_gpus = 1;
     bool cmn_center = true, cmn_norm_vars = false;
     int64_t batch_rows = 1 << 20, max_batch_rows = 0;
     bool pad_input = false, profile = false;
@@ -152,6 +154,9 @@ int ExtractMain(int argc, const char* const* argv, bool multiple_input) {
     po.Register("nnet-config", &nnet_config, "File with an 'output-node name=output input=...' line (extract.config)");
     po.Register("precision", &precision, "TDNN operand type: fp16 | bf16 | fp32 (fp32 = slow validation kernels)");
     po.Register("gpu-id", &gpu_id, "CUDA device ordinal (-1: $CVX_DEVICE or 0)");
+    po.Register("num-gpus", &num_gpus,
+                "Use this many GPUs (devices gpu-id .. gpu-id + num-gpus - 1) from ONE process: row batches go to the "
+                "GPUs in turn, one worker thread and engine per GPU; output order is unchanged");
     po.Register("batch-rows", &batch_rows, "Frames read from the feature pipe(s) per cvx_extract call");
     po.Register("max-batch-rows", &max_batch_rows, "Frames per packed device batch (0 = engine default)");
     po.Register("profile", &profile, "Print per-kernel CUDA-event times at the end");
@@ -258,8 +263,20 @@ int ExtractMain(int argc, const char* const* argv, bool multiple_input) {
     eo.precision = prec;
     eo.max_batch_rows = max_batch_rows;
     eo.profile = profile ? 1 : 0;
-    cvx_engine* engine = nullptr;
-    if (cvx_engine_create(model, &eo, &engine) != CVX_OK) throw KaldiError(std::string("creating the GPU engine: ") + cvx_last_error());
+    if (num_gpus < 1) throw KaldiError("--num-gpus must be >= 1");
+    int32_t ndev = 0;
+    if (cvx_device_count(&ndev) != CVX_OK) throw KaldiError(std::string("no usable CUDA device: ") + cvx_last_error());
+    if (gpu_id + num_gpus > ndev)
+      throw KaldiError("--gpu-id=" + std::to_string(gpu_id) + " --num-gpus=" + std::to_string(num_gpus) + " but only " +
+                       std::to_string(ndev) + " CUDA device(s) are visible");
+    // one engine per GPU (SURVEY 8e mode ii); engines share nothing, there is no collective
+    std::vector<cvx_engine*> engines(num_gpus, nullptr);
+    for (int g = 0; g < num_gpus; ++g) {
+      eo.device = gpu_id + g;
+      if (cvx_engine_create(model, &eo, &engines[g]) != CVX_OK)
+        throw KaldiError(std::string("creating the GPU engine: ") + cvx_last_error());
+    }
+    cvx_engine* engine = engines[0];
 
     if (!mean_vec.empty() || !transform_mat.empty() || normalize_length) {
       // the back-end's per-vector chain, applied before the embeddings leave the device
@@ -282,8 +299,9 @@ int ExtractMain(int argc, const char* const* argv, bool multiple_input) {
       }
       chain.normalize_length = normalize_length ? 1 : 0;
       chain.scaleup = scaleup ? 1 : 0;
-      if (cvx_engine_set_vector_chain(engine, &chain) != CVX_OK)
-        throw KaldiError(std::string("installing the vector post-step: ") + cvx_last_error());
+      for (cvx_engine* e : engines)
+        if (cvx_engine_set_vector_chain(e, &chain) != CVX_OK)
+          throw KaldiError(std::string("installing the vector post-step: ") + cvx_last_error());
     }
 
     std::vector<std::unique_ptr<SequentialMatrixReader>> readers;
@@ -294,7 +312,8 @@ int ExtractMain(int argc, const char* const* argv, bool multiple_input) {
     std::vector<cvx_prestep> prestep(num_inputs);
     for (int s = 0; s < num_inputs; ++s) prestep[s] = cvx_prestep{s == 0 ? cmn_window : 0, cmn_center ? 1 : 0, min_cmn_window, 0};
 
-    HostBatch hb[2];
+    // one batch being filled + one in flight per GPU
+    std::vector<HostBatch> hb(num_gpus + 1);
     for (HostBatch& b : hb) {
       b.feats.assign(num_inputs, nullptr);
       b.cap_rows.assign(num_inputs, 0);
@@ -308,48 +327,67 @@ int ExtractMain(int argc, const char* const* argv, bool multiple_input) {
     int64_t num_success = 0, num_fail = 0, frame_count = 0;
     auto t_start = std::chrono::steady_clock::now();
 
-    std::thread worker;
+    // Jobs finish in launch order (outputs keep the input order); job k runs on GPU k mod num_gpus.
+    struct Job {
+      int batch = -1;
+      std::thread th;
+      int status = CVX_OK;
+      std::string error;
+    };
+    std::deque<std::unique_ptr<Job>> inflight;
     struct Joiner {
-      std::thread& t;
+      std::deque<std::unique_ptr<Job>>& q;
       ~Joiner() {
-        if (t.joinable()) t.join();
+        for (auto& j : q)
+          if (j->th.joinable()) j->th.join();
       }
-    } joiner{worker};
-    int worker_status = CVX_OK;
-    std::string worker_error;
-    int inflight = -1;
-    auto finish_inflight = [&]() {
-      if (inflight < 0) return;
-      worker.join();
-      if (worker_status != CVX_OK) throw KaldiError("cvx_extract failed: " + worker_error);
-      HostBatch& b = hb[inflight];
+    } joiner{inflight};
+    std::vector<int> free_batches;
+    for (int i = 1; i <= num_gpus; ++i) free_batches.push_back(i);
+    int64_t launch_seq = 0;
+    auto finish_oldest = [&]() {
+      if (inflight.empty()) return;
+      std::unique_ptr<Job> job = std::move(inflight.front());
+      inflight.pop_front();
+      job->th.join();
+      if (job->status != CVX_OK) throw KaldiError("cvx_extract failed: " + job->error);
+      HostBatch& b = hb[job->batch];
       for (size_t u = 0; u < b.keys.size(); ++u) writer.Write(b.keys[u], b.out.data() + u * E, E);
       num_success += static_cast<int64_t>(b.keys.size());
       frame_count += b.frames;
       b.Reset();
-      inflight = -1;
+      free_batches.push_back(job->batch);
     };
-    auto launch = [&](int which) {
+    // Hands batch `which` to the next GPU and returns the index of a free batch to fill next.
+    auto launch = [&](int which) -> int {
       HostBatch& b = hb[which];
-      if (b.keys.empty()) return;
-      finish_inflight();
+      if (b.keys.empty()) return which;
+      // the GPU this job goes to is the one the oldest job in flight runs on
+      if (static_cast<int>(inflight.size()) == num_gpus) finish_oldest();
       b.out.assign(b.keys.size() * static_cast<size_t>(E), 0.f);
-      inflight = which;
-      worker = std::thread([&, which]() {
+      cvx_engine* eng = engines[launch_seq++ % num_gpus];
+      std::unique_ptr<Job> job(new Job);
+      job->batch = which;
+      Job* jp = job.get();
+      job->th = std::thread([&, which, eng, jp]() {
         HostBatch& w = hb[which];
         std::vector<const float*> f(w.feats.begin(), w.feats.end());
         if (raw_mode)
-          worker_status = cvx_extract_raw(engine, f.data(), prestep.data(), num_inputs, w.rows, w.utt_raw_start.data(),
-                                          vad_reader ? w.keep.data() : nullptr, w.utt_kept_start.data(),
-                                          static_cast<int32_t>(w.keys.size()), w.chunk_start.data(), w.chunk_len.data(),
-                                          w.chunk_utt.data(), w.chunk_weight.data(),
-                                          static_cast<int64_t>(w.chunk_start.size()), w.out.data(), 0);
+          jp->status = cvx_extract_raw(eng, f.data(), prestep.data(), num_inputs, w.rows, w.utt_raw_start.data(),
+                                       vad_reader ? w.keep.data() : nullptr, w.utt_kept_start.data(),
+                                       static_cast<int32_t>(w.keys.size()), w.chunk_start.data(), w.chunk_len.data(),
+                                       w.chunk_utt.data(), w.chunk_weight.data(),
+                                       static_cast<int64_t>(w.chunk_start.size()), w.out.data(), 0);
         else
-          worker_status = cvx_extract(engine, f.data(), num_inputs, w.rows, w.chunk_start.data(), w.chunk_len.data(),
-                                      w.chunk_utt.data(), w.chunk_weight.data(), static_cast<int64_t>(w.chunk_start.size()),
-                                      static_cast<int32_t>(w.keys.size()), w.out.data(), 0);
-        if (worker_status != CVX_OK) worker_error = cvx_last_error();
+          jp->status = cvx_extract(eng, f.data(), num_inputs, w.rows, w.chunk_start.data(), w.chunk_len.data(),
+                                   w.chunk_utt.data(), w.chunk_weight.data(), static_cast<int64_t>(w.chunk_start.size()),
+                                   static_cast<int32_t>(w.keys.size()), w.out.data(), 0);
+        if (jp->status != CVX_OK) jp->error = cvx_last_error();
       });
+      inflight.push_back(std::move(job));
+      const int next = free_batches.back();
+      free_batches.pop_back();
+      return next;
     };
 
     int cur = 0;
@@ -488,16 +526,12 @@ int ExtractMain(int argc, const char* const* argv, bool multiple_input) {
       if (!ok) ++num_fail;
       for (int i = 0; i < num_inputs; ++i) readers[i]->Next();
       if (vad_reader) vad_reader->Next();
-      if (hb[cur].rows >= batch_rows) {
-        launch(cur);
-        cur ^= 1;
-        if (inflight == cur) finish_inflight();
-      }
+      if (hb[cur].rows >= batch_rows) cur = launch(cur);
     }
     for (int i = 1; i < num_inputs; ++i)
       if (!readers[i]->Done()) CVX_WARN("feature stream " << (i + 1) << " has extra utterances after the first stream ended");
     launch(cur);
-    finish_inflight();
+    while (!inflight.empty()) finish_oldest();
     for (auto& r : readers) {
       int st = r->Close();
       if (st != 0) CVX_WARN("a feature input pipe exited with status " << st);
@@ -508,16 +542,17 @@ int ExtractMain(int argc, const char* const* argv, bool multiple_input) {
     CVX_LOG("Time taken " << elapsed << "s: real-time factor assuming 100 frames/sec is "
                           << (frame_count > 0 ? elapsed * 100.0 / static_cast<double>(frame_count) : 0.0));
     CVX_LOG("Done " << num_success << " utterances, failed for " << num_fail);
-    if (profile) {
+    for (int g = 0; profile && g < num_gpus; ++g) {
       cvx_kernel_profile recs[16];
       int32_t n = 0;
-      cvx_engine_get_profile(engine, recs, 16, &n);
+      cvx_engine_get_profile(engines[g], recs, 16, &n);
       for (int32_t i = 0; i < n; ++i)
-        CVX_LOG("profile " << recs[i].name << ": launches=" << recs[i].launches << " ms=" << recs[i].total_ms
-                           << (recs[i].flops > 0 ? " TFLOP/s=" + std::to_string(recs[i].flops / recs[i].total_ms * 1e-9) : "")
-                           << (recs[i].bytes > 0 ? " GB/s=" + std::to_string(recs[i].bytes / recs[i].total_ms * 1e-6) : ""));
+        CVX_LOG("profile gpu" << (gpu_id + g) << " " << recs[i].name << ": launches=" << recs[i].launches
+                              << " ms=" << recs[i].total_ms
+                              << (recs[i].flops > 0 ? " TFLOP/s=" + std::to_string(recs[i].flops / recs[i].total_ms * 1e-9) : "")
+                              << (recs[i].bytes > 0 ? " GB/s=" + std::to_string(recs[i].bytes / recs[i].total_ms * 1e-6) : ""));
     }
-    cvx_engine_destroy(engine);
+    for (cvx_engine* e : engines) cvx_engine_destroy(e);
     cvx_model_free(model);
     return num_success != 0 ? 0 : 1;
   } catch (const std::exception& e) {

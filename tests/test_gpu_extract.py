@@ -297,3 +297,24 @@ def test_cli_reads_compressed_feature_archives(cvx, kf, synth, model_dir, requir
     ref, ok = extract_all(Oracle(model, "tdnn6.affine", np.float64), {"input": deq}, lengths, chunk_size=200, min_chunk_size=25)
     rr, cc = parity_metrics(got, ref[ok])
     assert rr <= TOL_REL and cc >= TOL_COS, (rr, cc)
+
+
+def test_cli_num_gpus_is_checked_against_visible_devices(cvx, require_gpu, tmp_path):
+    """--num-gpus beyond the visible devices is refused before any work (SURVEY 8e mode ii)."""
+    import os
+    import subprocess
+    g = os.path.join(os.path.dirname(__file__), "golden")
+    exe = os.path.join(cvx.BIN_DIR, "nnet3-xvector-compute")
+    n = cvx.device_count()
+    r = subprocess.run([exe, f"--num-gpus={n + 1}", "--output-node=tdnn6.affine", f"{g}/v2_small_final.raw",
+                        f"ark:{g}/v2_small_feats.ark", f"ark:{tmp_path}/x.ark"], capture_output=True, text=True, timeout=300)
+    assert r.returncode != 0 and "CUDA device(s) are visible" in r.stderr
+    # all visible devices from one process: same archive as one device
+    outs = []
+    for k in (1, n):
+        r = subprocess.run([exe, f"--num-gpus={k}", "--batch-rows=300", "--min-chunk-size=25", "--chunk-size=200",
+                            "--output-node=tdnn6.affine", f"{g}/v2_small_final.raw", f"ark:{g}/v2_small_feats.ark",
+                            f"ark:{tmp_path}/x{k}.ark"], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr
+        outs.append(open(f"{tmp_path}/x{k}.ark", "rb").read())
+    assert outs[0] == outs[1]

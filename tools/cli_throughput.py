@@ -18,6 +18,7 @@ kf = importlib.import_module(P + ".kaldi_format")
 sy = importlib.import_module(P + ".synth")
 
 n_utts = int(sys.argv[1]) if len(sys.argv) > 1 else 400
+num_gpus = int(sys.argv[2]) if len(sys.argv) > 2 else 1   # > 1: also run --num-gpus=N and compare the archives
 d = tempfile.mkdtemp(prefix="cvx_cli_")
 model = os.path.join(d, "final.raw")
 kf.write_nnet3(model, sy.make_model("v5_cvector"), binary=True)
@@ -38,3 +39,15 @@ for label, feat in (("ark file", f"ark:{ark}"), ("ark through a pipe", f"ark:cat
     tail = [ln for ln in r.stderr.splitlines() if "Time taken" in ln or "Done " in ln]
     print(f"{label}: {frames} frames ({os.path.getsize(ark) / 1e9:.2f} GB) in {dt:.2f} s wall -> {frames / 100 / dt:,.0f} audio-s/s | "
           + " | ".join(t.split(") ", 1)[-1] for t in tail), flush=True)
+
+if num_gpus > 1:
+    t0 = time.perf_counter()
+    r = subprocess.run([exe, "--use-gpu=no", "--min-chunk-size=25", "--chunk-size=10000", "--output-node=tdnn6_xvec.affine",
+                        f"--num-gpus={num_gpus}", model, f"ark:{ark}", f"ark,scp:{d}/xn.ark,{d}/xn.scp"],
+                       capture_output=True, text=True)
+    dt = time.perf_counter() - t0
+    assert r.returncode == 0, r.stderr[-2000:]
+    tail = [ln for ln in r.stderr.splitlines() if "Time taken" in ln or "Done " in ln]
+    same = open(f"{d}/x.ark", "rb").read() == open(f"{d}/xn.ark", "rb").read()
+    print(f"ark file, --num-gpus={num_gpus}: {dt:.2f} s wall -> {frames / 100 / dt:,.0f} audio-s/s | "
+          + " | ".join(t.split(") ", 1)[-1] for t in tail) + f" | archive identical to the 1-GPU run: {same}", flush=True)
