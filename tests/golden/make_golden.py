@@ -8,7 +8,9 @@
 
 For each: a binary nnet3 model in genuine Kaldi format (orphan layers and heads
 kept, as in a real final.raw), a feature archive, extract.config, and the
-ORACLE's fp64 embeddings.  The reference ships no golden vectors for this path
+ORACLE's fp64 embeddings; for v5_small also the phonetic bottleneck at every frame
+(v5_small_frames.npz: what `nnet3-compute` on output tdnn5.batchnorm writes,
+extract_am_embedding.sh:79-85).  The reference ships no golden vectors for this path
 (parity unpinned); these pin the oracle and the CUDA path against
 regressions and let a Kaldi owner replay e.g.
 
@@ -59,3 +61,10 @@ for name, spec in SPECS.items():
     with open(os.path.join(here, f"{name}_extract.config"), "w") as f:
         f.write(f"output-node name=output input={spec['node']}\n")
     print(name, emb.shape, ok.tolist(), ok_pad.tolist())
+    if name == "v5_small":
+        node = "tdnn5.batchnorm"
+        orc = Oracle(model, node, np.float64)
+        rows = [orc.forward_frames({"input": feats[s:s + n]}) for s, n in zip(starts, LENGTHS) if n > 0]
+        np.savez_compressed(os.path.join(here, "v5_small_frames.npz"), output_node=node,
+                            frames=np.concatenate(rows).astype(np.float32), context=np.array(orc.frame_context()))
+        print("v5_small_frames", np.concatenate(rows).shape, orc.frame_context())

@@ -140,3 +140,20 @@ def test_cli_nnet3_compute(cvx, kf, synth, frame_models, require_gpu, tmp_path):
     r = subprocess.run([exe, "--output-node=tdnn6_xvec.affine", path, f"ark:{feats_ark}", f"ark,t:{tmp_path}/x.txt"],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode != 0 and "segment-level" in r.stderr
+
+
+def test_frame_golden_fixture_through_the_cli(cvx, kf, require_gpu, tmp_path):
+    """committed golden rows (tests/golden/v5_small_frames.npz): nnet3-compute on the committed model
+    and feature archive, output redirected to the phonetic bottleneck."""
+    import os
+    import subprocess
+    g = os.path.join(os.path.dirname(__file__), "golden")
+    zf = np.load(os.path.join(g, "v5_small_frames.npz"))
+    exe = os.path.join(cvx.BIN_DIR, "nnet3-compute")
+    r = subprocess.run([exe, f"--output-node={zf['output_node']}", f"{g}/v5_small_final.raw", f"ark:{g}/v5_small_feats.ark",
+                        f"ark:{tmp_path}/bn.ark"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    assert "Done 6 utterances, failed for 1" in r.stderr, r.stderr       # one zero-length utterance in the archive
+    got = np.concatenate([m for _, m in kf.read_ark(f"{tmp_path}/bn.ark")])
+    assert got.shape == zf["frames"].shape
+    assert np.abs(got - zf["frames"]).max() / np.abs(zf["frames"]).max() <= TOL_REL

@@ -221,6 +221,21 @@ def test_oracle_reproduces_committed_golden(kf, name):
     assert np.allclose(a, b, rtol=1e-9, atol=1e-11)
 
 
+def test_oracle_reproduces_committed_frame_golden(kf):
+    import os
+    g = os.path.join(os.path.dirname(__file__), "golden")
+    z, zf = np.load(os.path.join(g, "v5_small.npz")), np.load(os.path.join(g, "v5_small_frames.npz"))
+    model = kf.read_nnet3(os.path.join(g, "v5_small_final.raw"))
+    o = Oracle(model, str(zf["output_node"]), np.float64)
+    assert o.frame_context() == tuple(zf["context"].tolist())
+    rows, base = [], 0
+    for T in z["lengths"].tolist():
+        if T > 0:
+            rows.append(o.forward_frames({"input": z["feats"][base:base + T]}))
+        base += T
+    assert np.allclose(np.concatenate(rows), zf["frames"], rtol=1e-5, atol=1e-6)
+
+
 def test_operand_rounding_model_predicts_tolerance(synth):
     """Why fp16 and not bf16 operands: emulated operand rounding through the whole
     net (weights + activations at layer boundaries) -- bf16 misses the north-star
