@@ -381,9 +381,9 @@ class Extractor:
         return out
 
     def profile(self) -> List[dict]:
-        recs = (KernelProfile * 16)()
+        recs = (KernelProfile * 64)()   # kernel classes first, then one "layer:<name>" record per frame layer
         n = C.c_int32(0)
-        _check(self._lib.cvx_engine_get_profile(self._h, recs, 16, C.byref(n)))
+        _check(self._lib.cvx_engine_get_profile(self._h, recs, 64, C.byref(n)))
         return [dict(name=recs[i].name.decode(), launches=recs[i].launches, total_ms=recs[i].total_ms,
                      flops=recs[i].flops, bytes=recs[i].bytes) for i in range(n.value)]
 

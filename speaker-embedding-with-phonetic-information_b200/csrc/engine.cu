@@ -523,11 +523,12 @@ void Engine::BuildHaloArgs(FrameOp& op) {
 }
 
 // ------------------------------------------------------------- profile ----
-void Engine::ProfBegin(int cls, double flops, double bytes) {
+void Engine::ProfBegin(int cls, double flops, double bytes, int layer) {
   ++launches_;
   if (!profile_) return;
   PendingEvent pe;
   pe.cls = cls;
+  pe.layer = layer;
   pe.flops = flops;
   pe.bytes = bytes;
   for (cudaEvent_t* ev : {&pe.a, &pe.b}) {
@@ -556,6 +557,16 @@ void Engine::ProfResolve() {
     prof_flops_[pe.cls] += pe.flops;
     prof_bytes_[pe.cls] += pe.bytes;
     prof_launches_[pe.cls] += 1;
+    if (pe.layer >= 0) {
+      if (layer_ms_.size() != plan_.frame.size()) {
+        layer_ms_.assign(plan_.frame.size(), 0.0);
+        layer_flops_.assign(plan_.frame.size(), 0.0);
+        layer_launches_.assign(plan_.frame.size(), 0);
+      }
+      layer_ms_[pe.layer] += ms;
+      layer_flops_[pe.layer] += pe.flops;
+      layer_launches_[pe.layer] += 1;
+    }
     event_pool_.push_back(pe.a);
     event_pool_.push_back(pe.b);
   }
@@ -573,11 +584,23 @@ int Engine::GetProfile(cvx_kernel_profile* recs, int32_t max_recs) {
     recs[n].bytes = prof_bytes_[c];
     ++n;
   }
+  // then one record per frame layer: "layer:<name>"
+  for (size_t l = 0; l < layer_ms_.size() && n < max_recs; ++l) {
+    std::memset(&recs[n], 0, sizeof(recs[n]));
+    std::snprintf(recs[n].name, sizeof(recs[n].name), "layer:%s", plan_.frame[l].name.c_str());
+    recs[n].launches = layer_launches_[l];
+    recs[n].total_ms = layer_ms_[l];
+    recs[n].flops = layer_flops_[l];
+    ++n;
+  }
   return n;
 }
 
 void Engine::ResetProfile() {
   for (int c = 0; c < kNumProf; ++c) prof_ms_[c] = prof_flops_[c] = prof_bytes_[c] = 0, prof_launches_[c] = 0;
+  layer_ms_.clear();
+  layer_flops_.clear();
+  layer_launches_.clear();
 }
 
 // ---------------------------------------------------------- frame pass ----
@@ -620,7 +643,7 @@ void Engine::RunFrames(const float* const* dev_feats, int64_t rows, int64_t src_
   for (FrameOp& op : frame_ops_) {
     const Layer& L = plan_.frame[op.layer];
     const double flops = 2.0 * static_cast<double>(rows) * L.in_dim * L.out_dim;
-    ProfBegin(kProfGemm, flops, 0);
+    ProfBegin(kProfGemm, flops, 0, op.layer);
     if (elem_ == kF32) {
       TdnnGemmSimtArgs a;
       std::memset(&a, 0, sizeof(a));

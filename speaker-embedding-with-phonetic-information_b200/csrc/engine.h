@@ -115,6 +115,7 @@ class Engine {
   enum ProfClass { kProfStage = 0, kProfGemm, kProfPool, kProfPoolFin, kProfSegment, kProfAverage, kNumProf };
   struct PendingEvent {
     int cls;
+    int layer = -1;
     cudaEvent_t a, b;
     double flops, bytes;
   };
@@ -126,7 +127,7 @@ class Engine {
   // pool_meta != NULL: the pooled layer runs with the fused-pooling epilogue (partials -> d_partials_)
   void RunFrames(const float* const* dev_feats, int64_t rows, int64_t src_row_min, int64_t src_row_max,
                  const PoolGroupMeta* pool_meta = nullptr, float* f32_out = nullptr, int32_t f32_ld = 0);
-  void ProfBegin(int cls, double flops, double bytes);
+  void ProfBegin(int cls, double flops, double bytes, int layer = -1);
   void ProfEnd();
   void ProfResolve();
   template <typename T>
@@ -191,6 +192,8 @@ class Engine {
   std::vector<cudaEvent_t> event_pool_;
   double prof_ms_[kNumProf] = {}, prof_flops_[kNumProf] = {}, prof_bytes_[kNumProf] = {};
   int64_t prof_launches_[kNumProf] = {};
+  std::vector<double> layer_ms_, layer_flops_;  // per frame layer (profile mode)
+  std::vector<int64_t> layer_launches_;
   int64_t launches_ = 0;
 };
 

@@ -53,6 +53,16 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   }
 }
 
+// (sx, sxx) += (x, x * x) for a 16-bit x: sm_100a's mixed-precision FHADD / FHFMA take the 16-bit
+// operand directly and accumulate in fp32.
+template <bool kBF16>
+__device__ __forceinline__ void accum16(uint16_t x, float& sx, float& sxx) {
+  if constexpr (kBF16)
+    asm("add.rn.f32.bf16 %0, %2, %0;\n\tfma.rn.f32.bf16 %1, %2, %2, %1;" : "+f"(sx), "+f"(sxx) : "h"(x));
+  else
+    asm("add.rn.f32.f16 %0, %2, %0;\n\tfma.rn.f32.f16 %1, %2, %2, %1;" : "+f"(sx), "+f"(sxx) : "h"(x));
+}
+
 // kOutF32: the epilogue writes fp32 (32-column chunks) instead of the operand type -- used for
 // the segment-level layers, whose fp32 inputs/weights are fed as fp16 hi/lo splits.
 // kPool:   fused statistics pooling -- the epilogue of the pooled layer rounds its outputs to the
@@ -214,7 +224,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
             uint32_t r[32];
             ptx::tmem_ld_32x32b_x32(t_row + c * 64 + h * 32, r);
             ptx::tmem_ld_wait();
-            float v[32];
+            uint32_t pk[16];  // this lane's row, rounded to the operand type: the values a consumer would read
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {
               const float4 p = *reinterpret_cast<const float4*>(&smem_post[c * 64 + h * 32 + j]);
@@ -224,38 +234,40 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                 v0 = fmaxf(v0, 0.f);
                 v1 = fmaxf(v1, 0.f);
               }
-              const uint32_t pk = pack2<kBF16>(v0 + p.y, v1 + p.w);  // the value a consumer would read
-              if constexpr (kBF16) {
-                v[j] = __uint_as_float(pk << 16);
-                v[j + 1] = __uint_as_float(pk & 0xffff0000u);
-              } else {
-                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&pk));
-                v[j] = f.x;
-                v[j + 1] = f.y;
-              }
+              pk[j >> 1] = pack2<kBF16>(v0 + p.y, v1 + p.w);
             }
-            // transpose through this warp's (otherwise unused) staging buffer: lane = row writes its 32
-            // columns, then lane = column sums the valid rows; (col ^ row) keeps both phases conflict-free
-            float* tile = reinterpret_cast<float*>(buf);
+            // transpose through this warp's (otherwise unused) staging buffer as 16-bit values:
+            // lane = row writes its 16 words, word index ^ (row >> 1); then lane = column reads one
+            // 16-bit value per row and accumulates it with the mixed-precision FHADD / FHFMA
+            // (fp32 += fp16, no unpacking).  Both phases are bank-conflict free.
+            uint32_t* tile = reinterpret_cast<uint32_t*>(buf);
             __syncwarp();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) tile[lane * 32 + (j ^ lane)] = v[j];
+            for (int j = 0; j < 16; ++j) tile[lane * 16 + (j ^ (lane >> 1))] = pk[j];
             __syncwarp();
+            const uint32_t lp = static_cast<uint32_t>(lane) << 1;  // byte offset of column `lane` in an un-swizzled row
+            auto row_value = [&](int r) -> uint16_t {
+              return *reinterpret_cast<const uint16_t*>(buf + r * 64 + (lp ^ (static_cast<uint32_t>(r >> 1) << 2)));
+            };
 #pragma unroll 1
             for (int seg = 0; seg < 2; ++seg) {
               const int lo = seg ? meta.b0 : meta.a0, hi = seg ? meta.b1 : meta.a1;
               if (hi <= lo) continue;
-              float sx = 0.f, sxx = 0.f;
-#pragma unroll 4
-              for (int r = lo; r < hi; ++r) {
-                const float x = tile[r * 32 + (lane ^ r)];
-                sx += x;
-                sxx = fmaf(x, x, sxx);
+              float sx0 = 0.f, sx1 = 0.f, sxx0 = 0.f, sxx1 = 0.f;
+              if (lo == 0 && hi == 32) {  // interior group: every row is valid
+#pragma unroll
+                for (int r = 0; r < 32; r += 2) {
+                  accum16<kBF16>(row_value(r), sx0, sxx0);
+                  accum16<kBF16>(row_value(r + 1), sx1, sxx1);
+                }
+              } else {
+#pragma unroll 2
+                for (int r = lo; r < hi; ++r) accum16<kBF16>(row_value(r), sx0, sxx0);
               }
               const int slot = meta.slot + ((seg && has_a) ? 1 : 0);
               float* out = args.pool_partials + static_cast<int64_t>(slot) * 2 * args.pool_ld + n0 + c * 64 + h * 32 + lane;
-              out[0] = sx;
-              out[args.pool_ld] = sxx;
+              out[0] = sx0 + sx1;
+              out[args.pool_ld] = sxx0 + sxx1;
             }
           }
           continue;
