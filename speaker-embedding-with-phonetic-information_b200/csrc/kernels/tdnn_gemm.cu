@@ -18,6 +18,7 @@
 // ceil(d/16) K steps (KBlockDesc::k16), and the last N tile uses UMMA_N =
 // roundup(out_dim,16) - n0; pad columns beyond that are never read by a consumer.
 // Persistent CTAs (one per SM), static round-robin over (m_tile, n_tile).
+#include "epilogue.cuh"
 #include "kernels.h"
 #include "ptx.cuh"
 
@@ -61,7 +62,6 @@ __global__ void __launch_bounds__(kThreads, 1) tdnn_gemm_kernel(const __grid_con
   uint8_t* smem_a = smem + kSmemA;
   uint8_t* smem_b = smem + kSmemB;
   uint8_t* smem_c = smem + kSmemC;
-  float2* smem_post = reinterpret_cast<float2*>(smem + kSmemPost);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kSmemBars);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full_bar = empty_bar + kStages;
@@ -171,6 +171,10 @@ __global__ void __launch_bounds__(kThreads, 1) tdnn_gemm_kernel(const __grid_con
     const int et = threadIdx.x - 64;
     uint8_t* buf = smem_c + (warp - 2) * kCWarpBytes;
     int it = 0;
+    static_assert(kEpilogueThreads == kGemmBlockN, "one parameter column per epilogue thread");
+    int staged_n0 = -1, pre_n0 = -1;
+    float2 pre = make_float2(0.f, 0.f);
+    const int tile_step = gridDim.x;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m0 = (tile / num_n_tiles) * kGemmBlockM;
       const int n0 = (tile % num_n_tiles) * args.tile_n;
@@ -179,10 +183,22 @@ __global__ void __launch_bounds__(kThreads, 1) tdnn_gemm_kernel(const __grid_con
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
 
-      asm volatile("bar.sync 1, %0;" ::"n"(kEpilogueThreads) : "memory");  // previous tile's params no longer read
-      for (int j = et; j < kGemmBlockN; j += kEpilogueThreads)
-        smem_post[j] = (n0 + j < args.n_pad) ? __ldg(&args.post[n0 + j]) : make_float2(0.f, 0.f);
-      asm volatile("bar.sync 1, %0;" ::"n"(kEpilogueThreads) : "memory");
+      // Per-column parameters of this N tile: restaged only when the tile column changes, and then
+      // from registers loaded during the previous tile (the L2 latency is off the critical path).
+      if (n0 != staged_n0) {
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpilogueThreads) : "memory");  // previous tile's params no longer read
+        const float2 p = (pre_n0 == n0) ? pre : epi::load_post(args.post, n0 + et, args.n_pad);
+        epi::store_post<kBF16, false>(smem + kSmemPost, et, p);
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpilogueThreads) : "memory");
+        staged_n0 = n0;
+      }
+      if (tile + tile_step < num_tiles) {
+        const int nn0 = ((tile + tile_step) % num_n_tiles) * args.tile_n;
+        if (nn0 != n0) {
+          pre = epi::load_post(args.post, nn0 + et, args.n_pad);
+          pre_n0 = nn0;
+        }
+      }
 
       ptx::mbar_wait(&tmem_full_bar[as], aphase);
       ptx::tcgen05_fence_after();
@@ -201,17 +217,7 @@ __global__ void __launch_bounds__(kThreads, 1) tdnn_gemm_kernel(const __grid_con
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
             uint32_t pk[4];
-#pragma unroll
-            for (int e = 0; e < 8; e += 2) {
-              const float4 p = *reinterpret_cast<const float4*>(&smem_post[c * 64 + h * 32 + j + e]);
-              float v0 = __uint_as_float(r[j + e]) + p.x;
-              float v1 = __uint_as_float(r[j + e + 1]) + p.z;
-              if (args.relu) {
-                v0 = fmaxf(v0, 0.f);
-                v1 = fmaxf(v1, 0.f);
-              }
-              pk[e >> 1] = pack2<kBF16>(v0 + p.y, v1 + p.w);
-            }
+            epi::pack8<kBF16>(&r[j], smem + kSmemPost, c * 64 + h * 32 + j, args.relu != 0, pk);
             const int unit = h * 4 + (j >> 3);  // 16-byte unit inside the 128-byte row
             uint8_t* dst = half_chunk ? buf + lane * 64 + (unit << 4) : buf + lane * 128 + ((unit ^ (lane & 7)) << 4);
             *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);

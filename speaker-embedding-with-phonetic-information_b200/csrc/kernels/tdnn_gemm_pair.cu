@@ -15,6 +15,7 @@
 //                       stage in both CTAs / publishes the accumulator to both epilogues
 //   both CTAs   warps 2-9: epilogue of their own 128 rows; lane 0 of each warp arrives on
 //                       the leader's tmem_empty barrier.
+#include "epilogue.cuh"
 #include "kernels.h"
 #include "ptx.cuh"
 
@@ -193,6 +194,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     const int et = threadIdx.x - 64;
     uint8_t* buf = smem_c + (warp - 2) * kCWarpBytes;
     int it = 0;
+    static_assert(kEpilogueThreads == kGemmBlockN, "one parameter column per epilogue thread");
+    int staged_n0 = -1, pre_n0 = -1;
+    float2 pre = make_float2(0.f, 0.f);
     for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
       const int m0 = (tile / num_n_tiles) * (2 * kGemmBlockM) + static_cast<int>(rank) * kGemmBlockM;
       const int n0 = (tile % num_n_tiles) * args.tile_n;
@@ -202,10 +206,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
 
-      asm volatile("bar.sync 1, %0;" ::"n"(kEpilogueThreads) : "memory");  // previous tile's params no longer read
-      for (int j = et; j < kGemmBlockN; j += kEpilogueThreads)
-        smem_post[j] = (n0 + j < args.n_pad) ? __ldg(&args.post[n0 + j]) : make_float2(0.f, 0.f);
-      asm volatile("bar.sync 1, %0;" ::"n"(kEpilogueThreads) : "memory");
+      // Per-column parameters of this N tile: restaged only when the tile column changes, and then
+      // from registers loaded during the previous tile (the L2 latency is off the critical path).
+      if (n0 != staged_n0) {
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpilogueThreads) : "memory");  // previous tile's params no longer read
+        const float2 p = (pre_n0 == n0) ? pre : epi::load_post(args.post, n0 + et, args.n_pad);
+        epi::store_post<kBF16, kOutF32>(smem + kSmemPost, et, p);
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpilogueThreads) : "memory");
+        staged_n0 = n0;
+      }
+      if (tile + tile_step < num_tiles) {
+        const int nn0 = ((tile + tile_step) % num_n_tiles) * args.tile_n;
+        if (nn0 != n0) {
+          pre = epi::load_post(args.post, nn0 + et, args.n_pad);
+          pre_n0 = nn0;
+        }
+      }
 
       ptx::mbar_wait(&tmem_full_bar[as], aphase);
       ptx::tcgen05_fence_after();
@@ -226,15 +242,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
             ptx::tmem_ld_wait();
             uint32_t pk[16];  // this lane's row, rounded to the operand type: the values a consumer would read
 #pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              const float4 p = *reinterpret_cast<const float4*>(&smem_post[c * 64 + h * 32 + j]);
-              float v0 = __uint_as_float(r[j]) + p.x;
-              float v1 = __uint_as_float(r[j + 1]) + p.z;
-              if (args.relu) {
-                v0 = fmaxf(v0, 0.f);
-                v1 = fmaxf(v1, 0.f);
-              }
-              pk[j >> 1] = pack2<kBF16>(v0 + p.y, v1 + p.w);
+            for (int j = 0; j < 32; j += 8) {
+              uint32_t p4[4];
+              epi::pack8<kBF16>(&r[j], smem + kSmemPost, c * 64 + h * 32 + j, args.relu != 0, p4);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) pk[(j >> 1) + e] = p4[e];
             }
             // transpose through this warp's (otherwise unused) staging buffer as 16-bit values:
             // lane = row writes its 16 words, word index ^ (row >> 1); then lane = column reads one
@@ -300,26 +312,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
           // a tile whose width is an odd multiple of 32 ends in a half chunk: 32 columns, stored
           // through the un-swizzled 32-column map (rows 64 bytes apart in `buf`)
           const bool half_chunk = (n_cols - c * 64) < 64;
+          // both 32-column halves of the chunk are requested before the single wait
+          uint32_t r0[32], r1[32];
+          ptx::tmem_ld_32x32b_x32(t_row + c * 64, r0);
+          if (!half_chunk) ptx::tmem_ld_32x32b_x32(t_row + c * 64 + 32, r1);
+          ptx::tmem_ld_wait();
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             if (h == 1 && half_chunk) break;
-            uint32_t r[32];
-            ptx::tmem_ld_32x32b_x32(t_row + c * 64 + h * 32, r);
-            ptx::tmem_ld_wait();
+            const uint32_t* r = h ? r1 : r0;
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
               uint32_t pk[4];
-#pragma unroll
-              for (int e = 0; e < 8; e += 2) {
-                const float4 p = *reinterpret_cast<const float4*>(&smem_post[c * 64 + h * 32 + j + e]);
-                float v0 = __uint_as_float(r[j + e]) + p.x;
-                float v1 = __uint_as_float(r[j + e + 1]) + p.z;
-                if (args.relu) {
-                  v0 = fmaxf(v0, 0.f);
-                  v1 = fmaxf(v1, 0.f);
-                }
-                pk[e >> 1] = pack2<kBF16>(v0 + p.y, v1 + p.w);
-              }
+              epi::pack8<kBF16>(&r[j], smem + kSmemPost, c * 64 + h * 32 + j, args.relu != 0, pk);
               const int unit = h * 4 + (j >> 3);  // 16-byte unit inside the 128-byte row
               uint8_t* dst = half_chunk ? buf + lane * 64 + (unit << 4) : buf + lane * 128 + ((unit ^ (lane & 7)) << 4);
               *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
