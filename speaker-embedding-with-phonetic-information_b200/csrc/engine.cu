@@ -322,6 +322,7 @@ Engine::~Engine() {
   cudaFree(d_pool_meta_);
   cudaFree(d_slot_n_);
   cudaFree(d_slot_begin_);
+  cudaFree(d_chunk_rng_);
   cudaFree(d_seg_hi_);
   cudaFree(d_seg_lo_);
   for (SegOp& s : seg_ops_) {
@@ -776,7 +777,6 @@ void Engine::Extract(const float* const* feats, int32_t num_streams, int64_t tot
   };
   std::vector<Batch> batches;
   std::vector<PoolSlab> slabs;
-  std::vector<int32_t> chunk_slab_off(num_chunks + 1, 0);
   std::vector<int64_t> utt_off(static_cast<size_t>(num_utts) + 1, 0);
   std::vector<float> weights(num_chunks);
   int64_t prev_end = 0;
@@ -800,83 +800,75 @@ void Engine::Extract(const float* const* feats, int32_t num_streams, int64_t tot
   }
   for (int32_t u = 0; u < num_utts; ++u) utt_off[u + 1] += utt_off[u];
   const int64_t cap = std::max(max_batch_rows_, (max_chunk_rows + kGemmBlockM - 1) / kGemmBlockM * kGemmBlockM);
+  // valid (poolable) rows of every chunk, relative to its batch; hi inclusive
+  std::vector<int32_t> chunk_lo(num_chunks), chunk_hi(num_chunks);
   {
     int64_t c = 0;
     while (c < num_chunks) {
       Batch b;
       b.c0 = c;
       b.row0 = chunk_start[c];
-      b.slab0 = static_cast<int64_t>(slabs.size());
+      b.slab0 = b.slab1 = 0;
       while (c < num_chunks && chunk_start[c] + chunk_len[c] - b.row0 <= cap) {
-        const int64_t lo = chunk_start[c] - b.row0 + L;
-        const int64_t hi = chunk_start[c] - b.row0 + std::min<int64_t>(chunk_len[c] - 1 - R, rc);  // inclusive
-        chunk_slab_off[c] = static_cast<int32_t>(slabs.size() - b.slab0);
-        for (int64_t r = lo; r <= hi; r += kPoolSlabRows) {
-          PoolSlab s;
-          s.row_begin = r;
-          s.nrows = static_cast<int32_t>(std::min<int64_t>(kPoolSlabRows, hi - r + 1));
-          s.chunk = static_cast<int32_t>(c - b.c0);
-          slabs.push_back(s);
-        }
+        chunk_lo[c] = static_cast<int32_t>(chunk_start[c] - b.row0 + L);
+        chunk_hi[c] = static_cast<int32_t>(chunk_start[c] - b.row0 + std::min<int64_t>(chunk_len[c] - 1 - R, rc));
         ++c;
       }
       b.c1 = c;
       b.row1 = chunk_start[c - 1] + chunk_len[c - 1];
-      b.slab1 = static_cast<int64_t>(slabs.size());
       batches.push_back(b);
     }
   }
-  // ---- fused pooling tables: per batch, per 32-row group the (at most two) runs of valid rows ----
+  // ---- fused pooling: per batch, every 32-row group holds at most two runs of valid rows (tail of
+  // one chunk, head of the next); slot = one run.  The host only numbers the slots per chunk, the
+  // per-group table itself is built on the device (pool_meta_kernel), so this is O(chunks). ----
   bool fused = fused_pool_;
-  std::vector<PoolGroupMeta> pool_meta;            // all batches, batch bi starts at meta_pos[bi]
-  std::vector<int32_t> slot_n, slot_begin_packed;  // per batch: slots / [nchunks + 1] offsets
-  std::vector<int64_t> meta_pos(batches.size()), slot_pos(batches.size()), slot_begin_pos(batches.size());
-  int64_t max_slots = 0;
+  std::vector<int32_t> slot_begin_packed;  // per batch: [nchunks + 1] slot offsets
+  std::vector<int64_t> meta_pos(batches.size()), slot_pos(batches.size()), slot_begin_pos(batches.size()),
+      batch_groups(batches.size());
+  int64_t max_slots = 0, total_groups = 0, total_slots = 0;
   for (size_t bi = 0; bi < batches.size() && fused; ++bi) {
     const Batch& b = batches[bi];
     const int64_t rows = b.row1 - b.row0;
-    const int64_t ngroups = (rows + 2 * kGemmBlockM - 1) / (2 * kGemmBlockM) * (2 * kGemmBlockM) / 32;
-    meta_pos[bi] = static_cast<int64_t>(pool_meta.size());
-    slot_pos[bi] = static_cast<int64_t>(slot_n.size());
+    batch_groups[bi] = (rows + 2 * kGemmBlockM - 1) / (2 * kGemmBlockM) * (2 * kGemmBlockM) / 32;
+    meta_pos[bi] = total_groups;
+    slot_pos[bi] = total_slots;
     slot_begin_pos[bi] = static_cast<int64_t>(slot_begin_packed.size());
-    pool_meta.resize(pool_meta.size() + ngroups, PoolGroupMeta{0, 0, 0, 0, 0});
-    PoolGroupMeta* gm = pool_meta.data() + meta_pos[bi];
     int32_t nslots = 0;
-    for (int64_t c = b.c0; c < b.c1 && fused; ++c) {
+    for (int64_t c = b.c0; c < b.c1; ++c) {
+      // three runs in one group (tiny chunks): use the stand-alone pooling kernels
+      if (c + 2 < b.c1 && chunk_lo[c + 2] / 32 == chunk_hi[c] / 32) fused = false;
       slot_begin_packed.push_back(nslots);
-      const int64_t lo = chunk_start[c] - b.row0 + L;
-      const int64_t hi = chunk_start[c] - b.row0 + std::min<int64_t>(chunk_len[c] - 1 - R, rc);  // inclusive
-      for (int64_t g = lo / 32; g <= hi / 32; ++g) {
-        const int32_t f = static_cast<int32_t>(std::max<int64_t>(lo, g * 32) - g * 32);
-        const int32_t e = static_cast<int32_t>(std::min<int64_t>(hi + 1, g * 32 + 32) - g * 32);
-        PoolGroupMeta& m = gm[g];
-        if (m.a1 <= m.a0 && m.b1 <= m.b0) {  // first run of this group
-          m.slot = nslots;
-          m.a0 = static_cast<uint8_t>(f);
-          m.a1 = static_cast<uint8_t>(e);
-        } else if (m.b1 <= m.b0 && m.slot == nslots - 1) {  // second run: the slot right after the first
-          m.b0 = static_cast<uint8_t>(f);
-          m.b1 = static_cast<uint8_t>(e);
-        } else {
-          fused = false;  // three runs in one group (tiny chunks): use the stand-alone pooling kernels
-          break;
-        }
-        slot_n.push_back(e - f);
-        ++nslots;
-      }
+      nslots += chunk_hi[c] / 32 - chunk_lo[c] / 32 + 1;
     }
     slot_begin_packed.push_back(nslots);
     max_slots = std::max<int64_t>(max_slots, nslots);
+    total_groups += batch_groups[bi];
+    total_slots += nslots;
   }
 
+  // stand-alone pooling: slabs of <= kPoolSlabRows valid rows cut relative to each chunk;
   // chunk_slab_off is stored per batch as [c1-c0+1] entries relative to the batch's first slab
   std::vector<int32_t> slab_off_packed;
   std::vector<int64_t> slab_off_pos(batches.size());
-  for (size_t bi = 0; bi < batches.size(); ++bi) {
-    const Batch& b = batches[bi];
-    slab_off_pos[bi] = static_cast<int64_t>(slab_off_packed.size());
-    for (int64_t c = b.c0; c < b.c1; ++c) slab_off_packed.push_back(chunk_slab_off[c]);
-    slab_off_packed.push_back(static_cast<int32_t>(b.slab1 - b.slab0));
+  if (!fused) {
+    for (size_t bi = 0; bi < batches.size(); ++bi) {
+      Batch& b = batches[bi];
+      b.slab0 = static_cast<int64_t>(slabs.size());
+      slab_off_pos[bi] = static_cast<int64_t>(slab_off_packed.size());
+      for (int64_t c = b.c0; c < b.c1; ++c) {
+        slab_off_packed.push_back(static_cast<int32_t>(slabs.size() - b.slab0));
+        for (int64_t r = chunk_lo[c]; r <= chunk_hi[c]; r += kPoolSlabRows) {
+          PoolSlab sl;
+          sl.row_begin = r;
+          sl.nrows = static_cast<int32_t>(std::min<int64_t>(kPoolSlabRows, chunk_hi[c] - r + 1));
+          sl.chunk = static_cast<int32_t>(c - b.c0);
+          slabs.push_back(sl);
+        }
+      }
+      b.slab1 = static_cast<int64_t>(slabs.size());
+      slab_off_packed.push_back(static_cast<int32_t>(b.slab1 - b.slab0));
+    }
   }
 
   // ---- device scratch ----
@@ -889,15 +881,16 @@ void Engine::Extract(const float* const* feats, int32_t num_streams, int64_t tot
   EnsureRows(max_rows);
   const Buffer& pool_buf = buffers_[layer_buffer_[plan_.pool_src]];
   const int32_t D = PL.out_dim, pooled = plan_.PooledDim();
-  Grow(&d_slabs_, &slabs_cap_, slabs.size() * sizeof(PoolSlab));
-  Grow(&d_chunk_slab_off_, &chunk_slab_off_cap_, slab_off_packed.size() * 4);
+  Grow(&d_slabs_, &slabs_cap_, std::max<size_t>(slabs.size(), 1) * sizeof(PoolSlab));
+  Grow(&d_chunk_slab_off_, &chunk_slab_off_cap_, std::max<size_t>(slab_off_packed.size(), 1) * 4);
   Grow(&d_weights_, &weights_cap_, weights.size() * 4);
   Grow(&d_utt_off_, &utt_off_cap_, utt_off.size() * 8);
   Grow(&d_partials_, &partials_cap_, static_cast<size_t>(std::max(max_slabs, fused ? max_slots : 0)) * 2 * pool_buf.ld * 4);
   if (fused) {
-    Grow(&d_pool_meta_, &pool_meta_cap_, pool_meta.size() * sizeof(PoolGroupMeta));
-    Grow(&d_slot_n_, &slot_n_cap_, std::max<size_t>(slot_n.size(), 1) * 4);
+    Grow(&d_pool_meta_, &pool_meta_cap_, static_cast<size_t>(total_groups) * sizeof(PoolGroupMeta));
+    Grow(&d_slot_n_, &slot_n_cap_, static_cast<size_t>(std::max<int64_t>(total_slots, 1)) * 4);
     Grow(&d_slot_begin_, &slot_begin_cap_, slot_begin_packed.size() * 4);
+    Grow(&d_chunk_rng_, &chunk_rng_cap_, static_cast<size_t>(num_chunks) * 8);
   }
   // pooled statistics of several device batches are collected and the segment layers run on
   // up to kSegFlushChunks chunks at once (a [few chunks, 3000] GEMM per batch is latency bound)
@@ -923,13 +916,15 @@ void Engine::Extract(const float* const* feats, int32_t num_streams, int64_t tot
       for (int32_t s = 0; s < num_streams; ++s)
         Grow(&d_feat_[i][s], &d_feat_cap_[i][s], static_cast<size_t>(max_rows) * plan_.input_dims[s] * 4);
 
-  CVX_CUDA_CHECK(cudaMemcpyAsync(d_slabs_, slabs.data(), slabs.size() * sizeof(PoolSlab), cudaMemcpyHostToDevice, compute_));
-  CVX_CUDA_CHECK(cudaMemcpyAsync(d_chunk_slab_off_, slab_off_packed.data(), slab_off_packed.size() * 4,
-                                 cudaMemcpyHostToDevice, compute_));
   if (fused) {
-    CVX_CUDA_CHECK(cudaMemcpyAsync(d_pool_meta_, pool_meta.data(), pool_meta.size() * sizeof(PoolGroupMeta), cudaMemcpyHostToDevice, compute_));
-    CVX_CUDA_CHECK(cudaMemcpyAsync(d_slot_n_, slot_n.data(), slot_n.size() * 4, cudaMemcpyHostToDevice, compute_));
+    int32_t* rng = static_cast<int32_t*>(d_chunk_rng_);
+    CVX_CUDA_CHECK(cudaMemcpyAsync(rng, chunk_lo.data(), static_cast<size_t>(num_chunks) * 4, cudaMemcpyHostToDevice, compute_));
+    CVX_CUDA_CHECK(cudaMemcpyAsync(rng + num_chunks, chunk_hi.data(), static_cast<size_t>(num_chunks) * 4, cudaMemcpyHostToDevice, compute_));
     CVX_CUDA_CHECK(cudaMemcpyAsync(d_slot_begin_, slot_begin_packed.data(), slot_begin_packed.size() * 4, cudaMemcpyHostToDevice, compute_));
+  } else {
+    CVX_CUDA_CHECK(cudaMemcpyAsync(d_slabs_, slabs.data(), slabs.size() * sizeof(PoolSlab), cudaMemcpyHostToDevice, compute_));
+    CVX_CUDA_CHECK(cudaMemcpyAsync(d_chunk_slab_off_, slab_off_packed.data(), slab_off_packed.size() * 4,
+                                   cudaMemcpyHostToDevice, compute_));
   }
   CVX_CUDA_CHECK(cudaMemcpyAsync(d_weights_, weights.data(), weights.size() * 4, cudaMemcpyHostToDevice, compute_));
   CVX_CUDA_CHECK(cudaMemcpyAsync(d_utt_off_, utt_off.data(), utt_off.size() * 8, cudaMemcpyHostToDevice, compute_));
@@ -962,6 +957,17 @@ void Engine::Extract(const float* const* feats, int32_t num_streams, int64_t tot
       src_min = 0;
       src_max = rows;
     }
+    if (fused) {
+      // per-group run table and rows per slot of this batch, from the chunk ranges
+      const int32_t* rng = static_cast<const int32_t*>(d_chunk_rng_);
+      ProfBegin(kProfPoolFin, 0, static_cast<double>(batch_groups[bi]) * sizeof(PoolGroupMeta));
+      CVX_CUDA_CHECK(LaunchPoolMeta(rng + b.c0, rng + num_chunks + b.c0,
+                                    static_cast<const int32_t*>(d_slot_begin_) + slot_begin_pos[bi],
+                                    static_cast<int32_t>(b.c1 - b.c0), batch_groups[bi],
+                                    static_cast<PoolGroupMeta*>(d_pool_meta_) + meta_pos[bi],
+                                    static_cast<int32_t*>(d_slot_n_) + slot_pos[bi], compute_));
+      ProfEnd();
+    }
     RunFrames(dev, rows, src_min, src_max, fused ? static_cast<const PoolGroupMeta*>(d_pool_meta_) + meta_pos[bi] : nullptr);
     if (!dev_in) CVX_CUDA_CHECK(cudaEventRecord(feat_free_[fb], compute_));
 
@@ -969,7 +975,7 @@ void Engine::Extract(const float* const* feats, int32_t num_streams, int64_t tot
     const int32_t nchunks = static_cast<int32_t>(b.c1 - b.c0);
     const PoolSlab* dsl = static_cast<const PoolSlab*>(d_slabs_) + b.slab0;
     double pooled_rows = 0;
-    for (int64_t s = b.slab0; s < b.slab1; ++s) pooled_rows += slabs[s].nrows;
+    for (int64_t c = b.c0; c < b.c1; ++c) pooled_rows += chunk_hi[c] - chunk_lo[c] + 1;
     if (fused) {
       // the pooled layer's epilogue already left per-slot sums in d_partials_
       const int32_t bslots = slot_begin_packed[slot_begin_pos[bi] + nchunks];

@@ -163,8 +163,8 @@ class Engine {
   int64_t seg_split_rows_ = 0;
   int64_t last_num_chunks_ = 0;
   bool fused_pool_ = false;  // pooled layer's activations are reduced in its GEMM epilogue
-  void *d_pool_meta_ = nullptr, *d_slot_n_ = nullptr, *d_slot_begin_ = nullptr;
-  size_t pool_meta_cap_ = 0, slot_n_cap_ = 0, slot_begin_cap_ = 0;
+  void *d_pool_meta_ = nullptr, *d_slot_n_ = nullptr, *d_slot_begin_ = nullptr, *d_chunk_rng_ = nullptr;
+  size_t pool_meta_cap_ = 0, slot_n_cap_ = 0, slot_begin_cap_ = 0, chunk_rng_cap_ = 0;
   void RunPrestep(int32_t s, int32_t dim, const float* host_raw, const cvx_prestep& pre, int64_t total_raw_rows,
                   const int64_t* utt_raw_start, const int32_t* keep, const int64_t* utt_kept_start, int32_t num_utts);
   void *d_raw_[kMaxASources] = {}, *d_sel_[kMaxASources] = {};

@@ -160,6 +160,12 @@ cudaError_t LaunchStatsPoolFinalize(const float* partials, int32_t ld, const Poo
 cudaError_t LaunchSplitF32(const float* in, int32_t ld_in, int64_t m, int32_t k, void* hi, void* lo,
                            int32_t ld_out, int32_t elem, cudaStream_t stream);
 
+// fused-pooling tables of one batch, built on the device from the chunks' valid row ranges
+// [lo[c], hi[c]] (relative to the batch, hi inclusive, increasing): per 32-row group the (at most
+// two) runs of valid rows and their slots, and the number of rows of every slot
+cudaError_t LaunchPoolMeta(const int32_t* lo, const int32_t* hi, const int32_t* slot_begin, int32_t num_chunks,
+                           int64_t num_groups, PoolGroupMeta* meta, int32_t* slot_n, cudaStream_t stream);
+
 // fused-pooling finalize: chunk c owns slots [slot_begin[c], slot_begin[c+1]) with slot_n[] valid rows each
 cudaError_t LaunchStatsPoolFinalizeFused(const float* partials, int32_t ld, const int32_t* slot_begin,
                                          const int32_t* slot_n, int32_t num_chunks, int32_t total_slots,

@@ -252,7 +252,52 @@ __global__ void __launch_bounds__(256) stats_pool_finalize_fused_kernel(const fl
   }
 }
 
+// One thread per 32-row group: binary search for the first chunk whose valid range reaches the
+// group; that chunk's run and, if the next chunk starts inside the group too, a second run.  The
+// host guarantees that no group holds three runs (engine.cu) and numbers a chunk's slots
+// consecutively from slot_begin[c], one per group the chunk touches.
+__global__ void __launch_bounds__(256) pool_meta_kernel(const int32_t* __restrict__ lo, const int32_t* __restrict__ hi,
+                                                         const int32_t* __restrict__ slot_begin, int num_chunks,
+                                                         int64_t num_groups, PoolGroupMeta* __restrict__ meta,
+                                                         int32_t* __restrict__ slot_n) {
+  const int64_t g = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (g >= num_groups) return;
+  const int64_t g0 = g * 32, g1 = g0 + 32;
+  int a = 0, b = num_chunks;
+  while (a < b) {
+    const int mid = (a + b) >> 1;
+    if (hi[mid] >= g0) b = mid;
+    else a = mid + 1;
+  }
+  PoolGroupMeta m{0, 0, 0, 0, 0};
+  if (a < num_chunks && lo[a] < g1) {
+    const int32_t l = lo[a], h = hi[a];
+    const int f = static_cast<int>(max(static_cast<int64_t>(l), g0) - g0);
+    const int e = static_cast<int>(min(static_cast<int64_t>(h) + 1, g1) - g0);
+    m.slot = slot_begin[a] + static_cast<int32_t>(g - l / 32);
+    m.a0 = static_cast<uint8_t>(f);
+    m.a1 = static_cast<uint8_t>(e);
+    slot_n[m.slot] = e - f;
+    if (a + 1 < num_chunks && lo[a + 1] < g1) {  // head of the next chunk: its first slot = m.slot + 1
+      const int f2 = static_cast<int>(lo[a + 1] - g0);
+      const int e2 = static_cast<int>(min(static_cast<int64_t>(hi[a + 1]) + 1, g1) - g0);
+      m.b0 = static_cast<uint8_t>(f2);
+      m.b1 = static_cast<uint8_t>(e2);
+      slot_n[m.slot + 1] = e2 - f2;
+    }
+  }
+  meta[g] = m;
+}
+
 }  // namespace
+
+cudaError_t LaunchPoolMeta(const int32_t* lo, const int32_t* hi, const int32_t* slot_begin, int32_t num_chunks,
+                           int64_t num_groups, PoolGroupMeta* meta, int32_t* slot_n, cudaStream_t stream) {
+  if (num_groups <= 0) return cudaSuccess;
+  pool_meta_kernel<<<static_cast<unsigned>((num_groups + 255) / 256), 256, 0, stream>>>(lo, hi, slot_begin, num_chunks,
+                                                                                       num_groups, meta, slot_n);
+  return cudaGetLastError();
+}
 
 cudaError_t LaunchStatsPoolFinalizeFused(const float* partials, int32_t ld, const int32_t* slot_begin,
                                          const int32_t* slot_n, int32_t num_chunks, int32_t total_slots, int32_t dim,
