@@ -422,8 +422,6 @@ void Engine::EncodeMaps() {
     for (size_t s = op.srcs.size(); s < kMaxASources; ++s) a.a_maps[s] = a.a_maps[0];
     a.b_box_rows = std::min(kGemmBlockN, op.n_pad);
     Encode2D(&a.b_map, elem_, op.d_w, op.n_pad, op.k_pad, kGemmBlockK, a.b_box_rows);
-    a.b_box_rows_pair = std::min(kGemmBlockN / 2, op.n_pad);
-    Encode2D(&a.b_map_pair, elem_, op.d_w, op.n_pad, op.k_pad, kGemmBlockK, a.b_box_rows_pair);
     const Buffer& ob = buffers_[op.out_buffer];
     Encode2D(&a.c_map, elem_, ob.ptr, rows_cap_, ob.ld, 64, 32);
     Encode2D(&a.c_map_half, elem_, ob.ptr, rows_cap_, ob.ld, 32, 32, -1, /*swizzle=*/false);
@@ -436,6 +434,9 @@ void Engine::EncodeMaps() {
       a.tile_n = RoundUp((a.n_mma + nt - 1) / nt, 32);
     }
     a.num_n_tiles = (a.n_mma + a.tile_n - 1) / a.tile_n;
+    // each CTA of a pair stages half of a W tile: the box holds exactly tile_n / 2 rows
+    a.b_box_rows_pair = a.tile_n / 2;
+    Encode2D(&a.b_map_pair, elem_, op.d_w, op.n_pad, op.k_pad, kGemmBlockK, a.b_box_rows_pair);
     a.post = op.d_post;
     a.relu = plan_.frame[op.layer].relu ? 1 : 0;
     a.ab_format = elem_ == kBF16 ? 1 : 0;
@@ -677,9 +678,7 @@ void Engine::RunFrames(const float* const* dev_feats, int64_t rows, int64_t src_
         // rows beyond `rows` and columns beyond out_dim are clipped by the map
         TdnnGemmArgs fa = op.targs;
         Encode2D(&fa.c_map, kF32, f32_out, rows, f32_ld, 32, 32, L.out_dim);
-        fa.c_map_half = fa.c_map;
-        fa.tile_n = kGemmBlockN;
-        fa.num_n_tiles = (fa.n_mma + kGemmBlockN - 1) / kGemmBlockN;
+        fa.c_map_half = fa.c_map;  // (tile widths stay the layer's own: the fp32 epilogue stores 32-column chunks)
         fa.out_f32 = 1;
         CVX_CUDA_CHECK(LaunchTdnnGemmPair(fa, num_sms_, compute_));
       } else if (debug_ & kDebugSingleCtaGemm) {

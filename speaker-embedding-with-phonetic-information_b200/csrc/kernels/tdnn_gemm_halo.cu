@@ -10,6 +10,7 @@
 //
 //   A ring   4 slots x (144 rows x 128 B)   one activation tile per (source, column block)
 //   B ring   7 slots x (128 rows x 128 B)   this CTA's half of one W tile per (group, tap)
+//   (narrow layers, N <= 128: 7 activation slots + 7 weight slots of 64 rows, see Ring<>)
 //   both CTAs of the pair: warp 0 = TMA producer (A tile, then its taps' W tiles, in
 //   consumption order); leader CTA warp 1 = MMA issuer (tcgen05.mma.cta_group::2, M=256);
 //   warps 2-9 = epilogue (see tdnn_gemm_pair.cu, unchanged).
@@ -23,41 +24,41 @@
 namespace cvx {
 namespace {
 
-constexpr int kAStages = 4;
-constexpr int kBStages = 7;
 constexpr int kASlotBytes = (kGemmBlockM + kMaxHaloSpan) * 128;  // 18432
-constexpr int kBSlotBytes = (kGemmBlockN / 2) * 128;             // 16384
 constexpr int kCWarpBytes = 32 * 128;
-constexpr int kSmemA = 0;
-constexpr int kSmemB = kSmemA + kAStages * kASlotBytes;  // 73728
-constexpr int kSmemC = kSmemB + kBStages * kBSlotBytes;  // 188416
-constexpr int kSmemPost = kSmemC + 8 * kCWarpBytes;      // 221184
-constexpr int kSmemBars = kSmemPost + kGemmBlockN * 8;   // 223232
-constexpr int kNumBars = 2 * kAStages + 2 * kBStages + 4;
-constexpr int kSmemTmemPtr = kSmemBars + kNumBars * 8;
-constexpr int kSmemTotal = kSmemTmemPtr + 32;
 constexpr int kTmemCols = 512;
 constexpr int kThreads = 320;
 constexpr int kEpilogueThreads = 256;
 constexpr int kEpilogueWarps = 8;
-static_assert(kASlotBytes % 1024 == 0 && kSmemB % 1024 == 0 && kSmemC % 1024 == 0, "swizzle alignment");
-static_assert(kSmemTotal <= 232448, "shared memory budget");
 
-template <bool kBF16>
-__device__ __forceinline__ uint32_t pack2(float a, float b) {
-  if constexpr (kBF16) {
-    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&v);
-  } else {
-    uint32_t r;  // saturating: a finite fp32 never becomes an fp16 infinity
-    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
-    return r;
-  }
-}
+// Ring geometry.  Wide tiles (N > 128): 4 activation slots + 7 weight slots of 16 KB.  Narrow
+// layers (N <= 128, e.g. the 1950 -> 128 bottleneck) need only 8 KB per weight half-tile and their
+// tap groups last half as many MMA cycles, so the same lookahead in TIME needs more activation
+// slots: 7 + 7 x 8 KB (with 4 the MMA warp waited on HBM latency: 63 % tensor-pipe active).
+template <bool kNarrow>
+struct Ring {
+  static constexpr int kAStages = kNarrow ? 7 : 4;
+  static constexpr int kBStages = 7;
+  static constexpr int kBSlotBytes = kNarrow ? (kGemmBlockN / 4) * 128 : (kGemmBlockN / 2) * 128;  // 8192 : 16384
+  static constexpr int kSmemA = 0;
+  static constexpr int kSmemB = kSmemA + kAStages * kASlotBytes;
+  static constexpr int kSmemC = kSmemB + kBStages * kBSlotBytes;
+  static constexpr int kSmemPost = kSmemC + 8 * kCWarpBytes;
+  static constexpr int kSmemBars = kSmemPost + kGemmBlockN * 8;
+  static constexpr int kNumBars = 2 * kAStages + 2 * kBStages + 4;
+  static constexpr int kSmemTmemPtr = kSmemBars + kNumBars * 8;
+  static constexpr int kSmemTotal = kSmemTmemPtr + 32;
+  static_assert(kASlotBytes % 1024 == 0 && kSmemB % 1024 == 0 && kSmemC % 1024 == 0, "swizzle alignment");
+  static_assert(kSmemTotal <= 232448, "shared memory budget");
+};
 
-template <bool kBF16, bool kOutF32>
+template <bool kBF16, bool kOutF32, bool kNarrow>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     tdnn_gemm_halo_kernel(const __grid_constant__ TdnnGemmHaloArgs args) {
+  using R = Ring<kNarrow>;
+  constexpr int kAStages = R::kAStages, kBStages = R::kBStages, kBSlotBytes = R::kBSlotBytes;
+  constexpr int kSmemA = R::kSmemA, kSmemB = R::kSmemB, kSmemC = R::kSmemC, kSmemPost = R::kSmemPost,
+                kSmemBars = R::kSmemBars, kSmemTmemPtr = R::kSmemTmemPtr;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* smem_a = smem + kSmemA;
   uint8_t* smem_b = smem + kSmemB;
@@ -327,10 +328,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 
 }  // namespace
 
-cudaError_t LaunchTdnnGemmHalo(const TdnnGemmHaloArgs& args, int num_sms, cudaStream_t stream) {
+template <bool kNarrow>
+cudaError_t LaunchHalo(const TdnnGemmHaloArgs& args, int num_sms, cudaStream_t stream) {
   const bool bf16 = args.ab_format == 1;
-  auto kern = args.out_f32 ? (bf16 ? tdnn_gemm_halo_kernel<true, true> : tdnn_gemm_halo_kernel<false, true>)
-                           : (bf16 ? tdnn_gemm_halo_kernel<true, false> : tdnn_gemm_halo_kernel<false, false>);
+  auto kern = args.out_f32 ? (bf16 ? tdnn_gemm_halo_kernel<true, true, kNarrow> : tdnn_gemm_halo_kernel<false, true, kNarrow>)
+                           : (bf16 ? tdnn_gemm_halo_kernel<true, false, kNarrow> : tdnn_gemm_halo_kernel<false, false, kNarrow>);
+  constexpr int kSmemTotal = Ring<kNarrow>::kSmemTotal;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
   if (e != cudaSuccess) return e;
   const int tiles = ((args.num_m_tiles + 1) / 2) * args.num_n_tiles;
@@ -338,6 +341,12 @@ cudaError_t LaunchTdnnGemmHalo(const TdnnGemmHaloArgs& args, int num_sms, cudaSt
   const int clusters = tiles < num_sms / 2 ? tiles : num_sms / 2;
   kern<<<2 * clusters, kThreads, kSmemTotal, stream>>>(args);
   return cudaGetLastError();
+}
+
+cudaError_t LaunchTdnnGemmHalo(const TdnnGemmHaloArgs& args, int num_sms, cudaStream_t stream) {
+  // a W half-tile of <= 64 rows fits the narrow ring's 8 KB weight slots
+  if (args.b_box_rows_pair <= kGemmBlockN / 4) return LaunchHalo<true>(args, num_sms, stream);
+  return LaunchHalo<false>(args, num_sms, stream);
 }
 
 }  // namespace cvx
