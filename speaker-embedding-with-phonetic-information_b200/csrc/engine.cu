@@ -123,6 +123,9 @@ Engine::Engine(const Plan& plan, const cvx_engine_options& opts) : plan_(plan), 
   if (const char* env = std::getenv("CVX_GEMM_HALO")) {
     if (env[0] == '0') debug_ |= kDebugNoHaloGemm;  // A/B aid: plain CTA-pair kernel
   }
+  if (const char* env = std::getenv("CVX_INPUT_TAPS")) {
+    if (env[0] == '1') debug_ |= kDebugForceTapPath;  // A/B aid: input layers read per-tap tiles instead of a compact splice
+  }
   if (const char* env = std::getenv("CVX_GEMM_1CTA")) {
     if (env[0] == '1') debug_ |= kDebugSingleCtaGemm;  // A/B aid: same results, 1-CTA tiles
   }

@@ -66,12 +66,18 @@ template <typename T>
 __global__ void __launch_bounds__(256) stage_input_tiled_kernel(const __grid_constant__ StageArgs args) {
   constexpr int kVec = 16 / sizeof(T);
   extern __shared__ uint32_t s_mem[];
-  uint32_t* s_colmap = s_mem;
+  // s_src[c]: index of output column c's source inside the tile's feature rows, relative to the
+  // output row's own first element ((offset - off_min) * dim + column), or -1 for a padding column
+  int* s_src = reinterpret_cast<int*>(s_mem);
   float* s_feat = reinterpret_cast<float*>(s_mem + args.ld_out);
   const int dim = args.feat_dim[args.tile_stream];
   const float* __restrict__ src = args.feats[args.tile_stream];
   const int64_t r0 = static_cast<int64_t>(blockIdx.x) * kStageTileRows;
-  for (int c = threadIdx.x; c < args.ld_out; c += blockDim.x) s_colmap[c] = args.colmap[c];
+  for (int c = threadIdx.x; c < args.ld_out; c += blockDim.x) {
+    const uint32_t m = args.colmap[c];
+    s_src[c] = (m & 0x80000000u) ? (static_cast<int>((m >> 16) & 0xFFF) - 2048 - args.off_min) * dim + static_cast<int>(m & 0xFFFF)
+                                 : -1;
+  }
   const int n_src = (kStageTileRows + args.off_max - args.off_min) * dim;
   const int64_t first = (r0 + args.off_min) * dim;
   const int64_t lo = args.src_row_min * dim, hi = args.src_row_max * dim;
@@ -85,17 +91,13 @@ __global__ void __launch_bounds__(256) stage_input_tiled_kernel(const __grid_con
     const int row = u / groups;
     if (r0 + row >= args.rows) break;
     const int c0 = (u % groups) * kVec;
+    const float* base = s_feat + row * dim;
+    alignas(16) int idx[kVec];
+#pragma unroll
+    for (int e = 0; e < kVec; e += 4) *reinterpret_cast<int4*>(&idx[e]) = *reinterpret_cast<const int4*>(&s_src[c0 + e]);
     alignas(16) T vals[kVec];
 #pragma unroll
-    for (int e = 0; e < kVec; ++e) {
-      const uint32_t m = s_colmap[c0 + e];
-      float v = 0.f;
-      if (m & 0x80000000u) {
-        const int off = static_cast<int>((m >> 16) & 0xFFF) - 2048;
-        v = s_feat[(row + off - args.off_min) * dim + (m & 0xFFFF)];
-      }
-      vals[e] = to_elem<T>(v);
-    }
+    for (int e = 0; e < kVec; ++e) vals[e] = to_elem<T>(idx[e] >= 0 ? base[idx[e]] : 0.f);
     *reinterpret_cast<uint4*>(static_cast<T*>(args.out) + (r0 + row) * args.ld_out + c0) = *reinterpret_cast<uint4*>(vals);
   }
 }
