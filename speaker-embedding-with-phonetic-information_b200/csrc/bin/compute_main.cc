@@ -151,6 +151,8 @@ int ComputeMain(int argc, const char* const* argv) {
     SequentialMatrixReader reader(feat_rspecifier);
     MatrixWriter writer(matrix_wspecifier);
     const int32_t dim = cvx_model_input_dim(model, 0), E = info.embedding_dim;
+    // wide outputs (log-posteriors over thousands of senones): keep a batch's result under 1 GB of pinned memory
+    batch_rows = std::min<int64_t>(batch_rows, std::max<int64_t>(4096, (int64_t{1} << 28) / std::max(E, 1)));
     FrameBatch fb[2];
     for (FrameBatch& b : fb) {
       b.dim = dim;
