@@ -445,6 +445,9 @@ void Engine::EncodeMaps() {
     a.ab_format = elem_ == kBF16 ? 1 : 0;
     a.num_stages = 64;
     if (const char* env = std::getenv("CVX_GEMM_STAGES")) a.num_stages = std::max(1, std::atoi(env));
+    // first layers (K <= 128): weight half-tiles stay in shared memory for the whole launch
+    a.resident_b = a.num_kb <= 2 ? 1 : 0;
+    if (const char* env = std::getenv("CVX_RESIDENT_W")) a.resident_b = a.resident_b && env[0] != '0';
     BuildHaloArgs(op);
   }
 }

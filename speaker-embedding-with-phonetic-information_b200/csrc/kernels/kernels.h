@@ -61,6 +61,10 @@ struct TdnnGemmArgs {
   float* pool_partials;            // [slots][2][pool_ld]: sum x, sum x^2 per slot and column
   int32_t pool_ld;
   int32_t num_stages;     // smem ring depth actually used (<= the kernel's maximum; tuning aid)
+  // pair kernel, layers with at most 2 K blocks (K <= 128, the first TDNN layers): every CTA pair
+  // keeps ONE tile column for the whole launch and loads its weight half-tiles once instead of with
+  // every tile -- a quarter of the bytes such a tile moves through the SM
+  int32_t resident_b;
 };
 
 size_t TdnnGemmSmemBytes();

@@ -34,7 +34,7 @@ constexpr int kSmemB = kSmemA + kStages * kABytes;      // 98304
 constexpr int kSmemC = kSmemB + kStages * kBBytes;      // 196608
 constexpr int kSmemPost = kSmemC + 8 * kCWarpBytes;     // 229376
 constexpr int kSmemBars = kSmemPost + kGemmBlockN * 8;  // 231424
-constexpr int kNumBars = 2 * kStages + 4;
+constexpr int kNumBars = 2 * kStages + 5;
 constexpr int kSmemTmemPtr = kSmemBars + kNumBars * 8;  // 231552
 constexpr int kSmemTotal = kSmemTmemPtr + 32;           // 231584 <= 232448
 constexpr int kTmemCols = 512;
@@ -82,6 +82,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   uint64_t* empty_bar = full_bar + kStages;                            // per CTA
   uint64_t* tmem_full_bar = empty_bar + kStages;                       // per CTA
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;                        // used in the leader
+  uint64_t* b_res_bar = tmem_empty_bar + 2;                            // used in the leader (resident weights)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + kSmemTmemPtr);
 
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x) >> 5, 0);
@@ -98,6 +99,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       ptx::mbar_init(&tmem_full_bar[i], 1);
       ptx::mbar_init(&tmem_empty_bar[i], 2 * kEpilogueWarps);
     }
+    ptx::mbar_init(b_res_bar, 2);
     ptx::fence_mbar_init();
   }
   if (warp == 0 && lane == 0) {
@@ -118,6 +120,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   const int num_tiles = ((args.num_m_tiles + 1) >> 1) * num_n_tiles;  // 256-row tiles
   const int num_kb = args.num_kb;
   const int nstages = min(max(args.num_stages, 1), kStages);
+  const bool resident = args.resident_b != 0;
   const int first_tile = blockIdx.x >> 1;
   const int tile_step = gridDim.x >> 1;
 
@@ -126,7 +129,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     {
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t stage_bytes = kABytes + args.b_box_rows_pair * kGemmBlockK * 2;
+      const uint32_t b_bytes = args.b_box_rows_pair * kGemmBlockK * 2;
+      const uint32_t stage_bytes = kABytes + (resident ? 0u : b_bytes);
+      if (resident && first_tile < num_tiles) {
+        // this pair's tile column never changes (tile_step is a multiple of num_n_tiles): W slot kb holds
+        // K block kb for the whole launch
+        const int n0 = (first_tile % num_n_tiles) * args.tile_n;
+        const int n_cols = min(args.tile_n, args.n_mma - n0);
+        const int nb0 = n0 + static_cast<int>(rank) * (n_cols >> 1);
+        if (ptx::elect_one_sync()) {
+          ptx::mbar_arrive_expect_tx_cluster(b_res_bar, b_bytes * num_kb, 0);
+          for (int kb = 0; kb < num_kb; ++kb)
+            ptx::tma_load_2d_pair(smem_b + kb * kBBytes, &args.b_map_pair, b_res_bar, 0, kb * kGemmBlockK, nb0);
+        }
+        __syncwarp();
+      }
       for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
         const int m0 = (tile / num_n_tiles) * (2 * kGemmBlockM) + static_cast<int>(rank) * kGemmBlockM;
         const int n0 = (tile % num_n_tiles) * args.tile_n;
@@ -139,8 +156,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
             const KBlockDesc d = args.kb[kb];
             ptx::tma_load_2d_pair(smem_a + stage * kABytes, &args.a_maps[d.src], &full_bar[stage], 0, d.col,
                                   m0 + d.rowoff);
-            ptx::tma_load_2d_pair(smem_b + stage * kBBytes, &args.b_map_pair, &full_bar[stage], 0,
-                                  kb * kGemmBlockK, nb0);
+            if (!resident)
+              ptx::tma_load_2d_pair(smem_b + stage * kBBytes, &args.b_map_pair, &full_bar[stage], 0,
+                                    kb * kGemmBlockK, nb0);
           }
           __syncwarp();
           if (++stage == nstages) {
@@ -156,6 +174,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+      if (resident && first_tile < num_tiles) ptx::mbar_wait(b_res_bar, 0);  // both CTAs' weight half-tiles have landed
       for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
         const int n0 = (tile % num_n_tiles) * args.tile_n;
         const int n_cols = min(args.tile_n, args.n_mma - n0);  // multiple of 16
@@ -169,7 +188,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
           ptx::mbar_wait(&full_bar[stage], phase);  // both CTAs' A and W halves have landed
           ptx::tcgen05_fence_after();
           const uint64_t a_desc = ptx::make_umma_desc_sw128(ptx::smem_u32(smem_a + stage * kABytes));
-          const uint64_t b_desc = ptx::make_umma_desc_sw128(ptx::smem_u32(smem_b + stage * kBBytes));
+          const uint64_t b_desc = ptx::make_umma_desc_sw128(ptx::smem_u32(smem_b + (resident ? kb : stage) * kBBytes));
           const int k16 = args.kb[kb].k16;
           if (ptx::elect_one_sync()) {
 #pragma unroll
@@ -373,7 +392,14 @@ cudaError_t LaunchTdnnGemmPair(const TdnnGemmArgs& args, int num_sms, cudaStream
   if (e != cudaSuccess) return e;
   const int tiles = ((args.num_m_tiles + 1) / 2) * args.num_n_tiles;
   if (tiles <= 0) return cudaSuccess;
-  const int clusters = tiles < num_sms / 2 ? tiles : num_sms / 2;
+  int clusters = tiles < num_sms / 2 ? tiles : num_sms / 2;
+  if (args.resident_b) {
+    if (args.num_kb > kStages) return cudaErrorInvalidValue;
+    // a pair must keep its tile column: the stride over tiles is a multiple of the column count
+    // (tiles itself is one, so at least num_n_tiles pairs remain)
+    clusters = clusters / args.num_n_tiles * args.num_n_tiles;
+    if (clusters == 0) clusters = args.num_n_tiles;
+  }
   kern<<<2 * clusters, kThreads, kSmemTotal, stream>>>(args);
   return cudaGetLastError();
 }
