@@ -227,6 +227,23 @@ int32_t cvx_engine_output_dim(const cvx_engine* engine);
 int cvx_transform_vectors(int32_t device, const float* in, int64_t num_vectors, int32_t dim,
                           const cvx_vector_chain* chain, float* out, float* ratios);
 
+/* PLDA scoring, the last step of the back-end (`ivector-plda-scoring`, run_sre10.sh:122-129):
+ * enrolment vectors train [num_train, dim_in] (speaker means over train_num_utts[i] utterances;
+ * NULL = 1 each) and test vectors test [num_test, dim_in] are centred and projected by the model
+ * (y = transform (x - mean)), length-normalised the PLDA way when normalize_length is set
+ * (simple_length_norm: to sqrt(dim) instead), and every trial (trial_train[t], trial_test[t])
+ * gets its log-likelihood ratio.  Double precision on the device, like upstream. */
+typedef struct cvx_plda {
+  const double* mean;      /* [dim_in] */
+  const double* transform; /* [dim, dim_in] row-major: diagonalises the within- and between-class covariances */
+  const double* psi;       /* [dim] between-class variances in the transformed space */
+  int32_t dim_in, dim;
+  int32_t normalize_length, simple_length_norm; /* --normalize-length, --simple-length-normalization */
+} cvx_plda;
+int cvx_plda_score(int32_t device, const cvx_plda* plda, const float* train, const int32_t* train_num_utts,
+                   int32_t num_train, const float* test, int32_t num_test, const int32_t* trial_train,
+                   const int32_t* trial_test, int64_t num_trials, float* scores);
+
 /* ------------------------------------------------- frame-level outputs --
  * Replaces DecodableNnetSimple::GetOutput over a whole utterance as nnet3-compute uses it
  * [UPSTREAM-RECALL nnet3/nnet-am-decodable-simple.cc]: utterance u owns rows

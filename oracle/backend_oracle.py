@@ -65,3 +65,27 @@ def speaker_means(spk2utt: Sequence[Tuple[str, Sequence[str]]], vectors: Dict[st
         out.append((spk, np.mean(have, axis=0)))
         counts.append((spk, len(have)))
     return out, counts, missing
+
+
+def plda_transform(x, mean, transform, psi, num_examples=1, normalize_length=True, simple_length_norm=False):
+    """Plda::TransformIvector + GetNormalizationFactor [UPSTREAM-RECALL ivector/plda.cc]:
+    y = transform (x - mean); y *= sqrt(dim / sum y^2 / (psi + 1/n)) (or sqrt(dim) / ||y||)."""
+    y = (np.asarray(x, np.float64) - np.asarray(mean, np.float64)) @ np.asarray(transform, np.float64).T
+    n = np.broadcast_to(np.asarray(num_examples, np.float64), y.shape[:1])
+    if simple_length_norm:
+        f = np.sqrt(y.shape[1]) / np.sqrt((y * y).sum(axis=1))
+    else:
+        f = np.sqrt(y.shape[1] / (y * y / (np.asarray(psi, np.float64) + 1.0 / n[:, None])).sum(axis=1))
+    return y * f[:, None] if normalize_length else y
+
+
+def plda_llr(train, n, test, psi):
+    """Plda::LogLikelihoodRatio for one (transformed) enrolment vector averaged over n utterances and
+    one transformed test vector."""
+    psi = np.asarray(psi, np.float64)
+    mean = n * psi / (n * psi + 1.0) * train
+    var = 1.0 + psi / (n * psi + 1.0)
+    given = -0.5 * (np.log(var).sum() + np.log(2 * np.pi) * len(psi) + ((test - mean) ** 2 / var).sum())
+    var0 = psi + 1.0
+    without = -0.5 * (np.log(var0).sum() + np.log(2 * np.pi) * len(psi) + (test ** 2 / var0).sum())
+    return given - without

@@ -55,6 +55,11 @@ class VectorChain(C.Structure):
                 ("transform_cols", C.c_int32), ("normalize_length", C.c_int32), ("scaleup", C.c_int32)]
 
 
+class PldaModel(C.Structure):
+    _fields_ = [("mean", C.c_void_p), ("transform", C.c_void_p), ("psi", C.c_void_p), ("dim_in", C.c_int32),
+                ("dim", C.c_int32), ("normalize_length", C.c_int32), ("simple_length_norm", C.c_int32)]
+
+
 def _make_chain(mean, transform, normalize_length, scaleup):
     """-> (VectorChain, keep-alive arrays)."""
     ch = VectorChain()
@@ -78,7 +83,7 @@ ABI_SYMBOLS = [
     "cvx_last_error", "cvx_version", "cvx_model_load", "cvx_model_load_frames", "cvx_model_from_plan", "cvx_model_free",
     "cvx_model_get_info", "cvx_model_input_name", "cvx_model_input_dim", "cvx_model_describe",
     "cvx_engine_options_default", "cvx_engine_create", "cvx_engine_destroy", "cvx_extract",
-    "cvx_engine_last_chunk_embeddings", "cvx_extract_raw", "cvx_compute_frames", "cvx_engine_set_vector_chain", "cvx_engine_output_dim", "cvx_transform_vectors",
+    "cvx_engine_last_chunk_embeddings", "cvx_extract_raw", "cvx_compute_frames", "cvx_engine_set_vector_chain", "cvx_engine_output_dim", "cvx_transform_vectors", "cvx_plda_score",
     "cvx_test_prestep", "cvx_host_alloc", "cvx_host_free", "cvx_device_alloc",
     "cvx_device_free", "cvx_memcpy_h2d", "cvx_device_count", "cvx_engine_get_profile",
     "cvx_engine_reset_profile", "cvx_engine_launch_count", "cvx_engine_last_extract_ms", "cvx_test_tdnn_layer", "cvx_test_tdnn_layer_bench", "cvx_test_stats_pool",
@@ -128,6 +133,8 @@ def load_library() -> C.CDLL:
     lib.cvx_engine_output_dim.restype = C.c_int32
     lib.cvx_transform_vectors.argtypes = [C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.POINTER(VectorChain), C.c_void_p,
                                           C.c_void_p]
+    lib.cvx_plda_score.argtypes = [C.c_int32, C.POINTER(PldaModel), C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
+                                   C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     lib.cvx_engine_last_chunk_embeddings.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
     lib.cvx_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
     lib.cvx_host_free.argtypes = [C.c_void_p]
@@ -437,6 +444,29 @@ def transform_vectors(vectors: np.ndarray, mean=None, transform=None, normalize_
     ratios = np.zeros(v.shape[0], np.float32)
     _check(lib.cvx_transform_vectors(device, _ptr(v), v.shape[0], v.shape[1], C.byref(ch), _ptr(out), _ptr(ratios)))
     return out, ratios
+
+
+def plda_score(mean, transform, psi, train, test, trial_train, trial_test, train_num_utts=None,
+               normalize_length: bool = True, simple_length_norm: bool = False, device: int = 0) -> np.ndarray:
+    """PLDA log-likelihood ratios of a trial list on the device (cvx_plda_score), what
+    `ivector-plda-scoring [--normalize-length=true] [--num-utts=...]` writes per trial."""
+    lib = load_library()
+    m = PldaModel()
+    mean = np.ascontiguousarray(mean, np.float64)
+    tf = np.ascontiguousarray(transform, np.float64)
+    psi = np.ascontiguousarray(psi, np.float64)
+    m.mean, m.transform, m.psi = mean.ctypes.data, tf.ctypes.data, psi.ctypes.data
+    m.dim, m.dim_in = tf.shape
+    m.normalize_length, m.simple_length_norm = int(bool(normalize_length)), int(bool(simple_length_norm))
+    tr = np.ascontiguousarray(train, np.float32)
+    te = np.ascontiguousarray(test, np.float32)
+    ti = np.ascontiguousarray(trial_train, np.int32)
+    tj = np.ascontiguousarray(trial_test, np.int32)
+    nu = None if train_num_utts is None else np.ascontiguousarray(train_num_utts, np.int32)
+    scores = np.zeros(len(ti), np.float32)
+    _check(lib.cvx_plda_score(device, C.byref(m), _ptr(tr), _ptr(nu), tr.shape[0], _ptr(te), te.shape[0], _ptr(ti), _ptr(tj),
+                              len(ti), _ptr(scores)))
+    return scores
 
 
 def test_stats_pool(x: np.ndarray, begin: Sequence[int], end: Sequence[int], precision: str = "fp16",

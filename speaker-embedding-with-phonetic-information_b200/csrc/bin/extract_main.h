@@ -17,6 +17,7 @@ int IvectorMeanMain(int argc, const char* const* argv);
 int SubtractGlobalMeanMain(int argc, const char* const* argv);
 int TransformVecMain(int argc, const char* const* argv);
 int NormalizeLengthMain(int argc, const char* const* argv);
+int PldaScoringMain(int argc, const char* const* argv);
 // Kaldi object files holding one vector / one matrix (mean.vec, transform.mat)
 std::vector<float> ReadVectorFile(const std::string& rxfilename);
 Matrix ReadMatrixFile(const std::string& rxfilename);

@@ -306,4 +306,148 @@ int NormalizeLengthMain(int argc, const char* const* argv) {
   }
 }
 
+// ivector-plda-scoring (run_sre10.sh:122-129): every trial "<enrolled-speaker> <test-utterance>" gets
+// the PLDA log-likelihood ratio of the two vectors; transform, length normalisation and the scoring
+// of the whole trial list run on the device (cvx_plda_score).
+int PldaScoringMain(int argc, const char* const* argv) {
+  try {
+    ParseOptions po(
+        "Scores trials with a PLDA model: for every line '<key1> <key2>' of the trials file, key1 a\n"
+        "vector of the first (enrolment) table, key2 one of the second (test) table, writes\n"
+        "'<key1> <key2> <log-likelihood-ratio>'.\n"
+        "Usage: ivector-plda-scoring [options] <plda> <train-ivector-rspecifier> <test-ivector-rspecifier>\n"
+        " <trials-rxfilename> <scores-wxfilename>\n"
+        "e.g.: ivector-plda-scoring --num-utts=ark:exp/train/num_utts.ark plda ark:exp/train/spk_ivectors.ark\n"
+        " ark:exp/test/ivectors.ark trials scores\n");
+    std::string num_utts_rspecifier;
+    bool normalize_length = false, simple_length_norm = false;
+    po.Register("num-utts", &num_utts_rspecifier,
+                "Table of the number of utterances behind every enrolment vector (written by ivector-mean); default 1");
+    po.Register("normalize-length", &normalize_length, "If true, do PLDA length normalisation of the transformed vectors");
+    po.Register("simple-length-normalization", &simple_length_norm,
+                "If true, normalise to length sqrt(dim) instead of the PLDA-specific normalisation");
+    po.Read(argc, argv);
+    if (po.NumArgs() != 5) {
+      po.PrintUsage();
+      return 1;
+    }
+    // <Plda> mean (vector) transform (matrix) psi (vector) </Plda>
+    std::vector<float> mean_f, psi_f;
+    Matrix tf_f;
+    {
+      Input in(po.GetArg(1));
+      const bool binary = ReadBinaryHeader(in);
+      ExpectToken(in, "<Plda>");
+      ReadVector(in, binary, &mean_f);
+      ReadMatrix(in, binary, &tf_f);
+      ReadVector(in, binary, &psi_f);
+      ExpectToken(in, "</Plda>");
+      int st = in.Close();
+      if (st != 0) throw KaldiError("the PLDA input pipe exited with status " + std::to_string(st));
+    }
+    if (tf_f.cols != static_cast<int32_t>(mean_f.size()) || tf_f.rows != static_cast<int32_t>(psi_f.size()))
+      throw KaldiError("inconsistent dimensions in the PLDA model " + po.GetArg(1));
+    std::vector<double> mean(mean_f.begin(), mean_f.end()), psi(psi_f.begin(), psi_f.end()),
+        tf(tf_f.Data(), tf_f.Data() + static_cast<size_t>(tf_f.rows) * tf_f.cols);
+
+    VectorTable train = ReadVectorTable(po.GetArg(2)), test = ReadVectorTable(po.GetArg(3));
+    if ((train.size() && train.dim != tf_f.cols) || (test.size() && test.dim != tf_f.cols))
+      throw KaldiError("vector dimension does not match the PLDA model (" + std::to_string(tf_f.cols) + ")");
+    std::map<std::string, int32_t> train_index, test_index;
+    for (int64_t i = 0; i < train.size(); ++i) train_index[train.keys[i]] = static_cast<int32_t>(i);
+    for (int64_t i = 0; i < test.size(); ++i) test_index[test.keys[i]] = static_cast<int32_t>(i);
+    std::vector<int32_t> num_utts(static_cast<size_t>(train.size()), 1);
+    if (!num_utts_rspecifier.empty()) {
+      TableSpec spec = ParseRspecifier(num_utts_rspecifier);
+      if (spec.is_scp) throw KaldiError("--num-utts must be an archive of integers (ark:), as written by ivector-mean ... ark,t:");
+      Input in(spec.ark_name);
+      std::map<std::string, int32_t> seen;
+      while (!in.Eof()) {
+        std::istringstream line(in.ReadLine());
+        std::string key;
+        int32_t n = 0;
+        if (!(line >> key)) continue;
+        if (!(line >> n) || n <= 0) throw KaldiError("bad line for " + key + " in " + num_utts_rspecifier + " (text archives only)");
+        seen[key] = n;
+      }
+      in.Close();
+      for (int64_t i = 0; i < train.size(); ++i) {
+        auto it = seen.find(train.keys[i]);
+        if (it == seen.end()) throw KaldiError("Number of utterances not given for speaker " + train.keys[i]);
+        num_utts[i] = it->second;
+      }
+    }
+
+    std::vector<int32_t> ti, tj;
+    std::vector<std::pair<std::string, std::string>> names;
+    int64_t num_err = 0;
+    {
+      Input in(po.GetArg(4));
+      while (!in.Eof()) {
+        std::istringstream line(in.ReadLine());
+        std::string k1, k2;
+        if (!(line >> k1)) continue;
+        if (!(line >> k2)) throw KaldiError("Bad line in the trials file: expected two or more fields");
+        auto a = train_index.find(k1);
+        auto b = test_index.find(k2);
+        if (a == train_index.end()) {
+          CVX_WARN("Key " << k1 << " not present in training iVectors.");
+          ++num_err;
+          continue;
+        }
+        if (b == test_index.end()) {
+          CVX_WARN("Key " << k2 << " not present in test iVectors.");
+          ++num_err;
+          continue;
+        }
+        ti.push_back(a->second);
+        tj.push_back(b->second);
+        names.emplace_back(k1, k2);
+      }
+      in.Close();
+    }
+    std::vector<float> scores(ti.size(), 0.f);
+    if (!ti.empty()) {
+      cvx_plda model;
+      std::memset(&model, 0, sizeof(model));
+      model.mean = mean.data();
+      model.transform = tf.data();
+      model.psi = psi.data();
+      model.dim_in = tf_f.cols;
+      model.dim = tf_f.rows;
+      model.normalize_length = normalize_length ? 1 : 0;
+      model.simple_length_norm = simple_length_norm ? 1 : 0;
+      if (cvx_plda_score(DeviceFromEnv(), &model, train.data.data(), num_utts.data(), static_cast<int32_t>(train.size()),
+                         test.data.data(), static_cast<int32_t>(test.size()), ti.data(), tj.data(),
+                         static_cast<int64_t>(ti.size()), scores.data()) != CVX_OK)
+        throw KaldiError(std::string("cvx_plda_score failed: ") + cvx_last_error());
+    }
+    Output out;
+    out.Open(po.GetArg(5));
+    std::string buf;
+    double sum = 0.0, sumsq = 0.0;
+    for (size_t t = 0; t < names.size(); ++t) {
+      char num[48];
+      std::snprintf(num, sizeof num, "%.9g", scores[t]);
+      buf += names[t].first + " " + names[t].second + " " + num + "\n";
+      sum += scores[t];
+      sumsq += static_cast<double>(scores[t]) * scores[t];
+      if (buf.size() > (1u << 20)) {
+        out.Write(buf);
+        buf.clear();
+      }
+    }
+    out.Write(buf);
+    if (out.Close() != 0) throw KaldiError("error closing " + po.GetArg(5));
+    if (!names.empty()) {
+      const double m = sum / names.size(), sd = std::sqrt(std::max(0.0, sumsq / names.size() - m * m));
+      CVX_LOG("Mean score was " << m << ", standard deviation was " << sd);
+    }
+    CVX_LOG("Processed " << names.size() << " trials, " << num_err << " had errors.");
+    return !names.empty() ? 0 : 1;
+  } catch (const std::exception& e) {
+    return Fail(e);
+  }
+}
+
 }  // namespace cvx

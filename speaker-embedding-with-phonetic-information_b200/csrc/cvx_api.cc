@@ -213,6 +213,17 @@ int cvx_transform_vectors(int32_t device, const float* in, int64_t num_vectors, 
   return Guard([&] { cvx::TransformVectors(device, in, num_vectors, dim, *chain, out, ratios); });
 }
 
+int cvx_plda_score(int32_t device, const cvx_plda* plda, const float* train, const int32_t* train_num_utts, int32_t num_train,
+                   const float* test, int32_t num_test, const int32_t* trial_train, const int32_t* trial_test,
+                   int64_t num_trials, float* scores) {
+  if (!plda || !plda->mean || !plda->transform || !plda->psi) return Fail(CVX_ERR_INVALID, "cvx_plda_score: NULL model");
+  if (num_trials > 0 && (!train || !test || !trial_train || !trial_test || !scores))
+    return Fail(CVX_ERR_INVALID, "cvx_plda_score: NULL argument");
+  return Guard([&] {
+    cvx::PldaScore(device, *plda, train, train_num_utts, num_train, test, num_test, trial_train, trial_test, num_trials, scores);
+  });
+}
+
 int cvx_compute_frames(cvx_engine* engine, const float* const* feats, int32_t num_streams, int64_t total_rows,
                        const int64_t* utt_start, int32_t num_utts, float* out, uint32_t flags) {
   if (!engine) return Fail(CVX_ERR_INVALID, "cvx_compute_frames: NULL engine");

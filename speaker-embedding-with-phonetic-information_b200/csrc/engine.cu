@@ -1165,6 +1165,56 @@ void TransformVectors(int32_t device, const float* in, int64_t n, int32_t dim, c
   cleanup();
 }
 
+namespace {
+// RAII for the few device buffers of the stand-alone entry points
+struct DevBuf {
+  void* p = nullptr;
+  ~DevBuf() { cudaFree(p); }
+  template <typename T>
+  T* Upload(const T* host, size_t n) {
+    CVX_CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+    if (host && n) CVX_CUDA_CHECK(cudaMemcpy(p, host, n * sizeof(T), cudaMemcpyHostToDevice));
+    return static_cast<T*>(p);
+  }
+};
+}  // namespace
+
+void PldaScore(int32_t device, const cvx_plda& plda, const float* train, const int32_t* train_num_utts, int32_t num_train,
+               const float* test, int32_t num_test, const int32_t* trial_train, const int32_t* trial_test, int64_t num_trials,
+               float* scores) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    throw CudaError("no usable CUDA device; this path has no CPU fallback");
+  if (device < 0 || device >= ndev) throw InvalidArgument("device ordinal out of range");
+  if (plda.dim_in <= 0 || plda.dim <= 0 || num_train < 0 || num_test < 0 || num_trials < 0) throw InvalidArgument("bad PLDA sizes");
+  if (num_trials == 0) return;
+  for (int64_t t = 0; t < num_trials; ++t)
+    if (trial_train[t] < 0 || trial_train[t] >= num_train || trial_test[t] < 0 || trial_test[t] >= num_test)
+      throw InvalidArgument("trial " + std::to_string(t) + " refers to a vector that does not exist");
+  for (int32_t i = 0; train_num_utts && i < num_train; ++i)
+    if (train_num_utts[i] <= 0) throw InvalidArgument("train_num_utts must be positive");
+  CVX_CUDA_CHECK(cudaSetDevice(device));
+  const size_t di = plda.dim_in, d = plda.dim;
+  DevBuf b_mean, b_tf, b_psi, b_train, b_test, b_n, b_ytrain, b_ytest, b_ti, b_tj, b_scores;
+  const double* d_mean = b_mean.Upload(plda.mean, di);
+  const double* d_tf = b_tf.Upload(plda.transform, d * di);
+  const double* d_psi = b_psi.Upload(plda.psi, d);
+  const float* d_train = b_train.Upload(train, static_cast<size_t>(num_train) * di);
+  const float* d_test = b_test.Upload(test, static_cast<size_t>(num_test) * di);
+  const int32_t* d_n = train_num_utts ? b_n.Upload(train_num_utts, static_cast<size_t>(num_train)) : nullptr;
+  double* d_ytrain = b_ytrain.Upload<double>(nullptr, static_cast<size_t>(num_train) * d);
+  double* d_ytest = b_ytest.Upload<double>(nullptr, static_cast<size_t>(num_test) * d);
+  const int32_t* d_ti = b_ti.Upload(trial_train, static_cast<size_t>(num_trials));
+  const int32_t* d_tj = b_tj.Upload(trial_test, static_cast<size_t>(num_trials));
+  float* d_scores = b_scores.Upload<float>(nullptr, static_cast<size_t>(num_trials));
+  CVX_CUDA_CHECK(LaunchPldaTransform(d_train, num_train, plda.dim_in, d_mean, d_tf, plda.dim, d_psi, d_n, plda.normalize_length,
+                                     plda.simple_length_norm, d_ytrain, nullptr));
+  CVX_CUDA_CHECK(LaunchPldaTransform(d_test, num_test, plda.dim_in, d_mean, d_tf, plda.dim, d_psi, nullptr, plda.normalize_length,
+                                     plda.simple_length_norm, d_ytest, nullptr));
+  CVX_CUDA_CHECK(LaunchPldaScore(d_ytrain, d_n, d_ytest, d_psi, plda.dim, d_ti, d_tj, num_trials, d_scores, nullptr));
+  CVX_CUDA_CHECK(cudaMemcpy(scores, d_scores, static_cast<size_t>(num_trials) * 4, cudaMemcpyDeviceToHost));
+}
+
 // -------------------------------------------------------- frame outputs ----
 // nnet3-compute's product: the output layer at every frame of every utterance.
 // Utterances are packed back to back with `left` + `right` replicated edge frames each, so every

@@ -202,6 +202,11 @@ void TransformVectors(int32_t device, const float* in, int64_t num_vectors, int3
                       float* out, float* ratios);
 void ValidateVectorChain(const cvx_vector_chain& chain, int32_t dim);
 
+// PLDA scoring of a trial list (cvx_plda_score).
+void PldaScore(int32_t device, const cvx_plda& plda, const float* train, const int32_t* train_num_utts, int32_t num_train,
+               const float* test, int32_t num_test, const int32_t* trial_train, const int32_t* trial_test, int64_t num_trials,
+               float* scores);
+
 // Stand-alone pooling run for tests (cvx_test_stats_pool).
 void TestStatsPool(int32_t device, int32_t precision, const float* in, int64_t rows, int32_t dim, const int64_t* begin,
                    const int64_t* end, int64_t num_chunks, float variance_floor, float* out);

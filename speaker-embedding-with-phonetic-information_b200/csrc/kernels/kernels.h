@@ -206,5 +206,13 @@ cudaError_t LaunchVectorChain(const float* in, int64_t num_vectors, int32_t dim,
                               int32_t t_rows, int32_t t_cols, int32_t normalize, int32_t scaleup, int32_t keep_zero,
                               float* out, float* ratios, cudaStream_t stream);
 
+// ---- PLDA scoring (plda.cu): transform + length normalisation of vectors, then one warp per trial ----
+cudaError_t LaunchPldaTransform(const float* in, int64_t num_vectors, int32_t dim_in, const double* mean, const double* transform,
+                                int32_t dim, const double* psi, const int32_t* num_examples, int32_t normalize_length,
+                                int32_t simple_norm, double* out, cudaStream_t stream);
+cudaError_t LaunchPldaScore(const double* train, const int32_t* train_n, const double* test, const double* psi, int32_t dim,
+                            const int32_t* trial_train, const int32_t* trial_test, int64_t num_trials, float* scores,
+                            cudaStream_t stream);
+
 }  // namespace cvx
 #endif  // CVX_KERNELS_KERNELS_H_

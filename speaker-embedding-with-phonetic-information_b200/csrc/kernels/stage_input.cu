@@ -10,6 +10,8 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
+#include <type_traits>
+
 namespace cvx {
 namespace {
 
@@ -26,6 +28,21 @@ __device__ __forceinline__ __nv_bfloat16 to_elem<__nv_bfloat16>(float v) {
 template <>
 __device__ __forceinline__ float to_elem<float>(float v) {
   return v;
+}
+
+// two fp32 values -> one 32-bit word of two 16-bit operands (fp16: saturating, like to_elem)
+template <typename T>
+__device__ __forceinline__ uint32_t pack_pair(float a, float b) {
+  if constexpr (sizeof(T) == 4) {
+    return 0;  // unused for fp32
+  } else if constexpr (std::is_same<T, __half>::value) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+  } else {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
 }
 
 // colmap[c] for output column c: bit 31 = valid, [28,31) stream, [16,28) time offset + 2048,
@@ -95,10 +112,19 @@ __global__ void __launch_bounds__(256) stage_input_tiled_kernel(const __grid_con
     alignas(16) int idx[kVec];
 #pragma unroll
     for (int e = 0; e < kVec; e += 4) *reinterpret_cast<int4*>(&idx[e]) = *reinterpret_cast<const int4*>(&s_src[c0 + e]);
-    alignas(16) T vals[kVec];
+    float v[kVec];
 #pragma unroll
-    for (int e = 0; e < kVec; ++e) vals[e] = to_elem<T>(idx[e] >= 0 ? base[idx[e]] : 0.f);
-    *reinterpret_cast<uint4*>(static_cast<T*>(args.out) + (r0 + row) * args.ld_out + c0) = *reinterpret_cast<uint4*>(vals);
+    for (int e = 0; e < kVec; ++e) v[e] = idx[e] >= 0 ? base[idx[e]] : 0.f;
+    uint4 packed;
+    if constexpr (sizeof(T) == 4) {
+      packed = make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
+    } else {
+      uint32_t w[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) w[e] = pack_pair<T>(v[2 * e], v[2 * e + 1]);  // one saturating convert per column pair
+      packed = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    *reinterpret_cast<uint4*>(static_cast<T*>(args.out) + (r0 + row) * args.ld_out + c0) = packed;
   }
 }
 

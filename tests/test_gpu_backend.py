@@ -162,3 +162,87 @@ def test_cli_extraction_with_fused_backend_chain(cvx, kf, require_gpu, tmp_path)
     ref, _ = vector_chain(np.stack(list(plain.values())), mean, t)
     got = np.stack(list(fused.values()))
     assert got.shape[1] == 24 and np.abs(got - ref).max() <= 3e-5 * np.abs(ref).max()
+
+
+def _plda_model(dim_in, dim, seed):
+    rng = np.random.default_rng(seed)
+    mean = rng.normal(0.1, 0.3, dim_in)
+    tf = rng.normal(0, dim_in ** -0.5, (dim, dim_in))
+    psi = np.sort(rng.uniform(0.05, 8.0, dim))[::-1].copy()
+    return mean, tf, psi
+
+
+@pytest.mark.parametrize("normalize,simple", [(True, False), (True, True), (False, False)])
+def test_plda_scoring_matches_restatement(cvx, require_gpu, normalize, simple):
+    from oracle.backend_oracle import plda_llr, plda_transform
+    rng = np.random.default_rng(5)
+    mean, tf, psi = _plda_model(150, 150, 1)
+    train = rng.normal(0.1, 1.0, (12, 150)).astype(np.float32)
+    test = rng.normal(0.1, 1.0, (40, 150)).astype(np.float32)
+    n = rng.integers(1, 9, 12).astype(np.int32)
+    ti = rng.integers(0, 12, 500).astype(np.int32)
+    tj = rng.integers(0, 40, 500).astype(np.int32)
+    got = cvx.plda_score(mean, tf, psi, train, test, ti, tj, train_num_utts=n, normalize_length=normalize,
+                         simple_length_norm=simple)
+    yt = plda_transform(train, mean, tf, psi, n, normalize, simple)
+    ye = plda_transform(test, mean, tf, psi, 1, normalize, simple)
+    ref = np.array([plda_llr(yt[i], float(n[i]), ye[j], psi) for i, j in zip(ti, tj)])
+    assert np.abs(got - ref).max() <= 1e-4 * max(1.0, np.abs(ref).max())
+    # without num_utts every enrolment vector counts as one utterance
+    got1 = cvx.plda_score(mean, tf, psi, train, test, ti, tj, normalize_length=normalize, simple_length_norm=simple)
+    yt1 = plda_transform(train, mean, tf, psi, 1, normalize, simple)
+    ref1 = np.array([plda_llr(yt1[i], 1.0, ye[j], psi) for i, j in zip(ti, tj)])
+    assert np.abs(got1 - ref1).max() <= 1e-4 * max(1.0, np.abs(ref1).max())
+    with pytest.raises(cvx.CvxError):
+        cvx.plda_score(mean, tf, psi, train, test, [12], [0])          # trial refers to a missing vector
+
+
+def test_cli_plda_scoring(cvx, kf, require_gpu, tmp_path):
+    """ivector-plda-scoring with the recipe's argument shapes (run_sre10.sh:122-129): model through a
+    pipe, --num-utts from ivector-mean's text table, enrolment and test tables through the
+    subtract / transform / normalise pipes, trials through `cut`."""
+    import os
+    import subprocess
+    from oracle.backend_oracle import plda_llr, plda_transform, vector_chain
+    B = cvx.BIN_DIR
+    rng = np.random.default_rng(11)
+    v, gmean, lda = _chain_inputs(64, 20, 30, 13)
+    mean, tf, psi = _plda_model(20, 20, 2)
+    with open(tmp_path / "plda", "wb") as f:
+        f.write(b"\0B<Plda> ")
+        kf.write_vector(f, True, mean)
+        kf.write_matrix(f, True, tf)
+        kf.write_vector(f, True, psi)
+        f.write(b"</Plda> ")
+    _write_obj(kf, f"{tmp_path}/mean.vec", gmean)
+    _write_obj(kf, f"{tmp_path}/transform.mat", lda)
+    spk = [f"spk{i}" for i in range(6)]
+    utt = [f"utt{i:02d}" for i in range(24)]
+    kf.write_ark(f"{tmp_path}/spk.ark", list(zip(spk, v[:6])))
+    kf.write_ark(f"{tmp_path}/test.ark", list(zip(utt, v[6:])))
+    nu = rng.integers(1, 6, 6)
+    with open(tmp_path / "num_utts.ark", "w") as f:
+        for s, n in zip(spk, nu):
+            f.write(f"{s} {n}\n")
+    trials = [(spk[i], utt[j], "target" if (i + j) % 3 == 0 else "nontarget") for i in range(6) for j in range(0, 24, 2)]
+    trials.insert(5, ("spk_missing", utt[0], "nontarget"))
+    with open(tmp_path / "trials", "w") as f:
+        for t in trials:
+            f.write(" ".join(t) + "\n")
+    env = dict(os.environ, PATH=B + os.pathsep + os.environ["PATH"])
+    chain = (f"ivector-subtract-global-mean {tmp_path}/mean.vec ark:{{}} ark:- | transform-vec {tmp_path}/transform.mat ark:- ark:- | "
+             f"ivector-normalize-length ark:- ark:- |")
+    cmd = ["ivector-plda-scoring", "--normalize-length=true", f"--num-utts=ark:{tmp_path}/num_utts.ark",
+           f"cat {tmp_path}/plda |", "ark:" + chain.format(f"{tmp_path}/spk.ark"), "ark:" + chain.format(f"{tmp_path}/test.ark"),
+           f"cat '{tmp_path}/trials' | cut -d\\  --fields=1,2 |", f"{tmp_path}/scores"]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert "Processed 72 trials, 1 had errors." in r.stderr and "Key spk_missing not present in training iVectors." in r.stderr
+    lines = [ln.split() for ln in open(tmp_path / "scores")]
+    assert [(a, b) for a, b, _ in lines] == [(a, b) for a, b, _ in trials if a != "spk_missing"]
+    x, _ = vector_chain(v, gmean, lda)
+    yt = plda_transform(x[:6], mean, tf, psi, nu, True, False)
+    ye = plda_transform(x[6:], mean, tf, psi, 1, True, False)
+    ref = [plda_llr(yt[spk.index(a)], float(nu[spk.index(a)]), ye[utt.index(b)], psi) for a, b, _ in lines]
+    got = np.array([float(s) for _, _, s in lines])
+    assert np.abs(got - np.array(ref)).max() <= 2e-4 * max(1.0, np.abs(ref).max())

@@ -313,3 +313,21 @@ def test_backend_restatement_identities():
     means, counts, missing = speaker_means([("a", ["u0", "u1", "x"]), ("b", ["y"])], {"u0": v[0], "u1": v[1]})
     assert [s for s, _ in means] == ["a"] and counts == [("a", 2)] and missing == 2
     assert np.allclose(means[0][1], (v[0] + v[1]) / 2)
+
+
+def test_plda_restatement_properties():
+    """oracle/backend_oracle.py PLDA: after normalisation sum y^2/(psi + 1/n) == dim; the LLR of a
+    test vector equal to the class-posterior mean beats a far-away one; n only sharpens it."""
+    from oracle.backend_oracle import plda_llr, plda_transform
+    rng = np.random.default_rng(3)
+    mean, tf, psi = rng.normal(0, 1, 10), rng.normal(0, 1, (6, 10)), rng.uniform(0.1, 5, 6)
+    x = rng.normal(0, 1, (4, 10))
+    y = plda_transform(x, mean, tf, psi, 3)
+    assert np.allclose((y * y / (psi + 1 / 3)).sum(axis=1), 6)
+    ys = plda_transform(x, mean, tf, psi, 3, simple_length_norm=True)
+    assert np.allclose(np.linalg.norm(ys, axis=1), np.sqrt(6))
+    assert np.allclose(plda_transform(x, mean, tf, psi, 3, normalize_length=False), (x - mean) @ tf.T)
+    near = plda_llr(y[0], 3.0, 3 * psi / (3 * psi + 1) * y[0], psi)
+    far = plda_llr(y[0], 3.0, -y[0], psi)
+    assert near > 0 > far
+    assert plda_llr(y[0], 8.0, y[0], psi) > plda_llr(y[0], 1.0, y[0], psi)
