@@ -253,52 +253,67 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
           const bool has_a = meta.a1 > meta.a0, has_b = meta.b1 > meta.b0;
           if (!has_a && !has_b) break;  // no valid row in this 32-row group (edge / gap rows)
           const bool half_chunk = (n_cols - c * 64) < 64;
-#pragma unroll 1
-          for (int h = 0; h < 2; ++h) {
-            if (h == 1 && half_chunk) break;
-            uint32_t r[32];
-            ptx::tmem_ld_32x32b_x32(t_row + c * 64 + h * 32, r);
-            ptx::tmem_ld_wait();
-            uint32_t pk[16];  // this lane's row, rounded to the operand type: the values a consumer would read
+          // both 32-column halves of the chunk: loaded, rounded to the operand type (the values a
+          // consumer would read) and transposed together, so that each lane then sums TWO columns
+          // (one per half) with independent dependency chains.
+          uint32_t r0[32], r1[32];
+          ptx::tmem_ld_32x32b_x32(t_row + c * 64, r0);
+          if (!half_chunk) ptx::tmem_ld_32x32b_x32(t_row + c * 64 + 32, r1);
+          ptx::tmem_ld_wait();
+          uint32_t pk0[16], pk1[16];
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint32_t p4[4];
-              epi::pack8<kBF16>(&r[j], smem + kSmemPost, c * 64 + h * 32 + j, args.relu != 0, p4);
+          for (int j = 0; j < 32; j += 8) {
+            uint32_t p4[4];
+            epi::pack8<kBF16>(&r0[j], smem + kSmemPost, c * 64 + j, args.relu != 0, p4);
 #pragma unroll
-              for (int e = 0; e < 4; ++e) pk[(j >> 1) + e] = p4[e];
+            for (int e = 0; e < 4; ++e) pk0[(j >> 1) + e] = p4[e];
+            if (!half_chunk) {
+              epi::pack8<kBF16>(&r1[j], smem + kSmemPost, c * 64 + 32 + j, args.relu != 0, p4);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) pk1[(j >> 1) + e] = p4[e];
             }
-            // transpose through this warp's (otherwise unused) staging buffer as 16-bit values:
-            // lane = row writes its 16 words, word index ^ (row >> 1); then lane = column reads one
-            // 16-bit value per row and accumulates it with the mixed-precision FHADD / FHFMA
-            // (fp32 += fp16, no unpacking).  Both phases are bank-conflict free.
-            uint32_t* tile = reinterpret_cast<uint32_t*>(buf);
-            __syncwarp();
+          }
+          // transpose through this warp's (otherwise unused) staging buffer as 16-bit values, one
+          // 2 KB tile per half: lane = row writes its 16 words, word index ^ (row >> 1); then lane =
+          // column reads one 16-bit value per row and accumulates it with the mixed-precision
+          // FHADD / FHFMA (fp32 += fp16, no unpacking).  Both phases are bank-conflict free.
+          uint32_t* tile = reinterpret_cast<uint32_t*>(buf);
+          __syncwarp();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) tile[lane * 16 + (j ^ (lane >> 1))] = pk[j];
-            __syncwarp();
-            const uint32_t lp = static_cast<uint32_t>(lane) << 1;  // byte offset of column `lane` in an un-swizzled row
-            auto row_value = [&](int r) -> uint16_t {
-              return *reinterpret_cast<const uint16_t*>(buf + r * 64 + (lp ^ (static_cast<uint32_t>(r >> 1) << 2)));
-            };
+          for (int j = 0; j < 16; ++j) {
+            tile[lane * 16 + (j ^ (lane >> 1))] = pk0[j];
+            if (!half_chunk) tile[512 + lane * 16 + (j ^ (lane >> 1))] = pk1[j];
+          }
+          __syncwarp();
+          const uint32_t lp = static_cast<uint32_t>(lane) << 1;  // byte offset of column `lane` in an un-swizzled row
+          auto row_value = [&](int h, int r) -> uint16_t {
+            return *reinterpret_cast<const uint16_t*>(buf + h * 2048 + r * 64 + (lp ^ (static_cast<uint32_t>(r >> 1) << 2)));
+          };
 #pragma unroll 1
-            for (int seg = 0; seg < 2; ++seg) {
-              const int lo = seg ? meta.b0 : meta.a0, hi = seg ? meta.b1 : meta.a1;
-              if (hi <= lo) continue;
-              float sx0 = 0.f, sx1 = 0.f, sxx0 = 0.f, sxx1 = 0.f;
-              if (lo == 0 && hi == 32) {  // interior group: every row is valid
+          for (int seg = 0; seg < 2; ++seg) {
+            const int lo = seg ? meta.b0 : meta.a0, hi = seg ? meta.b1 : meta.a1;
+            if (hi <= lo) continue;
+            float sx0 = 0.f, sxx0 = 0.f, sx1 = 0.f, sxx1 = 0.f;  // column `lane` of half 0 / half 1
+            if (lo == 0 && hi == 32 && !half_chunk) {  // interior group: every row is valid
 #pragma unroll
-                for (int r = 0; r < 32; r += 2) {
-                  accum16<kBF16>(row_value(r), sx0, sxx0);
-                  accum16<kBF16>(row_value(r + 1), sx1, sxx1);
-                }
-              } else {
-#pragma unroll 2
-                for (int r = lo; r < hi; ++r) accum16<kBF16>(row_value(r), sx0, sxx0);
+              for (int r = 0; r < 32; ++r) {
+                accum16<kBF16>(row_value(0, r), sx0, sxx0);
+                accum16<kBF16>(row_value(1, r), sx1, sxx1);
               }
-              const int slot = meta.slot + ((seg && has_a) ? 1 : 0);
-              float* out = args.pool_partials + static_cast<int64_t>(slot) * 2 * args.pool_ld + n0 + c * 64 + h * 32 + lane;
-              out[0] = sx0 + sx1;
-              out[args.pool_ld] = sxx0 + sxx1;
+            } else {
+#pragma unroll 2
+              for (int r = lo; r < hi; ++r) {
+                accum16<kBF16>(row_value(0, r), sx0, sxx0);
+                if (!half_chunk) accum16<kBF16>(row_value(1, r), sx1, sxx1);
+              }
+            }
+            const int slot = meta.slot + ((seg && has_a) ? 1 : 0);
+            float* out = args.pool_partials + static_cast<int64_t>(slot) * 2 * args.pool_ld + n0 + c * 64 + lane;
+            out[0] = sx0;
+            out[args.pool_ld] = sxx0;
+            if (!half_chunk) {
+              out[32] = sx1;
+              out[args.pool_ld + 32] = sxx1;
             }
           }
           continue;
