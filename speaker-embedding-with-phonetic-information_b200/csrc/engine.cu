@@ -320,12 +320,13 @@ Engine::~Engine() {
     cudaFree(d_raw_[s]);
     cudaFree(d_sel_[s]);
   }
-  void* pre_scratch[] = {d_prefix_, d_pre_utt_start_, d_pre_kept_utt_, d_pre_keep_};
+  void* pre_scratch[] = {d_pre_aux_, d_pre_utt_start_, d_pre_kept_utt_, d_pre_keep_};
   for (void* p : pre_scratch) cudaFree(p);
   cudaFree(d_pool_meta_);
   cudaFree(d_slot_n_);
   cudaFree(d_slot_begin_);
   cudaFree(d_chunk_rng_);
+  for (cudaEvent_t ev : piece_events_) cudaEventDestroy(ev);
   cudaFree(d_seg_hi_);
   cudaFree(d_seg_lo_);
   for (SegOp& s : seg_ops_) {
@@ -946,6 +947,7 @@ void Engine::Extract(const float* const* feats, int32_t num_streams, int64_t tot
     const float* dev[kMaxASources] = {};
     int64_t src_min, src_max;
     if (dev_in) {
+      if (before_batch_) before_batch_(b.row1);  // cvx_extract_raw: pre-step of the pieces this batch reads
       for (int32_t s = 0; s < num_streams; ++s) dev[s] = feats[s] + b.row0 * plan_.input_dims[s];
       src_min = -b.row0;
       src_max = total_rows - b.row0;
@@ -1356,29 +1358,47 @@ void Engine::ComputeFrames(const float* const* feats, int32_t num_streams, int64
 }
 
 // ------------------------------------------------------------ pre-step ----
-void Engine::RunPrestep(int32_t s, int32_t dim, const float* host_raw, const cvx_prestep& pre, int64_t total_raw_rows,
-                        const int64_t* utt_raw_start, const int32_t* keep, const int64_t* utt_kept_start,
-                        int32_t num_utts) {
-  if (pre.norm_vars) throw InvalidArgument("sliding CMN with --norm-vars=true is not on this path (the recipes use false)");
-  if (pre.cmn_window < 0) throw InvalidArgument("negative cmn_window");
-  const int64_t total_kept = utt_kept_start[num_utts];
-  Grow(&d_raw_[s], &raw_cap_[s], static_cast<size_t>(total_raw_rows) * dim * 4);
-  Grow(&d_sel_[s], &sel_cap_[s], static_cast<size_t>(std::max<int64_t>(total_kept, 1)) * dim * 4);
-  CVX_CUDA_CHECK(cudaMemcpyAsync(d_raw_[s], host_raw, static_cast<size_t>(total_raw_rows) * dim * 4, cudaMemcpyHostToDevice,
-                                 compute_));
-  if (pre.cmn_window > 0) {
-    Grow(&d_prefix_, &prefix_cap_, static_cast<size_t>(total_raw_rows + num_utts) * dim * 8);
-    ProfBegin(kProfStage, 0, static_cast<double>(total_raw_rows) * dim * 12.0);
-    CVX_CUDA_CHECK(LaunchCmnPrefix(static_cast<const float*>(d_raw_[s]), dim, static_cast<const int64_t*>(d_pre_utt_start_),
-                                   num_utts, static_cast<double*>(d_prefix_), compute_));
-    ProfEnd();
-  }
-  ProfBegin(kProfStage, 0, static_cast<double>(total_kept) * dim * (pre.cmn_window > 0 ? 24.0 : 8.0));
-  CVX_CUDA_CHECK(LaunchCmnSelect(static_cast<const float*>(d_raw_[s]), dim, static_cast<const int64_t*>(d_pre_utt_start_),
-                                 static_cast<const int32_t*>(d_pre_kept_utt_), keep ? static_cast<const int32_t*>(d_pre_keep_) : nullptr,
-                                 total_kept, static_cast<const double*>(d_prefix_), pre.cmn_window, pre.cmn_center,
-                                 pre.min_cmn_window, static_cast<float*>(d_sel_[s]), compute_));
+// Pre-step kernels of utterances [u0, u1) (raw rows already on the device): the selected /
+// normalised rows [kept0, kept0 + num_kept) of stream s.
+void Engine::RunPrestep(int32_t s, int32_t dim, const cvx_prestep& pre, int32_t u0, int32_t u1, int64_t run0, int64_t num_runs,
+                        int64_t kept0, int64_t num_kept, bool has_keep) {
+  const int32_t* d_keep = has_keep ? static_cast<const int32_t*>(d_pre_keep_) : nullptr;
+  const int64_t* aux = static_cast<const int64_t*>(d_pre_aux_);  // [n + 1] run starts, then [n + 1] kept starts
+  ProfBegin(kProfStage, 0, static_cast<double>(num_runs) * CmnRunFrames() * dim * 4.0 + static_cast<double>(num_kept) * dim * 4.0);
+  if (pre.cmn_window > 0)
+    CVX_CUDA_CHECK(LaunchCmnSliding(static_cast<const float*>(d_raw_[s]), dim, static_cast<const int64_t*>(d_pre_utt_start_), aux,
+                                    aux + pre_num_utts_ + 1, d_keep, u0, u1 - u0, run0, num_runs, pre.cmn_window,
+                                    pre.cmn_center, pre.min_cmn_window, static_cast<float*>(d_sel_[s]), compute_));
+  else
+    CVX_CUDA_CHECK(LaunchCmnSelect(static_cast<const float*>(d_raw_[s]), dim, static_cast<const int64_t*>(d_pre_utt_start_),
+                                   static_cast<const int32_t*>(d_pre_kept_utt_), d_keep, kept0, num_kept,
+                                   static_cast<float*>(d_sel_[s]), compute_));
   ProfEnd();
+}
+
+// Uploads the per-call index arrays of the pre-step; returns the run offsets (host copy).
+std::vector<int64_t> Engine::UploadPrestepIndex(const int64_t* utt_raw_start, const int32_t* keep, const int64_t* utt_kept_start,
+                                                int32_t num_utts, const std::vector<int32_t>& kept_utt) {
+  const int64_t total_kept = utt_kept_start[num_utts];
+  const int32_t run = CmnRunFrames();
+  std::vector<int64_t> aux(2 * (static_cast<size_t>(num_utts) + 1));
+  aux[0] = 0;
+  for (int32_t u = 0; u < num_utts; ++u) aux[u + 1] = aux[u] + (utt_raw_start[u + 1] - utt_raw_start[u] + run - 1) / run;
+  for (int32_t u = 0; u <= num_utts; ++u) aux[num_utts + 1 + u] = utt_kept_start[u];
+  pre_num_utts_ = num_utts;
+  Grow(&d_pre_utt_start_, &pre_utt_start_cap_, static_cast<size_t>(num_utts + 1) * 8);
+  Grow(&d_pre_kept_utt_, &pre_kept_utt_cap_, std::max<size_t>(kept_utt.size(), 1) * 4);
+  Grow(&d_pre_aux_, &pre_aux_cap_, aux.size() * 8);
+  CVX_CUDA_CHECK(cudaMemcpyAsync(d_pre_utt_start_, utt_raw_start, static_cast<size_t>(num_utts + 1) * 8, cudaMemcpyHostToDevice, compute_));
+  CVX_CUDA_CHECK(cudaMemcpyAsync(d_pre_kept_utt_, kept_utt.data(), kept_utt.size() * 4, cudaMemcpyHostToDevice, compute_));
+  CVX_CUDA_CHECK(cudaMemcpyAsync(d_pre_aux_, aux.data(), aux.size() * 8, cudaMemcpyHostToDevice, compute_));
+  if (keep) {
+    Grow(&d_pre_keep_, &pre_keep_cap_, std::max<size_t>(static_cast<size_t>(total_kept), 1) * 4);
+    CVX_CUDA_CHECK(cudaMemcpyAsync(d_pre_keep_, keep, static_cast<size_t>(total_kept) * 4, cudaMemcpyHostToDevice, compute_));
+  }
+  CVX_CUDA_CHECK(cudaStreamSynchronize(compute_));  // the host vectors have been consumed
+  aux.resize(static_cast<size_t>(num_utts) + 1);
+  return aux;
 }
 
 static void CheckPrestepIndex(int64_t total_raw_rows, const int64_t* utt_raw_start, const int32_t* keep,
@@ -1414,30 +1434,71 @@ void Engine::ExtractRaw(const float* const* raw, const cvx_prestep* pre, int32_t
   std::vector<int32_t> kept_utt;
   CheckPrestepIndex(total_raw_rows, utt_raw_start, keep, utt_kept_start, num_utts, &kept_utt);
   const int64_t total_kept = utt_kept_start[num_utts];
-  Grow(&d_pre_utt_start_, &pre_utt_start_cap_, static_cast<size_t>(num_utts + 1) * 8);
-  Grow(&d_pre_kept_utt_, &pre_kept_utt_cap_, std::max<size_t>(kept_utt.size(), 1) * 4);
-  CVX_CUDA_CHECK(cudaMemcpyAsync(d_pre_utt_start_, utt_raw_start, static_cast<size_t>(num_utts + 1) * 8, cudaMemcpyHostToDevice, compute_));
-  CVX_CUDA_CHECK(cudaMemcpyAsync(d_pre_kept_utt_, kept_utt.data(), kept_utt.size() * 4, cudaMemcpyHostToDevice, compute_));
-  if (keep) {
-    Grow(&d_pre_keep_, &pre_keep_cap_, std::max<size_t>(static_cast<size_t>(total_kept), 1) * 4);
-    CVX_CUDA_CHECK(cudaMemcpyAsync(d_pre_keep_, keep, static_cast<size_t>(total_kept) * 4, cudaMemcpyHostToDevice, compute_));
-  }
+  const std::vector<int64_t> run_start = UploadPrestepIndex(utt_raw_start, keep, utt_kept_start, num_utts, kept_utt);
   // all Grow()s first: they synchronise and may free buffers earlier kernels of this call read
   for (int32_t s = 0; s < num_streams; ++s) {
+    if (plan_.input_dims[s] > 128 && pre[s].cmn_window > 0) throw InvalidArgument("sliding CMN supports feature dims up to 128");
     Grow(&d_raw_[s], &raw_cap_[s], static_cast<size_t>(total_raw_rows) * plan_.input_dims[s] * 4);
     Grow(&d_sel_[s], &sel_cap_[s], static_cast<size_t>(std::max<int64_t>(total_kept, 1)) * plan_.input_dims[s] * 4);
-    if (pre[s].cmn_window > 0)
-      Grow(&d_prefix_, &prefix_cap_, static_cast<size_t>(total_raw_rows + num_utts) * plan_.input_dims[s] * 8);
   }
   const float* sel[kMaxASources] = {};
   for (int32_t s = 0; s < num_streams; ++s) {
     if (!raw[s]) throw InvalidArgument("pre-step: NULL feature stream");
-    RunPrestep(s, plan_.input_dims[s], raw[s], pre[s], total_raw_rows, utt_raw_start, keep, utt_kept_start, num_utts);
+    if (pre[s].norm_vars) throw InvalidArgument("sliding CMN with --norm-vars=true is not on this path (the recipes use false)");
+    if (pre[s].cmn_window < 0) throw InvalidArgument("negative cmn_window");
     sel[s] = static_cast<const float*>(d_sel_[s]);
   }
-  CVX_CUDA_CHECK(cudaStreamSynchronize(compute_));  // kept_utt (host vector) has been consumed
-  Extract(sel, num_streams, total_kept, chunk_start, chunk_len, chunk_utt, chunk_weight, num_chunks, num_utts, out,
-          flags | CVX_FLAG_DEVICE_INPUT);
+
+  // Pieces of whole utterances (>= kPieceRows raw rows each): all raw copies are queued on the copy
+  // stream now; the pre-step kernels of a piece are queued on the compute stream right before the
+  // first device batch that reads its rows, so the copy of piece p+1 overlaps the GEMMs of piece p.
+  struct Piece {
+    int32_t u0, u1;
+  };
+  constexpr int64_t kPieceRows = 1 << 18;
+  std::vector<Piece> pieces;
+  for (int32_t u = 0; u < num_utts;) {
+    int32_t v = u;
+    while (v < num_utts && utt_raw_start[v] - utt_raw_start[u] < kPieceRows) ++v;
+    pieces.push_back({u, v});
+    u = v;
+  }
+  while (piece_events_.size() < pieces.size()) {
+    cudaEvent_t ev;
+    CVX_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    piece_events_.push_back(ev);
+  }
+  for (size_t p = 0; p < pieces.size(); ++p) {
+    const int64_t r0 = utt_raw_start[pieces[p].u0], r1 = utt_raw_start[pieces[p].u1];
+    for (int32_t s = 0; s < num_streams; ++s) {
+      const int32_t dim = plan_.input_dims[s];
+      CVX_CUDA_CHECK(cudaMemcpyAsync(static_cast<float*>(d_raw_[s]) + r0 * dim, raw[s] + r0 * dim,
+                                     static_cast<size_t>(r1 - r0) * dim * 4, cudaMemcpyHostToDevice, copy_));
+    }
+    CVX_CUDA_CHECK(cudaEventRecord(piece_events_[p], copy_));
+  }
+  size_t next_piece = 0;
+  before_batch_ = [&](int64_t row_end) {
+    while (next_piece < pieces.size() && utt_kept_start[pieces[next_piece].u0] < row_end) {
+      const Piece& pc = pieces[next_piece];
+      CVX_CUDA_CHECK(cudaStreamWaitEvent(compute_, piece_events_[next_piece], 0));
+      const int64_t k0 = utt_kept_start[pc.u0], k1 = utt_kept_start[pc.u1];
+      for (int32_t s = 0; s < num_streams; ++s)
+        RunPrestep(s, plan_.input_dims[s], pre[s], pc.u0, pc.u1, run_start[pc.u0], run_start[pc.u1] - run_start[pc.u0], k0,
+                   k1 - k0, keep != nullptr);
+      ++next_piece;
+    }
+  };
+  try {
+    Extract(sel, num_streams, total_kept, chunk_start, chunk_len, chunk_utt, chunk_weight, num_chunks, num_utts, out,
+            flags | CVX_FLAG_DEVICE_INPUT);
+  } catch (...) {
+    before_batch_ = nullptr;
+    cudaStreamSynchronize(copy_);
+    throw;
+  }
+  before_batch_ = nullptr;
+  CVX_CUDA_CHECK(cudaStreamSynchronize(copy_));  // pieces no batch needed (utterances without chunks)
 }
 
 void Engine::DebugPrestep(const float* raw, int32_t dim, const cvx_prestep& pre, int64_t total_raw_rows,
@@ -1447,18 +1508,14 @@ void Engine::DebugPrestep(const float* raw, int32_t dim, const cvx_prestep& pre,
   std::vector<int32_t> kept_utt;
   CheckPrestepIndex(total_raw_rows, utt_raw_start, keep, utt_kept_start, num_utts, &kept_utt);
   const int64_t total_kept = utt_kept_start[num_utts];
-  Grow(&d_pre_utt_start_, &pre_utt_start_cap_, static_cast<size_t>(num_utts + 1) * 8);
-  Grow(&d_pre_kept_utt_, &pre_kept_utt_cap_, std::max<size_t>(kept_utt.size(), 1) * 4);
-  CVX_CUDA_CHECK(cudaMemcpyAsync(d_pre_utt_start_, utt_raw_start, static_cast<size_t>(num_utts + 1) * 8, cudaMemcpyHostToDevice, compute_));
-  CVX_CUDA_CHECK(cudaMemcpyAsync(d_pre_kept_utt_, kept_utt.data(), kept_utt.size() * 4, cudaMemcpyHostToDevice, compute_));
-  if (keep) {
-    Grow(&d_pre_keep_, &pre_keep_cap_, std::max<size_t>(static_cast<size_t>(total_kept), 1) * 4);
-    CVX_CUDA_CHECK(cudaMemcpyAsync(d_pre_keep_, keep, static_cast<size_t>(total_kept) * 4, cudaMemcpyHostToDevice, compute_));
-  }
+  const std::vector<int64_t> run_start = UploadPrestepIndex(utt_raw_start, keep, utt_kept_start, num_utts, kept_utt);
+  if (dim > 128 && pre.cmn_window > 0) throw InvalidArgument("sliding CMN supports feature dims up to 128");
   Grow(&d_raw_[0], &raw_cap_[0], static_cast<size_t>(total_raw_rows) * dim * 4);
   Grow(&d_sel_[0], &sel_cap_[0], static_cast<size_t>(std::max<int64_t>(total_kept, 1)) * dim * 4);
-  if (pre.cmn_window > 0) Grow(&d_prefix_, &prefix_cap_, static_cast<size_t>(total_raw_rows + num_utts) * dim * 8);
-  RunPrestep(0, dim, raw, pre, total_raw_rows, utt_raw_start, keep, utt_kept_start, num_utts);
+  if (pre.norm_vars) throw InvalidArgument("sliding CMN with --norm-vars=true is not on this path (the recipes use false)");
+  if (pre.cmn_window < 0) throw InvalidArgument("negative cmn_window");
+  CVX_CUDA_CHECK(cudaMemcpyAsync(d_raw_[0], raw, static_cast<size_t>(total_raw_rows) * dim * 4, cudaMemcpyHostToDevice, compute_));
+  RunPrestep(0, dim, pre, 0, num_utts, 0, run_start[num_utts], 0, total_kept, keep != nullptr);
   CVX_CUDA_CHECK(cudaMemcpyAsync(out, d_sel_[0], static_cast<size_t>(total_kept) * dim * 4, cudaMemcpyDeviceToHost, compute_));
   CVX_CUDA_CHECK(cudaStreamSynchronize(compute_));
   ProfResolve();

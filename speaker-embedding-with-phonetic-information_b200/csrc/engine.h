@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <functional>
 #include <map>
 #include <stdexcept>
 #include <string>
@@ -165,12 +166,17 @@ class Engine {
   bool fused_pool_ = false;  // pooled layer's activations are reduced in its GEMM epilogue
   void *d_pool_meta_ = nullptr, *d_slot_n_ = nullptr, *d_slot_begin_ = nullptr, *d_chunk_rng_ = nullptr;
   size_t pool_meta_cap_ = 0, slot_n_cap_ = 0, slot_begin_cap_ = 0, chunk_rng_cap_ = 0;
-  void RunPrestep(int32_t s, int32_t dim, const float* host_raw, const cvx_prestep& pre, int64_t total_raw_rows,
-                  const int64_t* utt_raw_start, const int32_t* keep, const int64_t* utt_kept_start, int32_t num_utts);
+  void RunPrestep(int32_t s, int32_t dim, const cvx_prestep& pre, int32_t u0, int32_t u1, int64_t run0, int64_t num_runs,
+                  int64_t kept0, int64_t num_kept, bool has_keep);
+  std::vector<int64_t> UploadPrestepIndex(const int64_t* utt_raw_start, const int32_t* keep, const int64_t* utt_kept_start,
+                                          int32_t num_utts, const std::vector<int32_t>& kept_utt);
+  int32_t pre_num_utts_ = 0;
+  std::function<void(int64_t)> before_batch_;  // set by ExtractRaw: called with a device batch's last row + 1
+  std::vector<cudaEvent_t> piece_events_;
   void *d_raw_[kMaxASources] = {}, *d_sel_[kMaxASources] = {};
   size_t raw_cap_[kMaxASources] = {}, sel_cap_[kMaxASources] = {};
-  void *d_prefix_ = nullptr, *d_pre_utt_start_ = nullptr, *d_pre_kept_utt_ = nullptr, *d_pre_keep_ = nullptr;
-  size_t prefix_cap_ = 0, pre_utt_start_cap_ = 0, pre_kept_utt_cap_ = 0, pre_keep_cap_ = 0;
+  void *d_pre_aux_ = nullptr, *d_pre_utt_start_ = nullptr, *d_pre_kept_utt_ = nullptr, *d_pre_keep_ = nullptr;
+  size_t pre_aux_cap_ = 0, pre_utt_start_cap_ = 0, pre_kept_utt_cap_ = 0, pre_keep_cap_ = 0;
   cudaEvent_t call_begin_ = nullptr, call_end_ = nullptr;
   float last_call_ms_ = 0.f;
 

@@ -184,13 +184,18 @@ cudaError_t LaunchUttAverage(const float* chunk_emb, int32_t dim, const int64_t*
                              const float* chunk_weight, int32_t num_utts, float* out, cudaStream_t stream);
 
 // ---- feature pre-step: sliding-window CMN + voiced-frame selection (prestep.cu) ----
-// prefix: double [(total_raw_rows + num_utts), dim]; utterance u owns T_u + 1 rows from utt_start[u] + u
-cudaError_t LaunchCmnPrefix(const float* x, int32_t dim, const int64_t* utt_start, int32_t num_utts, double* prefix,
-                            cudaStream_t stream);
-// out[j] = x[frame keep[j] of utterance kept_utt[j]] - window mean (cmn_window == 0: plain selection)
+// Both kernels take the call's whole index arrays and a sub-range (utterances [utt0, utt0 + num_utts) =
+// runs [run0, run0 + num_runs), kept rows [kept0, kept0 + num_kept)), so that a call can be
+// pre-processed piece by piece as its raw features arrive.
+// Sliding CMN + selection: utt_run_start[u] = number of CmnRunFrames()-frame runs before utterance u.
+cudaError_t LaunchCmnSliding(const float* x, int32_t dim, const int64_t* utt_start, const int64_t* utt_run_start,
+                             const int64_t* utt_kept_start, const int32_t* keep, int32_t utt0, int32_t num_utts, int64_t run0,
+                             int64_t num_runs, int32_t cmn_window, int32_t center, int32_t min_window, float* out,
+                             cudaStream_t stream);
+int32_t CmnRunFrames();
+// plain selection: out[j] = x[frame keep[j] of utterance kept_utt[j]]
 cudaError_t LaunchCmnSelect(const float* x, int32_t dim, const int64_t* utt_start, const int32_t* kept_utt,
-                            const int32_t* keep, int64_t total_kept, const double* prefix, int32_t cmn_window,
-                            int32_t center, int32_t min_window, float* out, cudaStream_t stream);
+                            const int32_t* keep, int64_t kept0, int64_t num_kept, float* out, cudaStream_t stream);
 
 // ---- frame-level outputs (frame_output.cu): edge replication in, compaction (+log-softmax) out ----
 // utt_start [num_utts + 1] in compact rows; utterance u owns padded rows from utt_start[u] + u * (left + right)

@@ -8,30 +8,112 @@
 // frames whose VAD value is non-zero, in order).  Window rule restated from upstream
 // Kaldi's SlidingWindowCmn (src/feat/feature-functions.cc), sums in double like upstream.
 //
-//   cmn_prefix_kernel   one warp per utterance: P[t+1][c] = P[t][c] + x[t][c] (double),
-//                       lanes = feature columns, so every row is one coalesced read
-//   cmn_select_kernel   one thread per (kept frame, column): window [ws, we) of its source
-//                       frame, out = x[t] - (P[we] - P[ws]) / (we - ws); writes the compacted
-//                       fp32 rows the rest of the path consumes
-// HBM-bound: 92 B read + 184 B of prefix written per raw frame, then ~280 B per kept frame.
+//   cmn_sliding_kernel  one warp per run of 128 consecutive frames of one utterance, lanes = feature
+//                       columns: the window sum of the run's first frame is summed directly
+//                       (<= cmn_window coalesced row reads), then the window slides frame by frame
+//                       (add the entering row, subtract the leaving one, in double) -- the same
+//                       running sum upstream keeps; out = x[t] - sum / (we - ws) is written for
+//                       the frames that survive selection only, at their compacted position
+//   cmn_select_kernel   plain selection (no CMN for this stream): one thread per (kept frame, column)
+// The rows a run re-reads are in L1/L2 (neighbouring runs share their windows): ~92 B of HBM reads
+// per raw frame and 92 B written per kept frame.  (The first version kept a double prefix-sum
+// array built by one warp per UTTERANCE: 64 warps per call, 270 ms for 9 M frames.)
 #include "kernels.h"
 
 namespace cvx {
 namespace {
 
-__global__ void __launch_bounds__(128) cmn_prefix_kernel(const float* __restrict__ x, int dim,
-                                                          const int64_t* __restrict__ utt_start, int num_utts,
-                                                          double* __restrict__ prefix) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= num_utts) return;
-  const int64_t r0 = utt_start[warp], r1 = utt_start[warp + 1];
-  double* p = prefix + (r0 + warp) * dim;  // utterance u owns rows [r0+u, r1+u+1): T+1 prefix rows
-  for (int c = lane; c < dim; c += 32) {
-    double s = 0.0;
-    p[c] = 0.0;
-    for (int64_t t = r0; t < r1; ++t) {
-      s += static_cast<double>(x[t * dim + c]);
-      p[(t - r0 + 1) * dim + c] = s;
+constexpr int kCmnRun = 128;     // frames per warp
+constexpr int kCmnMaxColGroups = 4;  // feature dims up to 128
+
+// [ws, we) of frame t in an utterance of num_frames frames (SlidingWindowCmn's rule)
+__device__ __forceinline__ void cmn_window_bounds(int t, int num_frames, int cmn_window, int center, int min_window, int* ws_out,
+                                                  int* we_out) {
+  int ws, we;
+  if (center) {
+    ws = t - cmn_window / 2;
+    we = ws + cmn_window;
+  } else {
+    ws = t - cmn_window;
+    we = t + 1;
+  }
+  if (ws < 0) {
+    we -= ws;
+    ws = 0;
+  }
+  if (!center && we > t) we = max(t + 1, min_window);
+  if (we > num_frames) {
+    ws -= (we - num_frames);
+    we = num_frames;
+    if (ws < 0) ws = 0;
+  }
+  *ws_out = ws;
+  *we_out = we;
+}
+
+__global__ void __launch_bounds__(128) cmn_sliding_kernel(const float* __restrict__ x, int dim,
+                                                           const int64_t* __restrict__ utt_start,
+                                                           const int64_t* __restrict__ utt_run_start,
+                                                           const int64_t* __restrict__ utt_kept_start,
+                                                           const int32_t* __restrict__ keep, int utt0, int num_utts,
+                                                           int64_t run0, int64_t num_runs, int cmn_window, int center,
+                                                           int min_window, float* __restrict__ out) {
+  const int64_t w = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= num_runs) return;
+  const int64_t run = run0 + w;
+  int lo = utt0, hi = utt0 + num_utts - 1;  // largest u with utt_run_start[u] <= run (empty utterances have no runs)
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (utt_run_start[mid] <= run) lo = mid;
+    else hi = mid - 1;
+  }
+  const int u = lo;
+  const int64_t r0 = utt_start[u];
+  const int num_frames = static_cast<int>(utt_start[u + 1] - r0);
+  const int t0 = static_cast<int>(run - utt_run_start[u]) * kCmnRun, t1 = min(num_frames, t0 + kCmnRun);
+  // position of the run's first surviving frame among the kept rows
+  int64_t kp = utt_kept_start[u], ke = utt_kept_start[u + 1];
+  if (keep) {
+    int64_t a = kp, b = ke;
+    while (a < b) {
+      const int64_t mid = (a + b) >> 1;
+      if (keep[mid] >= t0) b = mid;
+      else a = mid + 1;
+    }
+    kp = a;
+  } else {
+    kp += t0;
+  }
+  const float* xu = x + r0 * dim;
+  double sum[kCmnMaxColGroups] = {0.0, 0.0, 0.0, 0.0};
+  int ws, we;
+  cmn_window_bounds(t0, num_frames, cmn_window, center, min_window, &ws, &we);
+  for (int r = ws; r < we; ++r)
+#pragma unroll
+    for (int k = 0; k < kCmnMaxColGroups; ++k)
+      if (lane + 32 * k < dim) sum[k] += static_cast<double>(xu[static_cast<int64_t>(r) * dim + lane + 32 * k]);
+  for (int t = t0; t < t1; ++t) {
+    int nws, nwe;
+    cmn_window_bounds(t, num_frames, cmn_window, center, min_window, &nws, &nwe);
+    for (; we < nwe; ++we)
+#pragma unroll
+      for (int k = 0; k < kCmnMaxColGroups; ++k)
+        if (lane + 32 * k < dim) sum[k] += static_cast<double>(xu[static_cast<int64_t>(we) * dim + lane + 32 * k]);
+    for (; ws < nws; ++ws)
+#pragma unroll
+      for (int k = 0; k < kCmnMaxColGroups; ++k)
+        if (lane + 32 * k < dim) sum[k] -= static_cast<double>(xu[static_cast<int64_t>(ws) * dim + lane + 32 * k]);
+    const bool kept = keep ? (kp < ke && keep[kp] == t) : true;
+    if (kept) {
+      const double inv = 1.0 / static_cast<double>(we - ws);
+#pragma unroll
+      for (int k = 0; k < kCmnMaxColGroups; ++k)
+        if (lane + 32 * k < dim) {
+          const int c = lane + 32 * k;
+          out[kp * dim + c] = static_cast<float>(static_cast<double>(xu[static_cast<int64_t>(t) * dim + c]) - sum[k] * inv);
+        }
+      ++kp;
     }
   }
 }
@@ -39,62 +121,39 @@ __global__ void __launch_bounds__(128) cmn_prefix_kernel(const float* __restrict
 __global__ void __launch_bounds__(256) cmn_select_kernel(const float* __restrict__ x, int dim,
                                                           const int64_t* __restrict__ utt_start,
                                                           const int32_t* __restrict__ kept_utt,
-                                                          const int32_t* __restrict__ keep, int64_t total_kept,
-                                                          const double* __restrict__ prefix, int cmn_window, int center,
-                                                          int min_window, float* __restrict__ out) {
+                                                          const int32_t* __restrict__ keep, int64_t kept0,
+                                                          int64_t num_kept, float* __restrict__ out) {
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const int64_t j = idx / dim;
   const int c = static_cast<int>(idx % dim);
-  if (j >= total_kept) return;
-  const int u = kept_utt[j];
-  const int64_t r0 = utt_start[u];
-  const int num_frames = static_cast<int>(utt_start[u + 1] - r0);
+  if (idx / dim >= num_kept) return;
+  const int64_t j = kept0 + idx / dim;  // kept rows [kept0, kept0 + num_kept) of the call
+  const int64_t r0 = utt_start[kept_utt[j]];
   const int t = keep ? keep[j] : static_cast<int>(j - r0);  // frame inside its utterance
-  float v = x[(r0 + t) * dim + c];
-  if (cmn_window > 0) {
-    int ws, we;  // [ws, we)
-    if (center) {
-      ws = t - cmn_window / 2;
-      we = ws + cmn_window;
-    } else {
-      ws = t - cmn_window;
-      we = t + 1;
-    }
-    if (ws < 0) {
-      we -= ws;
-      ws = 0;
-    }
-    if (!center && we > t) we = max(t + 1, min_window);
-    if (we > num_frames) {
-      ws -= (we - num_frames);
-      we = num_frames;
-      if (ws < 0) ws = 0;
-    }
-    const double* p = prefix + (r0 + u) * dim;
-    const double mean = (p[static_cast<int64_t>(we) * dim + c] - p[static_cast<int64_t>(ws) * dim + c]) / (we - ws);
-    v = static_cast<float>(static_cast<double>(v) - mean);
-  }
-  out[j * dim + c] = v;
+  out[j * dim + c] = x[(r0 + t) * dim + c];
 }
 
 }  // namespace
 
-cudaError_t LaunchCmnPrefix(const float* x, int32_t dim, const int64_t* utt_start, int32_t num_utts, double* prefix,
-                            cudaStream_t stream) {
-  if (num_utts <= 0) return cudaSuccess;
-  const unsigned grid = static_cast<unsigned>((static_cast<int64_t>(num_utts) * 32 + 127) / 128);
-  cmn_prefix_kernel<<<grid, 128, 0, stream>>>(x, dim, utt_start, num_utts, prefix);
+cudaError_t LaunchCmnSliding(const float* x, int32_t dim, const int64_t* utt_start, const int64_t* utt_run_start,
+                             const int64_t* utt_kept_start, const int32_t* keep, int32_t utt0, int32_t num_utts, int64_t run0,
+                             int64_t num_runs, int32_t cmn_window, int32_t center, int32_t min_window, float* out,
+                             cudaStream_t stream) {
+  if (num_runs <= 0 || num_utts <= 0) return cudaSuccess;
+  if (dim > 32 * kCmnMaxColGroups) return cudaErrorInvalidValue;
+  const unsigned grid = static_cast<unsigned>((num_runs * 32 + 127) / 128);
+  cmn_sliding_kernel<<<grid, 128, 0, stream>>>(x, dim, utt_start, utt_run_start, utt_kept_start, keep, utt0, num_utts, run0,
+                                               num_runs, cmn_window, center, min_window, out);
   return cudaGetLastError();
 }
 
+int32_t CmnRunFrames() { return kCmnRun; }
+
 cudaError_t LaunchCmnSelect(const float* x, int32_t dim, const int64_t* utt_start, const int32_t* kept_utt,
-                            const int32_t* keep, int64_t total_kept, const double* prefix, int32_t cmn_window,
-                            int32_t center, int32_t min_window, float* out, cudaStream_t stream) {
-  if (total_kept <= 0) return cudaSuccess;
-  const int64_t total = total_kept * dim;
+                            const int32_t* keep, int64_t kept0, int64_t num_kept, float* out, cudaStream_t stream) {
+  if (num_kept <= 0) return cudaSuccess;
+  const int64_t total = num_kept * dim;
   const unsigned grid = static_cast<unsigned>((total + 255) / 256);
-  cmn_select_kernel<<<grid, 256, 0, stream>>>(x, dim, utt_start, kept_utt, keep, total_kept, prefix, cmn_window, center,
-                                              min_window, out);
+  cmn_select_kernel<<<grid, 256, 0, stream>>>(x, dim, utt_start, kept_utt, keep, kept0, num_kept, out);
   return cudaGetLastError();
 }
 

@@ -30,10 +30,11 @@ with open(ark, "wb") as f:
         kf.write_ark(f, [(k, rng.standard_normal((int(T), 23), dtype=np.float32))])
 frames = int(lengths.sum())
 exe = os.path.join(cvx.BIN_DIR, "nnet3-xvector-compute")
-for label, feat in (("ark file", f"ark:{ark}"), ("ark through a pipe", f"ark:cat {ark} |")):
+for label, feat, extra in (("ark file", f"ark:{ark}", []), ("ark through a pipe", f"ark:cat {ark} |", []),
+                           ("ark file, sliding CMN on the GPU (raw mode)", f"ark:{ark}", ["--cmn-window=300"])):
     t0 = time.perf_counter()
     r = subprocess.run([exe, "--use-gpu=no", "--min-chunk-size=25", "--chunk-size=10000", "--output-node=tdnn6_xvec.affine",
-                        model, feat, f"ark,scp:{d}/x.ark,{d}/x.scp"], capture_output=True, text=True)
+                        *extra, model, feat, f"ark,scp:{d}/x{len(extra)}.ark,{d}/x{len(extra)}.scp"], capture_output=True, text=True)
     dt = time.perf_counter() - t0
     assert r.returncode == 0, r.stderr[-2000:]
     tail = [ln for ln in r.stderr.splitlines() if "Time taken" in ln or "Done " in ln]
@@ -48,6 +49,6 @@ if num_gpus > 1:
     dt = time.perf_counter() - t0
     assert r.returncode == 0, r.stderr[-2000:]
     tail = [ln for ln in r.stderr.splitlines() if "Time taken" in ln or "Done " in ln]
-    same = open(f"{d}/x.ark", "rb").read() == open(f"{d}/xn.ark", "rb").read()
+    same = open(f"{d}/x0.ark", "rb").read() == open(f"{d}/xn.ark", "rb").read()
     print(f"ark file, --num-gpus={num_gpus}: {dt:.2f} s wall -> {frames / 100 / dt:,.0f} audio-s/s | "
           + " | ".join(t.split(") ", 1)[-1] for t in tail) + f" | archive identical to the 1-GPU run: {same}", flush=True)
