@@ -96,3 +96,27 @@ def test_cli_raw_features_with_vad(cvx, kf, synth, model_dir, require_gpu, tmp_p
     assert list(got) == [k for k, o in zip(keys, ok) if o]
     rr, cc = parity_metrics(np.stack([got[k] for k in got]), ref[ok])
     assert rr <= 1e-3 and cc >= 0.9999, (rr, cc)
+
+
+def test_extract_raw_in_several_pieces(cvx, synth, model_dir, require_gpu):
+    """a call large enough for the raw copies to be cut into several pieces and several device
+    batches (copies overlapping compute): same embeddings as pre-processing everything on the host
+    first, for every utterance, in both VAD and no-VAD form."""
+    from oracle.prestep_oracle import select_voiced, sliding_cmn
+    ps = importlib.import_module(PKG + ".prestep")
+    path, _ = model_dir("v2_xvector")
+    ex = cvx.Extractor(cvx.Model(path, "tdnn6.affine"), precision="fp16", max_batch_rows=131072)
+    rng = np.random.default_rng(9)
+    lengths = rng.integers(2000, 30000, 48).tolist()                # ~770 k raw rows: 3+ pieces, 4+ device batches
+    x, vad = _data(lengths, 23, 3, voiced_p=0.8)
+    for use_vad in (True, False):
+        v = vad if use_vad else None
+        emb, ok = ps.extract_raw(ex, {"input": x}, lengths, v, {"input": 300}, chunk_size=10000, min_chunk_size=25)
+        pieces, kept, r = [], [], 0
+        for T, m in zip(lengths, vad):
+            seg = sliding_cmn(x[r:r + T], 300, True)
+            seg = select_voiced(seg, m) if use_vad else seg
+            pieces.append(seg); kept.append(len(seg)); r += T
+        ref, ok_ref = ex.extract({"input": np.concatenate(pieces)}, kept, chunk_size=10000, min_chunk_size=25)
+        assert ok.all() and ok_ref.all()
+        assert np.max(np.abs(emb - ref)) <= 2e-3 * np.max(np.abs(ref)), use_vad
