@@ -16,11 +16,13 @@
 #include "extract_main.h"
 
 #include <chrono>
+#include <condition_variable>
 #include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <fstream>
 #include <memory>
+#include <mutex>
 #include <thread>
 
 #include "../../../include/cvx.h"
@@ -264,6 +266,54 @@ int ExtractMain(int argc, const char* const* argv, bool multiple_input) {
     eo.max_batch_rows = max_batch_rows;
     eo.profile = profile ? 1 : 0;
     if (num_gpus < 1) throw KaldiError("--num-gpus must be >= 1");
+    // Pinned host batches: one being filled + one in flight per GPU.  Pinning ~100 MB takes longer than
+    // building an engine, so a helper thread allocates them, first batch first, while the main
+    // thread creates the engines; a batch is waited for only when the reader is about to fill it (a job of
+    // less than one batch never waits for the second).  Whole batches are pinned up front because
+    // growing pinned memory step by step costs more than the I/O.
+    std::vector<HostBatch> hb(num_gpus + 1);
+    for (HostBatch& b : hb) {
+      b.feats.assign(num_inputs, nullptr);
+      b.cap_rows.assign(num_inputs, 0);
+      b.dims.resize(num_inputs);
+      for (int s = 0; s < num_inputs; ++s) b.dims[s] = cvx_model_input_dim(model, s);
+    }
+    struct BatchPool {
+      std::vector<HostBatch>& hb;
+      int64_t rows;
+      int32_t device;
+      std::mutex mu;
+      std::condition_variable cv;
+      int ready = 0;
+      std::string error;
+      std::thread th;
+      BatchPool(std::vector<HostBatch>& h, int64_t r, int32_t dev) : hb(h), rows(r), device(dev) {
+        th = std::thread([this] {
+          for (size_t i = 0; i < hb.size(); ++i) {
+            try {
+              hb[i].Reserve(rows);
+            } catch (const std::exception& e) {
+              std::lock_guard<std::mutex> lk(mu);
+              error = e.what();
+              ready = static_cast<int>(hb.size());
+              cv.notify_all();
+              return;
+            }
+            std::lock_guard<std::mutex> lk(mu);
+            ready = static_cast<int>(i) + 1;
+            cv.notify_all();
+          }
+        });
+      }
+      void WaitFor(int i) {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return ready > i; });
+        if (!error.empty()) throw KaldiError("allocating pinned host memory: " + error);
+      }
+      ~BatchPool() {
+        if (th.joinable()) th.join();
+      }
+    } batch_pool(hb, batch_rows + batch_rows / 8 + 65536, gpu_id);
     int32_t ndev = 0;
     if (cvx_device_count(&ndev) != CVX_OK) throw KaldiError(std::string("no usable CUDA device: ") + cvx_last_error());
     if (gpu_id + num_gpus > ndev)
@@ -312,16 +362,7 @@ int ExtractMain(int argc, const char* const* argv, bool multiple_input) {
     std::vector<cvx_prestep> prestep(num_inputs);
     for (int s = 0; s < num_inputs; ++s) prestep[s] = cvx_prestep{s == 0 ? cmn_window : 0, cmn_center ? 1 : 0, min_cmn_window, 0};
 
-    // one batch being filled + one in flight per GPU
-    std::vector<HostBatch> hb(num_gpus + 1);
-    for (HostBatch& b : hb) {
-      b.feats.assign(num_inputs, nullptr);
-      b.cap_rows.assign(num_inputs, 0);
-      b.dims.resize(num_inputs);
-      for (int s = 0; s < num_inputs; ++s) b.dims[s] = cvx_model_input_dim(model, s);
-      // pin the whole batch up front: growing pinned memory step by step costs more than the I/O
-      b.Reserve(batch_rows + batch_rows / 8 + 65536);
-    }
+    batch_pool.WaitFor(0);  // the first pinned batch (allocated while the engines were built)
     const int32_t E = cvx_engine_output_dim(engine);
     const int32_t ctx = info.left_context + info.right_context + 1;
     int64_t num_success = 0, num_fail = 0, frame_count = 0;
@@ -387,6 +428,7 @@ int ExtractMain(int argc, const char* const* argv, bool multiple_input) {
       inflight.push_back(std::move(job));
       const int next = free_batches.back();
       free_batches.pop_back();
+      batch_pool.WaitFor(next);
       return next;
     };
 
