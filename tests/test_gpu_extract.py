@@ -318,3 +318,23 @@ def test_cli_num_gpus_is_checked_against_visible_devices(cvx, require_gpu, tmp_p
         assert r.returncode == 0, r.stderr
         outs.append(open(f"{tmp_path}/x{k}.ark", "rb").read())
     assert outs[0] == outs[1]
+
+
+def test_one_very_long_utterance_without_chunking(cvx, synth, model_dir, require_gpu):
+    """--chunk-size=-1 on an utterance longer than a device batch (the engine grows its batch) and
+    longer than the pooling window: like upstream, only frames inside the window [0, right-context]
+    are pooled, so the result equals that of the utterance cut at right-context + R + 1 frames."""
+    path, _ = model_dir("v2_xvector")
+    mod = cvx.Model(path, "tdnn6.affine")
+    ex = cvx.Extractor(mod, precision="fp16")
+    T = 600_000                                    # > the 524 288-row default batch
+    x = synth.make_features([T], 23, 5)
+    whole, ok = ex.extract({"input": x}, [T], chunk_size=-1, min_chunk_size=25)
+    assert ok.all() and np.isfinite(whole).all()
+    cut = 10000 + mod.info.right_context + 1       # stats layer right-context of the recipes' nets
+    head, _ = ex.extract({"input": x[:cut]}, [cut], chunk_size=-1, min_chunk_size=25)
+    assert np.max(np.abs(whole - head)) <= 2e-5 * np.max(np.abs(head))
+    # and chunked the recipe's way it is the frame-weighted average of 60 chunks
+    chunked, _ = ex.extract({"input": x}, [T], chunk_size=10000, min_chunk_size=25)
+    per_chunk = ex.last_chunk_embeddings(60)
+    assert np.allclose(chunked[0], per_chunk.mean(axis=0), rtol=1e-4, atol=1e-5)
