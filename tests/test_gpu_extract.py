@@ -338,3 +338,19 @@ def test_one_very_long_utterance_without_chunking(cvx, synth, model_dir, require
     chunked, _ = ex.extract({"input": x}, [T], chunk_size=10000, min_chunk_size=25)
     per_chunk = ex.last_chunk_embeddings(60)
     assert np.allclose(chunked[0], per_chunk.mean(axis=0), rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("topology", ["v2_xvector", "v5_cvector"])
+def test_bf16_operands_end_to_end(cvx, synth, model_dir, require_gpu, topology):
+    """the bf16 variants of every kernel (pair / halo / narrow ring / fused pooling / segment split):
+    not the default -- bf16 misses the 1e-3 tolerance -- but they must stay correct."""
+    from oracle.nnet3_oracle import extract_all, parity_metrics
+    path, model = model_dir(topology)
+    node = embedding_node(synth, topology)
+    mod = cvx.Model(path, node)
+    lengths = [300, 57, 1234, 100, 640]
+    feats = _inputs(synth, mod, lengths, 31)
+    got, ok = cvx.Extractor(mod, precision="bf16").extract(feats, lengths, chunk_size=500, min_chunk_size=25)
+    ref, _ = extract_all(_oracle(model, node), feats, lengths, chunk_size=500, min_chunk_size=25)
+    r, c = parity_metrics(got[ok], ref[ok])
+    assert r <= 8e-3 and c >= 0.9999, (r, c)
