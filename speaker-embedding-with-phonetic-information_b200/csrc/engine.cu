@@ -103,6 +103,16 @@ void Engine::Grow(void** p, size_t* cap, size_t bytes) {
 }
 
 Engine::Engine(const Plan& plan, const cvx_engine_options& opts) : plan_(plan), opts_(opts) {
+  try {
+    Build();
+  } catch (...) {
+    Release();  // a constructor that throws runs no destructor: free what was already allocated
+    throw;
+  }
+}
+
+void Engine::Build() {
+  const cvx_engine_options& opts = opts_;
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0)
@@ -294,8 +304,10 @@ Engine::Engine(const Plan& plan, const cvx_engine_options& opts) : plan_(plan), 
   if (const char* env = std::getenv("CVX_FUSED_POOL")) fused_pool_ = fused_pool_ && env[0] != '0';
 }
 
-Engine::~Engine() {
-  cudaSetDevice(opts_.device);
+Engine::~Engine() { Release(); }
+
+void Engine::Release() noexcept {
+  if (cudaSetDevice(opts_.device) != cudaSuccess) return;  // no usable device: nothing was allocated
   cudaDeviceSynchronize();
   for (Buffer& b : buffers_)
     if (b.ptr) cudaFree(b.ptr);
@@ -327,6 +339,7 @@ Engine::~Engine() {
   cudaFree(d_slot_begin_);
   cudaFree(d_chunk_rng_);
   for (cudaEvent_t ev : piece_events_) cudaEventDestroy(ev);
+  piece_events_.clear();
   cudaFree(d_seg_hi_);
   cudaFree(d_seg_lo_);
   for (SegOp& s : seg_ops_) {

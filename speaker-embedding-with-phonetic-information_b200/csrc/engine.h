@@ -121,6 +121,8 @@ class Engine {
     double flops, bytes;
   };
 
+  void Build();             // the constructor's work
+  void Release() noexcept;  // frees every device / stream / event resource (destructor, failed constructor)
   int32_t StagingFor(const std::vector<Tap>& taps);
   void EnsureRows(int64_t rows);
   void EncodeMaps();
