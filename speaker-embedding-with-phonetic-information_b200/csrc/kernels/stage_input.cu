@@ -103,11 +103,17 @@ __global__ void __launch_bounds__(256) stage_input_tiled_kernel(const __grid_con
     s_feat[i] = (g >= lo && g < hi) ? __ldg(src + g) : 0.f;
   }
   __syncthreads();
-  const int groups = args.ld_out / kVec;
-  for (int u = threadIdx.x; u < kStageTileRows * groups; u += blockDim.x) {
-    const int row = u / groups;
-    if (r0 + row >= args.rows) break;
-    const int c0 = (u % groups) * kVec;
+  // A warp covers 8 rows x 4 consecutive column groups: with 16-bit outputs (8 columns per group) the 32
+  // shared-memory reads of one instruction then fall into 32 different banks for any odd feature
+  // dimension (rows 23 floats apart give 8 distinct residues mod 8, groups add multiples of 8), and a
+  // row's four 16-byte stores are one contiguous 64-byte segment.
+  const int groups = args.ld_out / kVec;  // multiple of 8
+  const int quads = groups >> 2;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int item = warp; item < (kStageTileRows / 8) * quads; item += blockDim.x >> 5) {
+    const int row = (item / quads) * 8 + (lane >> 2);
+    if (r0 + row >= args.rows) continue;
+    const int c0 = ((item % quads) * 4 + (lane & 3)) * kVec;
     const float* base = s_feat + row * dim;
     alignas(16) int idx[kVec];
 #pragma unroll
