@@ -627,7 +627,7 @@ void Engine::ResetProfile() {
 
 // ---------------------------------------------------------- frame pass ----
 void Engine::RunFrames(const float* const* dev_feats, int64_t rows, int64_t src_row_min, int64_t src_row_max,
-                       const PoolGroupMeta* pool_meta, float* f32_out, int32_t f32_ld) {
+                       const PoolGroupMeta* pool_meta, float* f32_out, int32_t f32_ld, int32_t pool_slots) {
   for (const Staging& s : stagings_) {
     StageArgs a;
     std::memset(&a, 0, sizeof(a));
@@ -692,6 +692,7 @@ void Engine::RunFrames(const float* const* dev_feats, int64_t rows, int64_t src_
         fa.pool_meta = pool_meta;
         fa.pool_partials = static_cast<float*>(d_partials_);
         fa.pool_ld = buffers_[op.out_buffer].ld;
+        fa.pool_slots = pool_slots;
         CVX_CUDA_CHECK(LaunchTdnnGemmPair(fa, num_sms_, compute_));
       } else if (f32_out && &op == &frame_ops_.back()) {
         // frame-output mode: the last layer's epilogue writes fp32 rows (no 16-bit rounding of the result);
@@ -988,7 +989,9 @@ void Engine::Extract(const float* const* feats, int32_t num_streams, int64_t tot
                                     static_cast<int32_t*>(d_slot_n_) + slot_pos[bi], compute_));
       ProfEnd();
     }
-    RunFrames(dev, rows, src_min, src_max, fused ? static_cast<const PoolGroupMeta*>(d_pool_meta_) + meta_pos[bi] : nullptr);
+    const int32_t batch_slots = fused ? slot_begin_packed[slot_begin_pos[bi] + (b.c1 - b.c0)] : 0;
+    RunFrames(dev, rows, src_min, src_max, fused ? static_cast<const PoolGroupMeta*>(d_pool_meta_) + meta_pos[bi] : nullptr,
+              nullptr, 0, batch_slots);
     if (!dev_in) CVX_CUDA_CHECK(cudaEventRecord(feat_free_[fb], compute_));
 
     const int32_t nslabs = static_cast<int32_t>(b.slab1 - b.slab0);

@@ -129,7 +129,8 @@ class Engine {
   void BuildHaloArgs(FrameOp& op);
   // pool_meta != NULL: the pooled layer runs with the fused-pooling epilogue (partials -> d_partials_)
   void RunFrames(const float* const* dev_feats, int64_t rows, int64_t src_row_min, int64_t src_row_max,
-                 const PoolGroupMeta* pool_meta = nullptr, float* f32_out = nullptr, int32_t f32_ld = 0);
+                 const PoolGroupMeta* pool_meta = nullptr, float* f32_out = nullptr, int32_t f32_ld = 0,
+                 int32_t pool_slots = 0);
   void ProfBegin(int cls, double flops, double bytes, int layer = -1);
   void ProfEnd();
   void ProfResolve();

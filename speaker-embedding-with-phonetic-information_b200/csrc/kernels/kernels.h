@@ -58,8 +58,10 @@ struct TdnnGemmArgs {
   int32_t out_f32;        // pair kernel only: write fp32 output (c_map is an fp32 map with 32-column boxes)
   int32_t c_row0;         // row offset added to every output store (segment layers write into a slice)
   const PoolGroupMeta* pool_meta;  // non-NULL: fused pooling (see PoolGroupMeta), no activation store
-  float* pool_partials;            // [slots][2][pool_ld]: sum x, sum x^2 per slot and column
-  int32_t pool_ld;
+  // partials, blocked by 64 columns so that the finalize kernel streams them:
+  // [column block][pool_slots][2 (sum x, sum x^2)][64]
+  float* pool_partials;
+  int32_t pool_ld, pool_slots;
   int32_t num_stages;     // smem ring depth actually used (<= the kernel's maximum; tuning aid)
   // pair kernel, layers with at most 2 K blocks (K <= 128, the first TDNN layers): every CTA pair
   // keeps ONE tile column for the whole launch and loads its weight half-tiles once instead of with
@@ -170,7 +172,8 @@ cudaError_t LaunchSplitF32(const float* in, int32_t ld_in, int64_t m, int32_t k,
 cudaError_t LaunchPoolMeta(const int32_t* lo, const int32_t* hi, const int32_t* slot_begin, int32_t num_chunks,
                            int64_t num_groups, PoolGroupMeta* meta, int32_t* slot_n, cudaStream_t stream);
 
-// fused-pooling finalize: chunk c owns slots [slot_begin[c], slot_begin[c+1]) with slot_n[] valid rows each
+// fused-pooling finalize: chunk c owns slots [slot_begin[c], slot_begin[c+1]) with slot_n[] valid rows each;
+// partials in the blocked layout of TdnnGemmArgs::pool_partials with pool_slots = total_slots
 cudaError_t LaunchStatsPoolFinalizeFused(const float* partials, int32_t ld, const int32_t* slot_begin,
                                          const int32_t* slot_n, int32_t num_chunks, int32_t total_slots,
                                          int32_t dim, int32_t output_stddevs, float variance_floor, float* stats,

@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(256) stats_pool_finalize_kernel(const float* _
 // each Chan merge; the lanes are then merged in order through shared memory (deterministic).
 // kLanes = 4 for long chunks (hundreds of slots), 1 for short segments (a handful of slots).
 template <int kLanes>
-__global__ void __launch_bounds__(256) stats_pool_finalize_fused_kernel(const float* __restrict__ partials, int ld,
+__global__ void __launch_bounds__(256) stats_pool_finalize_fused_kernel(const float* __restrict__ partials, int total_slots,
                                                                          const int32_t* __restrict__ slot_begin,
                                                                          const int32_t* __restrict__ slot_n, int dim,
                                                                          int output_stddevs, float floor_,
@@ -202,14 +202,16 @@ __global__ void __launch_bounds__(256) stats_pool_finalize_fused_kernel(const fl
   const int a = s0 + part * per, b = min(s1, a + per);
   float n = 0.f, mean = 0.f, m2 = 0.f;
   if (j < dim) {
+    // column j of slot s: block j / 64 of the blocked layout -- consecutive slots are 512 bytes apart
+    const float* col = partials + (static_cast<int64_t>(j >> 6) * total_slots * 2) * 64 + (j & 63);
     for (int s = a; s < b; s += 8) {
       float nb = 0.f, sx = 0.f, sxx = 0.f;
       float vx[8], vxx[8];
 #pragma unroll
       for (int t = 0; t < 8; ++t) {
         const bool on = s + t < b;
-        vx[t] = on ? partials[static_cast<int64_t>(s + t) * 2 * ld + j] : 0.f;
-        vxx[t] = on ? partials[static_cast<int64_t>(s + t) * 2 * ld + ld + j] : 0.f;
+        vx[t] = on ? col[static_cast<int64_t>(s + t) * 128] : 0.f;
+        vxx[t] = on ? col[static_cast<int64_t>(s + t) * 128 + 64] : 0.f;
         nb += on ? static_cast<float>(slot_n[s + t]) : 0.f;
       }
 #pragma unroll
@@ -306,11 +308,11 @@ cudaError_t LaunchStatsPoolFinalizeFused(const float* partials, int32_t ld, cons
   if (num_chunks <= 0) return cudaSuccess;
   if (total_slots / num_chunks >= 32) {  // long chunks: split each chunk's slots over 4 lanes
     dim3 grid(num_chunks, (dim + 63) / 64);
-    stats_pool_finalize_fused_kernel<4><<<grid, 256, 0, stream>>>(partials, ld, slot_begin, slot_n, dim, output_stddevs,
+    stats_pool_finalize_fused_kernel<4><<<grid, 256, 0, stream>>>(partials, total_slots, slot_begin, slot_n, dim, output_stddevs,
                                                                   variance_floor, stats, ld_stats);
   } else {
     dim3 grid(num_chunks, (dim + 255) / 256);
-    stats_pool_finalize_fused_kernel<1><<<grid, 256, 0, stream>>>(partials, ld, slot_begin, slot_n, dim, output_stddevs,
+    stats_pool_finalize_fused_kernel<1><<<grid, 256, 0, stream>>>(partials, total_slots, slot_begin, slot_n, dim, output_stddevs,
                                                                   variance_floor, stats, ld_stats);
   }
   return cudaGetLastError();

@@ -308,12 +308,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
               }
             }
             const int slot = meta.slot + ((seg && has_a) ? 1 : 0);
-            float* out = args.pool_partials + static_cast<int64_t>(slot) * 2 * args.pool_ld + n0 + c * 64 + lane;
+            // blocked layout [column block of 64][slot][sum | sum of squares][64] (the tile column base is a
+            // multiple of 32, so a half's 32 columns stay inside one block)
+            const int col = n0 + c * 64;
+            float* out = args.pool_partials +
+                         ((static_cast<int64_t>(col >> 6) * args.pool_slots + slot) * 2) * 64 + (col & 63) + lane;
             out[0] = sx0;
-            out[args.pool_ld] = sxx0;
+            out[64] = sxx0;
             if (!half_chunk) {
-              out[32] = sx1;
-              out[args.pool_ld + 32] = sxx1;
+              float* out1 = args.pool_partials +
+                            ((static_cast<int64_t>((col + 32) >> 6) * args.pool_slots + slot) * 2) * 64 + ((col + 32) & 63) + lane;
+              out1[0] = sx1;
+              out1[64] = sxx1;
             }
           }
           continue;
