@@ -273,6 +273,25 @@ void cvx_device_free(int32_t device, void* ptr);
 int cvx_memcpy_h2d(int32_t device, void* dst, const void* src, size_t bytes);
 int cvx_device_count(int32_t* count);
 
+/* ------------------------------------------------------- job fan-out --
+ * The recipe starts `nj` processes per stage with --use-gpu=yes and no device hint
+ * (extract_xvectors_new.sh:83-89); upstream picks a device per process in CuDevice::SelectGpuId.
+ * cvx_acquire_device gives every process of a box its own GPU: it takes an advisory lock file
+ * (flock, $CVX_LOCK_DIR or /tmp, named by PCI bus id, released when the process exits) on the
+ * first device nobody holds; when all devices are held the jobs spread evenly and *sharers
+ * (may be NULL) is the number of jobs already on the chosen device.  wait != 0 (--use-gpu=wait):
+ * block until a device is free instead of sharing. */
+int cvx_acquire_device(int32_t wait, int32_t* device, int32_t* sharers);
+/* Test entry: the same lock protocol over `num_devices` made-up devices in directory `dir`. */
+int cvx_test_acquire_lock(const char* dir, int32_t num_devices, int32_t wait, int32_t* device, int32_t* sharers);
+
+/* Length-balanced utterance shards (replaces utils/split_data.sh for this path,
+ * extract_xvectors_new.sh:72-74): greedy longest-processing-time over frame counts -- utterances
+ * sorted by length (descending, ties in input order) go to the currently lightest shard (ties: the
+ * lowest shard index).  shard_of[u] receives the 0-based shard of utterance u.  Deterministic:
+ * every job computes the same partition from utt2num_frames without communicating. */
+int cvx_lpt_shards(const int64_t* lengths, int64_t num_utts, int32_t num_shards, int32_t* shard_of);
+
 /* Profile of the calls since the last reset (opts.profile = 1): one record per
  * kernel class. */
 typedef struct cvx_kernel_profile {

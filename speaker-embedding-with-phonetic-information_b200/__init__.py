@@ -87,6 +87,7 @@ ABI_SYMBOLS = [
     "cvx_test_prestep", "cvx_host_alloc", "cvx_host_free", "cvx_device_alloc",
     "cvx_device_free", "cvx_memcpy_h2d", "cvx_device_count", "cvx_engine_get_profile",
     "cvx_engine_reset_profile", "cvx_engine_launch_count", "cvx_engine_last_extract_ms", "cvx_test_tdnn_layer", "cvx_test_tdnn_layer_bench", "cvx_test_stats_pool",
+    "cvx_acquire_device", "cvx_test_acquire_lock", "cvx_lpt_shards",
 ]
 
 _lib = None
@@ -155,6 +156,9 @@ def load_library() -> C.CDLL:
                                               C.c_int32, C.POINTER(C.c_double)]
     lib.cvx_test_stats_pool.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
                                         C.c_int64, C.c_float, C.c_void_p]
+    lib.cvx_acquire_device.argtypes = [C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    lib.cvx_test_acquire_lock.argtypes = [C.c_char_p, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    lib.cvx_lpt_shards.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
     _lib = lib
     return lib
 
@@ -172,6 +176,15 @@ def device_count() -> int:
     n = C.c_int32(0)
     load_library().cvx_device_count(C.byref(n))
     return n.value
+
+
+def lpt_shards(lengths: Sequence[int], num_shards: int) -> np.ndarray:
+    """shard index per utterance from the C ABI's cvx_lpt_shards (the partition the drop-in
+    programs use for --shard=J/N --utt2num-frames=...; same rule as shard.lpt_shards)."""
+    ln = np.ascontiguousarray(lengths, np.int64)
+    out = np.zeros(len(ln), np.int32)
+    _check(load_library().cvx_lpt_shards(_ptr(ln), len(ln), num_shards, _ptr(out)))
+    return out
 
 
 class PinnedArray:

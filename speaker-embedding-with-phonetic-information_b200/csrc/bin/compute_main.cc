@@ -18,6 +18,7 @@
 #include "../../../include/cvx.h"
 #include "../kaldi_io.h"
 #include "extract_main.h"
+#include "job_util.h"
 
 namespace cvx {
 namespace {
@@ -75,6 +76,7 @@ int ComputeMain(int argc, const char* const* argv) {
         "e.g.: nnet3-compute final.raw scp:feats.scp ark:nnet_prediction.ark\n"
         "See also: nnet3-xvector-compute\n");
     std::string use_gpu = "yes", output_node, nnet_config, precision = "fp16", ivectors, online_ivectors;
+    std::string shard_spec, utt2num_frames;
     int32_t gpu_id = -1, subsampling = 1;
     int64_t batch_rows = 1 << 19, max_batch_rows = 0;
     bool apply_exp = false, use_priors = false, profile = false;
@@ -93,7 +95,9 @@ int ComputeMain(int argc, const char* const* argv) {
                 "nnet3-copy --nnet-config=extract.config)");
     po.Register("nnet-config", &nnet_config, "File with an 'output-node name=output input=...' line (extract.config)");
     po.Register("precision", &precision, "TDNN operand type: fp16 | bf16 | fp32 (fp32 = slow validation kernels)");
-    po.Register("gpu-id", &gpu_id, "CUDA device ordinal (-1: $CVX_DEVICE or 0)");
+    po.Register("gpu-id", &gpu_id, "CUDA device ordinal (-1: $CVX_DEVICE, else a free GPU is picked and held through a lock file)");
+    po.Register("shard", &shard_spec, "J/N: process only the J-th (1-based) of N length-balanced shards of the feature table");
+    po.Register("utt2num-frames", &utt2num_frames, "frame counts for --shard (scp inputs can do without)");
     po.Register("batch-rows", &batch_rows, "Frames read from the feature pipe per cvx_compute_frames call");
     po.Register("max-batch-rows", &max_batch_rows, "Frames per packed device batch (0 = engine default)");
     po.Register("profile", &profile, "Print per-kernel CUDA-event times at the end");
@@ -126,10 +130,8 @@ int ComputeMain(int argc, const char* const* argv) {
     else if (precision == "bf16") prec = CVX_PRECISION_BF16;
     else if (precision == "fp32") prec = CVX_PRECISION_FP32;
     else throw KaldiError("invalid --precision " + precision);
-    if (gpu_id < 0) {
-      const char* e = std::getenv("CVX_DEVICE");
-      gpu_id = e ? std::atoi(e) : 0;
-    }
+    const std::pair<int32_t, int32_t> shard = ParseShard(shard_spec);
+    gpu_id = ChooseDevice(gpu_id, use_gpu, 1);
 
     cvx_model* model = nullptr;
     if (cvx_model_load_frames(nnet_rxfilename.c_str(), output_node.empty() ? nullptr : output_node.c_str(), &model) != CVX_OK)
@@ -148,7 +150,17 @@ int ComputeMain(int argc, const char* const* argv) {
     cvx_engine* engine = nullptr;
     if (cvx_engine_create(model, &eo, &engine) != CVX_OK) throw KaldiError(std::string("creating the GPU engine: ") + cvx_last_error());
 
-    SequentialMatrixReader reader(feat_rspecifier);
+    std::unordered_map<std::string, int32_t> bin_of;
+    std::function<bool(const std::string&)> keep;
+    if (shard.second > 1) {
+      const TableSpec fs = ParseRspecifier(feat_rspecifier);
+      bin_of = AssignShards(utt2num_frames, fs.is_scp ? fs.scp_name : std::string(), shard.second, nullptr);
+      keep = [&](const std::string& k) {
+        auto it = bin_of.find(k);
+        return it != bin_of.end() && it->second == shard.first;
+      };
+    }
+    SequentialMatrixReader reader(feat_rspecifier, false, keep);
     MatrixWriter writer(matrix_wspecifier);
     const int32_t dim = cvx_model_input_dim(model, 0), E = info.embedding_dim;
     // wide outputs (log-posteriors over thousands of senones): keep a batch's result under 1 GB of pinned memory

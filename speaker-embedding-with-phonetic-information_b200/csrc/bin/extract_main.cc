@@ -10,9 +10,13 @@
 //
 // Chunking / averaging follows nnet3-xvector-compute.cc main();
 // the forward pass itself goes through the C ABI (include/cvx.h) to the CUDA side.
-// Utterances are packed into row batches; worker threads (one per GPU in use, --num-gpus) run
-// cvx_extract on full batches while the main thread keeps reading the feature pipe(s) into a
-// free one; results are written in launch order.
+// Utterances are packed into row batches; a worker thread per GPU runs cvx_extract on full batches
+// while the reader keeps filling a free one.  One process can drive several GPUs (--num-gpus=G):
+// with scp inputs every GPU gets its own reader thread over a length-balanced share of the table
+// ("lanes": nothing is shared between them, the main thread merges their results back into table
+// order); with archive / pipe inputs (one sequential stream) the single reader hands batches to
+// the GPUs in turn.  --shard=J/N restricts the job to the J-th of N length-balanced shards of the
+// table (replaces utils/split_data.sh, extract_xvectors_new.sh:72-74).
 #include "extract_main.h"
 
 #include <chrono>
@@ -24,9 +28,11 @@
 #include <memory>
 #include <mutex>
 #include <thread>
+#include <unordered_map>
 
 #include "../../../include/cvx.h"
 #include "../kaldi_io.h"
+#include "job_util.h"
 
 namespace cvx {
 namespace {
@@ -40,7 +46,8 @@ struct HostBatch {
   std::vector<int64_t> chunk_start;
   std::vector<int32_t> chunk_len, chunk_utt;
   std::vector<float> chunk_weight;
-  std::vector<float> out;
+  float* out = nullptr;             // pinned: the embeddings come back with an asynchronous copy
+  size_t out_cap = 0;
   int64_t frames = 0;  // un-padded input frames of the successful utterances
   // raw-feature mode (device pre-step): rows are raw frames, chunks index the selected frames
   int64_t kept_rows = 0;
@@ -72,6 +79,17 @@ struct HostBatch {
       cap_rows[s] = ncap;
     }
   }
+  void ReserveOut(size_t n) {
+    if (n <= out_cap) return;
+    cvx_host_free(out);
+    out = nullptr;
+    out_cap = 0;
+    void* p = nullptr;
+    const size_t ncap = std::max<size_t>(n * 5 / 4, 1 << 16);
+    if (cvx_host_alloc(&p, ncap * sizeof(float)) != CVX_OK) throw KaldiError(cvx_last_error());
+    out = static_cast<float*>(p);
+    out_cap = ncap;
+  }
   void AppendRow(const std::vector<const float*>& src_rows) {
     for (size_t s = 0; s < feats.size(); ++s)
       std::memcpy(feats[s] + static_cast<size_t>(rows) * dims[s], src_rows[s], dims[s] * sizeof(float));
@@ -79,8 +97,76 @@ struct HostBatch {
   }
   ~HostBatch() {
     for (float* p : feats) cvx_host_free(p);
+    cvx_host_free(out);
   }
 };
+
+// Pins host batches on a helper thread, first batch first: pinning ~100 MB takes longer than
+// building an engine, and a job of less than one batch never waits for the second.
+struct BatchPool {
+  std::vector<HostBatch>& hb;
+  int64_t rows;
+  std::mutex mu;
+  std::condition_variable cv;
+  int ready = 0;
+  std::string error;
+  std::thread th;
+  BatchPool(std::vector<HostBatch>& h, int64_t r) : hb(h), rows(r) {
+    th = std::thread([this] {
+      for (size_t i = 0; i < hb.size(); ++i) {
+        try {
+          hb[i].Reserve(rows);
+        } catch (const std::exception& e) {
+          std::lock_guard<std::mutex> lk(mu);
+          error = e.what();
+          ready = static_cast<int>(hb.size());
+          cv.notify_all();
+          return;
+        }
+        std::lock_guard<std::mutex> lk(mu);
+        ready = static_cast<int>(i) + 1;
+        cv.notify_all();
+      }
+    });
+  }
+  void WaitFor(int i) {
+    std::unique_lock<std::mutex> lk(mu);
+    cv.wait(lk, [&] { return ready > i; });
+    if (!error.empty()) throw KaldiError("allocating pinned host memory: " + error);
+  }
+  ~BatchPool() {
+    if (th.joinable()) th.join();
+  }
+};
+
+// Results of one lane, consumed in order by the merging writer.
+struct ResultQueue {
+  std::mutex mu;
+  std::condition_variable cv;
+  std::deque<std::pair<std::string, std::vector<float>>> q;
+  bool done = false;
+  void Push(const std::string& key, const float* v, int32_t n) {
+    std::lock_guard<std::mutex> lk(mu);
+    q.emplace_back(key, std::vector<float>(v, v + n));
+    cv.notify_all();
+  }
+  void Finish() {
+    std::lock_guard<std::mutex> lk(mu);
+    done = true;
+    cv.notify_all();
+  }
+};
+
+struct LaneResult {
+  int64_t num_success = 0, num_fail = 0, frame_count = 0;
+  std::string error;
+};
+
+uint32_t KeyHash(const std::string& s) {  // FNV-1a: the same in every job of a stage
+  uint32_t h = 2166136261u;
+  for (unsigned char c : s) h = (h ^ c) * 16777619u;
+  return h;
+}
 
 }  // namespace
 
@@ -131,6 +217,7 @@ int ExtractMain(int argc, const char* const* argv, bool multiple_input) {
     ParseOptions po(multiple_input ? usage_multi : usage_single);
 
     std::string use_gpu = "yes", output_node, nnet_config, precision = "fp16", names, vad_rspecifier;
+    std::string shard_spec, utt2num_frames;
     std::string mean_vec, transform_mat;
     bool normalize_length = false, scaleup = true;
     int32_t chunk_size = -1, min_chunk_size = 100, gpu_id = -1, cmn_window = 0, min_cmn_window = 100, num_gpus = 1;
@@ -155,10 +242,19 @@ int ExtractMain(int argc, const char* const* argv, bool multiple_input) {
                 "nnet3-copy --nnet-config=extract.config)");
     po.Register("nnet-config", &nnet_config, "File with an 'output-node name=output input=...' line (extract.config)");
     po.Register("precision", &precision, "TDNN operand type: fp16 | bf16 | fp32 (fp32 = slow validation kernels)");
-    po.Register("gpu-id", &gpu_id, "CUDA device ordinal (-1: $CVX_DEVICE or 0)");
+    po.Register("gpu-id", &gpu_id,
+                "CUDA device ordinal (-1: $CVX_DEVICE, else a free GPU is picked and held through a lock file, so that "
+                "the nj jobs of a recipe stage spread over the GPUs of the box)");
     po.Register("num-gpus", &num_gpus,
-                "Use this many GPUs (devices gpu-id .. gpu-id + num-gpus - 1) from ONE process: row batches go to the "
-                "GPUs in turn, one worker thread and engine per GPU; output order is unchanged");
+                "Use this many GPUs (devices gpu-id .. gpu-id + num-gpus - 1) from ONE process, one engine per GPU. "
+                "scp inputs: one reader thread per GPU over a length-balanced share of the table; archive / pipe "
+                "inputs: row batches go to the GPUs in turn.  Output order is the table's either way");
+    po.Register("shard", &shard_spec,
+                "J/N: process only the J-th (1-based, like JOB) of N length-balanced shards of the feature table "
+                "(greedy LPT over frame counts; replaces utils/split_data.sh)");
+    po.Register("utt2num-frames", &utt2num_frames,
+                "utt2num_frames file of the data dir: frame counts for --shard / --num-gpus balancing (scp inputs can do "
+                "without: the counts are then read from the matrix headers)");
     po.Register("batch-rows", &batch_rows, "Frames read from the feature pipe(s) per cvx_extract call");
     po.Register("max-batch-rows", &max_batch_rows, "Frames per packed device batch (0 = engine default)");
     po.Register("profile", &profile, "Print per-kernel CUDA-event times at the end");
@@ -223,10 +319,12 @@ int ExtractMain(int argc, const char* const* argv, bool multiple_input) {
     else if (precision == "bf16") prec = CVX_PRECISION_BF16;
     else if (precision == "fp32") prec = CVX_PRECISION_FP32;
     else throw KaldiError("invalid --precision " + precision);
-    if (gpu_id < 0) {
-      const char* e = std::getenv("CVX_DEVICE");
-      gpu_id = e ? std::atoi(e) : 0;
-    }
+    if (pad_input && chunk_size != -1 && chunk_size < min_chunk_size)
+      CVX_WARN("--chunk-size=" << chunk_size << " is below --min-chunk-size=" << min_chunk_size
+                               << ": with --pad-input=true every chunk is padded to the minimum size");
+    if (num_gpus < 1) throw KaldiError("--num-gpus must be >= 1");
+    const std::pair<int32_t, int32_t> shard = ParseShard(shard_spec);
+    gpu_id = ChooseDevice(gpu_id, use_gpu, num_gpus);
 
     cvx_model* model = nullptr;
     if (cvx_model_load(nnet_rxfilename.c_str(), output_node.empty() ? nullptr : output_node.c_str(), &model) != CVX_OK)
@@ -265,66 +363,49 @@ int ExtractMain(int argc, const char* const* argv, bool multiple_input) {
     eo.precision = prec;
     eo.max_batch_rows = max_batch_rows;
     eo.profile = profile ? 1 : 0;
-    if (num_gpus < 1) throw KaldiError("--num-gpus must be >= 1");
-    // Pinned host batches: one being filled + one in flight per GPU.  Pinning ~100 MB takes longer than
-    // building an engine, so a helper thread allocates them, first batch first, while the main
-    // thread creates the engines; a batch is waited for only when the reader is about to fill it (a job of
-    // less than one batch never waits for the second).  Whole batches are pinned up front because
-    // growing pinned memory step by step costs more than the I/O.
-    std::vector<HostBatch> hb(num_gpus + 1);
-    for (HostBatch& b : hb) {
-      b.feats.assign(num_inputs, nullptr);
-      b.cap_rows.assign(num_inputs, 0);
-      b.dims.resize(num_inputs);
-      for (int s = 0; s < num_inputs; ++s) b.dims[s] = cvx_model_input_dim(model, s);
-    }
-    struct BatchPool {
-      std::vector<HostBatch>& hb;
-      int64_t rows;
-      int32_t device;
-      std::mutex mu;
-      std::condition_variable cv;
-      int ready = 0;
-      std::string error;
-      std::thread th;
-      BatchPool(std::vector<HostBatch>& h, int64_t r, int32_t dev) : hb(h), rows(r), device(dev) {
-        th = std::thread([this] {
-          for (size_t i = 0; i < hb.size(); ++i) {
-            try {
-              hb[i].Reserve(rows);
-            } catch (const std::exception& e) {
-              std::lock_guard<std::mutex> lk(mu);
-              error = e.what();
-              ready = static_cast<int>(hb.size());
-              cv.notify_all();
-              return;
-            }
-            std::lock_guard<std::mutex> lk(mu);
-            ready = static_cast<int>(i) + 1;
-            cv.notify_all();
-          }
-        });
-      }
-      void WaitFor(int i) {
-        std::unique_lock<std::mutex> lk(mu);
-        cv.wait(lk, [&] { return ready > i; });
-        if (!error.empty()) throw KaldiError("allocating pinned host memory: " + error);
-      }
-      ~BatchPool() {
-        if (th.joinable()) th.join();
-      }
-    } batch_pool(hb, batch_rows + batch_rows / 8 + 65536, gpu_id);
     int32_t ndev = 0;
     if (cvx_device_count(&ndev) != CVX_OK) throw KaldiError(std::string("no usable CUDA device: ") + cvx_last_error());
     if (gpu_id + num_gpus > ndev)
       throw KaldiError("--gpu-id=" + std::to_string(gpu_id) + " --num-gpus=" + std::to_string(num_gpus) + " but only " +
                        std::to_string(ndev) + " CUDA device(s) are visible");
-    // one engine per GPU (SURVEY 8e mode ii); engines share nothing, there is no collective
+
+    // ---- work partition: this job's shard, and inside it one lane per GPU when the tables are scp ----
+    std::vector<TableSpec> feat_specs;
+    bool scp_input = true;
+    for (const std::string& r : feat_rspecifiers) {
+      feat_specs.push_back(ParseRspecifier(r));
+      scp_input = scp_input && feat_specs.back().is_scp;
+    }
+    if (!vad_rspecifier.empty()) scp_input = scp_input && ParseRspecifier(vad_rspecifier).is_scp;
+    const int num_lanes = (num_gpus > 1 && scp_input) ? num_gpus : 1;
+    const int32_t num_bins = shard.second * num_lanes;
+    std::unordered_map<std::string, int32_t> bin_of;
+    if (num_bins > 1) {
+      bin_of = AssignShards(utt2num_frames, feat_specs[0].is_scp ? feat_specs[0].scp_name : std::string(), num_bins, nullptr);
+      CVX_LOG("shard " << (shard.first + 1) << "/" << shard.second << ": " << num_lanes << " reader lane(s), "
+                       << bin_of.size() << " utterances balanced by frame count over " << num_bins << " bins");
+    }
+    // bin of a key; keys without a frame count (not in utt2num_frames) are spread by hash
+    auto key_bin = [&](const std::string& key) -> int32_t {
+      auto it = bin_of.find(key);
+      return it != bin_of.end() ? it->second : static_cast<int32_t>(KeyHash(key) % static_cast<uint32_t>(num_bins));
+    };
+
+    // one engine per GPU (SURVEY 8e mode ii); engines share nothing, there is no collective.  Built
+    // concurrently: each is ~0.3 s of weight re-packing and uploads.
     std::vector<cvx_engine*> engines(num_gpus, nullptr);
-    for (int g = 0; g < num_gpus; ++g) {
-      eo.device = gpu_id + g;
-      if (cvx_engine_create(model, &eo, &engines[g]) != CVX_OK)
-        throw KaldiError(std::string("creating the GPU engine: ") + cvx_last_error());
+    {
+      std::vector<std::string> errs(num_gpus);
+      std::vector<std::thread> th;
+      for (int g = 0; g < num_gpus; ++g)
+        th.emplace_back([&, g] {
+          cvx_engine_options o = eo;
+          o.device = gpu_id + g;
+          if (cvx_engine_create(model, &o, &engines[g]) != CVX_OK) errs[g] = cvx_last_error();
+        });
+      for (std::thread& t : th) t.join();
+      for (const std::string& e : errs)
+        if (!e.empty()) throw KaldiError("creating the GPU engine: " + e);
     }
     cvx_engine* engine = engines[0];
 
@@ -354,229 +435,314 @@ int ExtractMain(int argc, const char* const* argv, bool multiple_input) {
           throw KaldiError(std::string("installing the vector post-step: ") + cvx_last_error());
     }
 
-    std::vector<std::unique_ptr<SequentialMatrixReader>> readers;
-    for (int i = 0; i < num_inputs; ++i) readers.emplace_back(new SequentialMatrixReader(feat_rspecifiers[i]));
-    VectorWriter writer(vector_wspecifier);
-    std::unique_ptr<SequentialMatrixReader> vad_reader;
-    if (!vad_rspecifier.empty()) vad_reader.reset(new SequentialMatrixReader(vad_rspecifier, /*allow_vectors=*/true));
     std::vector<cvx_prestep> prestep(num_inputs);
     for (int s = 0; s < num_inputs; ++s) prestep[s] = cvx_prestep{s == 0 ? cmn_window : 0, cmn_center ? 1 : 0, min_cmn_window, 0};
-
-    batch_pool.WaitFor(0);  // the first pinned batch (allocated while the engines were built)
     const int32_t E = cvx_engine_output_dim(engine);
     const int32_t ctx = info.left_context + info.right_context + 1;
-    int64_t num_success = 0, num_fail = 0, frame_count = 0;
     auto t_start = std::chrono::steady_clock::now();
 
-    // Jobs finish in launch order (outputs keep the input order); job k runs on GPU k mod num_gpus.
-    struct Job {
-      int batch = -1;
-      std::thread th;
-      int status = CVX_OK;
-      std::string error;
-    };
-    std::deque<std::unique_ptr<Job>> inflight;
-    struct Joiner {
-      std::deque<std::unique_ptr<Job>>& q;
-      ~Joiner() {
-        for (auto& j : q)
-          if (j->th.joinable()) j->th.join();
+    // ---- one lane: reader(s) -> pinned row batches -> cvx_extract on `engs` (in turn) -> emit, in table order ----
+    auto run_lane = [&](const std::vector<cvx_engine*>& engs, const std::function<bool(const std::string&)>& keep,
+                        const std::function<void(const std::string&, const float*)>& emit, LaneResult* res) {
+      const int ngpu = static_cast<int>(engs.size());
+      // pinned host batches: one being filled + one in flight per GPU of this lane
+      std::vector<HostBatch> hb(ngpu + 1);
+      for (HostBatch& b : hb) {
+        b.feats.assign(num_inputs, nullptr);
+        b.cap_rows.assign(num_inputs, 0);
+        b.dims.resize(num_inputs);
+        for (int s = 0; s < num_inputs; ++s) b.dims[s] = cvx_model_input_dim(model, s);
       }
-    } joiner{inflight};
-    std::vector<int> free_batches;
-    for (int i = 1; i <= num_gpus; ++i) free_batches.push_back(i);
-    int64_t launch_seq = 0;
-    auto finish_oldest = [&]() {
-      if (inflight.empty()) return;
-      std::unique_ptr<Job> job = std::move(inflight.front());
-      inflight.pop_front();
-      job->th.join();
-      if (job->status != CVX_OK) throw KaldiError("cvx_extract failed: " + job->error);
-      HostBatch& b = hb[job->batch];
-      for (size_t u = 0; u < b.keys.size(); ++u) writer.Write(b.keys[u], b.out.data() + u * E, E);
-      num_success += static_cast<int64_t>(b.keys.size());
-      frame_count += b.frames;
-      b.Reset();
-      free_batches.push_back(job->batch);
-    };
-    // Hands batch `which` to the next GPU and returns the index of a free batch to fill next.
-    auto launch = [&](int which) -> int {
-      HostBatch& b = hb[which];
-      if (b.keys.empty()) return which;
-      // the GPU this job goes to is the one the oldest job in flight runs on
-      if (static_cast<int>(inflight.size()) == num_gpus) finish_oldest();
-      b.out.assign(b.keys.size() * static_cast<size_t>(E), 0.f);
-      cvx_engine* eng = engines[launch_seq++ % num_gpus];
-      std::unique_ptr<Job> job(new Job);
-      job->batch = which;
-      Job* jp = job.get();
-      job->th = std::thread([&, which, eng, jp]() {
-        HostBatch& w = hb[which];
-        std::vector<const float*> f(w.feats.begin(), w.feats.end());
-        if (raw_mode)
-          jp->status = cvx_extract_raw(eng, f.data(), prestep.data(), num_inputs, w.rows, w.utt_raw_start.data(),
-                                       vad_reader ? w.keep.data() : nullptr, w.utt_kept_start.data(),
-                                       static_cast<int32_t>(w.keys.size()), w.chunk_start.data(), w.chunk_len.data(),
-                                       w.chunk_utt.data(), w.chunk_weight.data(),
-                                       static_cast<int64_t>(w.chunk_start.size()), w.out.data(), 0);
-        else
-          jp->status = cvx_extract(eng, f.data(), num_inputs, w.rows, w.chunk_start.data(), w.chunk_len.data(),
-                                   w.chunk_utt.data(), w.chunk_weight.data(), static_cast<int64_t>(w.chunk_start.size()),
-                                   static_cast<int32_t>(w.keys.size()), w.out.data(), 0);
-        if (jp->status != CVX_OK) jp->error = cvx_last_error();
-      });
-      inflight.push_back(std::move(job));
-      const int next = free_batches.back();
-      free_batches.pop_back();
-      batch_pool.WaitFor(next);
-      return next;
-    };
+      BatchPool batch_pool(hb, batch_rows + batch_rows / 8 + 65536);
+      std::vector<std::unique_ptr<SequentialMatrixReader>> readers;
+      for (int i = 0; i < num_inputs; ++i) readers.emplace_back(new SequentialMatrixReader(feat_rspecifiers[i], false, keep));
+      std::unique_ptr<SequentialMatrixReader> vad_reader;
+      if (!vad_rspecifier.empty()) vad_reader.reset(new SequentialMatrixReader(vad_rspecifier, /*allow_vectors=*/true, keep));
+      batch_pool.WaitFor(0);
+      int64_t& num_success = res->num_success;
+      int64_t& num_fail = res->num_fail;
+      int64_t& frame_count = res->frame_count;
 
-    int cur = 0;
-    if (num_inputs == 1 && !pad_input) {
-      // binary float matrices are read straight into the pinned batch at its tail
-      readers[0]->Value().placer = [&](int32_t rows, int32_t cols) -> float* {
-        HostBatch& b = hb[cur];
-        if (cols != b.dims[0]) return nullptr;
-        b.Reserve(b.rows + rows + std::max(min_chunk_size, 0));
-        return b.feats[0] + static_cast<size_t>(b.rows) * b.dims[0];
+      // Jobs finish in launch order (outputs keep the input order); job k runs on GPU k mod ngpu.
+      struct Job {
+        int batch = -1;
+        std::thread th;
+        int status = CVX_OK;
+        std::string error;
       };
-    }
-    std::vector<const Matrix*> mats(num_inputs);
-    std::vector<const float*> row_ptrs(num_inputs);
-    for (; !readers[0]->Done(); ) {
-      const std::string utt = readers[0]->Key();
-      bool ok = true;
-      for (int i = 0; i < num_inputs; ++i) {
-        if (readers[i]->Done() || readers[i]->Key() != utt)
-          throw KaldiError("feature streams are not in lock-step at utterance " + utt);
-        mats[stream_of_arg[i]] = &readers[i]->Value();
+      std::deque<std::unique_ptr<Job>> inflight;
+      struct Joiner {
+        std::deque<std::unique_ptr<Job>>& q;
+        ~Joiner() {
+          for (auto& j : q)
+            if (j->th.joinable()) j->th.join();
+        }
+      } joiner{inflight};
+      std::vector<int> free_batches;
+      for (int i = 1; i <= ngpu; ++i) free_batches.push_back(i);
+      int64_t launch_seq = 0;
+      auto finish_oldest = [&]() {
+        if (inflight.empty()) return;
+        std::unique_ptr<Job> job = std::move(inflight.front());
+        inflight.pop_front();
+        job->th.join();
+        if (job->status != CVX_OK) throw KaldiError("cvx_extract failed: " + job->error);
+        HostBatch& b = hb[job->batch];
+        for (size_t u = 0; u < b.keys.size(); ++u) emit(b.keys[u], b.out + u * E);
+        num_success += static_cast<int64_t>(b.keys.size());
+        frame_count += b.frames;
+        b.Reset();
+        free_batches.push_back(job->batch);
+      };
+      // Hands batch `which` to the next GPU and returns the index of a free batch to fill next.
+      auto launch = [&](int which) -> int {
+        HostBatch& b = hb[which];
+        if (b.keys.empty()) return which;
+        // the GPU this job goes to is the one the oldest job in flight runs on
+        if (static_cast<int>(inflight.size()) == ngpu) finish_oldest();
+        b.ReserveOut(b.keys.size() * static_cast<size_t>(E));
+        cvx_engine* eng = engs[launch_seq++ % ngpu];
+        std::unique_ptr<Job> job(new Job);
+        job->batch = which;
+        Job* jp = job.get();
+        job->th = std::thread([&, which, eng, jp]() {
+          HostBatch& w = hb[which];
+          std::vector<const float*> f(w.feats.begin(), w.feats.end());
+          if (raw_mode)
+            jp->status = cvx_extract_raw(eng, f.data(), prestep.data(), num_inputs, w.rows, w.utt_raw_start.data(),
+                                         vad_reader ? w.keep.data() : nullptr, w.utt_kept_start.data(),
+                                         static_cast<int32_t>(w.keys.size()), w.chunk_start.data(), w.chunk_len.data(),
+                                         w.chunk_utt.data(), w.chunk_weight.data(),
+                                         static_cast<int64_t>(w.chunk_start.size()), w.out, 0);
+          else
+            jp->status = cvx_extract(eng, f.data(), num_inputs, w.rows, w.chunk_start.data(), w.chunk_len.data(),
+                                     w.chunk_utt.data(), w.chunk_weight.data(), static_cast<int64_t>(w.chunk_start.size()),
+                                     static_cast<int32_t>(w.keys.size()), w.out, 0);
+          if (jp->status != CVX_OK) jp->error = cvx_last_error();
+        });
+        inflight.push_back(std::move(job));
+        const int next = free_batches.back();
+        free_batches.pop_back();
+        batch_pool.WaitFor(next);
+        return next;
+      };
+
+      int cur = 0;
+      if (num_inputs == 1 && !pad_input) {
+        // binary float matrices are read straight into the pinned batch at its tail
+        readers[0]->Value().placer = [&](int32_t rows, int32_t cols) -> float* {
+          HostBatch& b = hb[cur];
+          if (cols != b.dims[0]) return nullptr;
+          b.Reserve(b.rows + rows + std::max(min_chunk_size, 0));
+          return b.feats[0] + static_cast<size_t>(b.rows) * b.dims[0];
+        };
       }
-      const int32_t Traw = mats[0]->rows;
-      // raw mode: select-voiced-frames' rule (frames with VAD != 0, in order)
-      std::vector<int32_t> utt_keep;
-      if (vad_reader) {
-        if (vad_reader->Done() || vad_reader->Key() != utt)
-          throw KaldiError("the VAD table is not in lock-step with the features at utterance " + utt);
-        const Matrix& v = vad_reader->Value();
-        const int64_t n = static_cast<int64_t>(v.rows) * v.cols;
-        if (n != Traw) {
-          CVX_WARN("Mismatch in number for frames " << Traw << " for features and VAD " << n << ", for utterance " << utt);
-          ok = false;
-        } else {
-          for (int32_t i = 0; i < Traw; ++i)
-            if (v.Data()[i] != 0.0f) utt_keep.push_back(i);
-          if (utt_keep.empty()) {
-            CVX_WARN("No features were judged as voiced for utterance " << utt);
+      std::vector<const Matrix*> mats(num_inputs);
+      std::vector<const float*> row_ptrs(num_inputs);
+      for (; !readers[0]->Done(); ) {
+        const std::string utt = readers[0]->Key();
+        bool ok = true;
+        for (int i = 0; i < num_inputs; ++i) {
+          if (readers[i]->Done() || readers[i]->Key() != utt)
+            throw KaldiError("feature streams are not in lock-step at utterance " + utt);
+          mats[stream_of_arg[i]] = &readers[i]->Value();
+        }
+        const int32_t Traw = mats[0]->rows;
+        // raw mode: select-voiced-frames' rule (frames with VAD != 0, in order).  The VAD table is looked
+        // up by key like the random-access table of the pipe it replaces (scp,s,cs: sorted keys): entries
+        // for other utterances are passed over, a missing one fails this utterance only.
+        std::vector<int32_t> utt_keep;
+        if (vad_reader) {
+          while (!vad_reader->Done() && vad_reader->Key() < utt) vad_reader->Next();
+          if (vad_reader->Done() || vad_reader->Key() != utt) {
+            CVX_WARN("No VAD entry for utterance " << utt << " in " << vad_rspecifier);
             ok = false;
-          }
-        }
-      }
-      const int32_t T = vad_reader ? static_cast<int32_t>(utt_keep.size()) : Traw;  // frames the chunks are cut from
-      for (int s = 0; s < num_inputs; ++s) {
-        if (mats[s]->rows != Traw) {
-          CVX_WARN("Feature streams of " << utt << " have different numbers of rows (" << Traw << " vs " << mats[s]->rows << ")");
-          ok = false;
-        }
-        if (Traw > 0 && mats[s]->cols != hb[cur].dims[s])
-          throw KaldiError("feature dimension " + std::to_string(mats[s]->cols) + " of " + utt + " does not match the network's input dim " +
-                           std::to_string(hb[cur].dims[s]));
-      }
-      if (ok && Traw == 0) {
-        CVX_WARN("Zero-length utterance: " << utt);
-        ok = false;
-      }
-      if (ok && !pad_input && T < min_chunk_size) {
-        CVX_WARN("Minimum chunk size of " << min_chunk_size << " is greater than the number of rows in utterance: " << utt);
-        ok = false;
-      }
-      if (ok) {
-        // nnet3-xvector-compute.cc main(): this_chunk_size, num_chunks, per-chunk offset
-        int32_t this_chunk = chunk_size;
-        if (chunk_size == -1 || T < chunk_size) this_chunk = T;
-        const int32_t num_chunks = (T + this_chunk - 1) / this_chunk;
-        HostBatch& b = hb[cur];
-        b.Reserve(b.rows + Traw + std::max(min_chunk_size, 0));
-        const int64_t chunk_base = raw_mode ? b.kept_rows : b.rows;
-        const int32_t utt_index = static_cast<int32_t>(b.keys.size());
-        const size_t chunks_before = b.chunk_start.size();
-        const int64_t rows_before = b.rows;
-        // Fast path (no replicated rows needed): the utterance's rows go into the batch as one
-        // block -- or are already there when the reader placed them (single stream).
-        const bool tail_needs_pad = pad_input && (T - (num_chunks - 1) * this_chunk) < min_chunk_size;
-        bool block_copied = false;
-        if (!tail_needs_pad) {
-          for (int s = 0; s < num_inputs; ++s) {
-            float* dst = b.feats[s] + static_cast<size_t>(b.rows) * b.dims[s];
-            if (mats[s]->Data() != dst) std::memcpy(dst, mats[s]->Data(), static_cast<size_t>(Traw) * b.dims[s] * sizeof(float));
-          }
-          block_copied = true;
-        }
-        for (int32_t ci = 0; ci < num_chunks; ++ci) {
-          const int32_t begin = ci * this_chunk;
-          const int32_t offset = std::min(this_chunk, T - begin);
-          int32_t left_pad = 0, right_pad = 0;
-          bool use = true;
-          if (offset < min_chunk_size) {
-            if (!pad_input) use = false;
-            else {
-              left_pad = (min_chunk_size - offset) / 2;
-              right_pad = min_chunk_size - offset - left_pad;
+          } else {
+            const Matrix& v = vad_reader->Value();
+            const int64_t n = static_cast<int64_t>(v.rows) * v.cols;
+            if (n != Traw) {
+              CVX_WARN("Mismatch in number for frames " << Traw << " for features and VAD " << n << ", for utterance " << utt);
+              ok = false;
+            } else {
+              for (int32_t i = 0; i < Traw; ++i)
+                if (v.Data()[i] != 0.0f) utt_keep.push_back(i);
+              if (utt_keep.empty()) {
+                CVX_WARN("No features were judged as voiced for utterance " << utt);
+                ok = false;
+              }
             }
           }
-          const int32_t rows_here = left_pad + offset + right_pad;
-          if (use && rows_here < ctx) {
-            CVX_WARN("Chunk of " << rows_here << " frames of utterance " << utt << " is shorter than the network's context ("
-                                 << ctx << " frames); skipping it");
-            use = false;
-          }
-          const int64_t start = raw_mode ? chunk_base + begin : b.rows;
-          if (block_copied) {
-            if (!raw_mode) b.rows += offset;
-          } else {
-            auto put = [&](int32_t r) {
-              for (int s = 0; s < num_inputs; ++s) row_ptrs[s] = mats[s]->Row(r);
-              b.AppendRow(row_ptrs);
-            };
-            for (int32_t k = 0; k < left_pad; ++k) put(begin);
-            for (int32_t r = begin; r < begin + offset; ++r) put(r);
-            for (int32_t k = 0; k < right_pad; ++k) put(begin + offset - 1);
-          }
-          if (use) {
-            b.chunk_start.push_back(start);
-            b.chunk_len.push_back(rows_here);
-            b.chunk_utt.push_back(utt_index);
-            b.chunk_weight.push_back(static_cast<float>(offset));
-          }
         }
-        if (b.chunk_start.size() == chunks_before) {
-          CVX_WARN("No usable chunk in utterance " << utt);
-          b.rows = rows_before;
+        const int32_t T = vad_reader ? static_cast<int32_t>(utt_keep.size()) : Traw;  // frames the chunks are cut from
+        for (int s = 0; s < num_inputs; ++s) {
+          if (mats[s]->rows != Traw) {
+            CVX_WARN("Feature streams of " << utt << " have different numbers of rows (" << Traw << " vs " << mats[s]->rows << ")");
+            ok = false;
+          }
+          if (Traw > 0 && mats[s]->cols != hb[cur].dims[s])
+            throw KaldiError("feature dimension " + std::to_string(mats[s]->cols) + " of " + utt + " does not match the network's input dim " +
+                             std::to_string(hb[cur].dims[s]));
+        }
+        if (ok && Traw == 0) {
+          CVX_WARN("Zero-length utterance: " << utt);
           ok = false;
-        } else {
-          b.keys.push_back(utt);
-          b.frames += T;
-          if (raw_mode) {
-            b.rows = rows_before + Traw;
-            b.kept_rows += T;
-            b.utt_raw_start.push_back(b.rows);
-            b.utt_kept_start.push_back(b.kept_rows);
-            b.keep.insert(b.keep.end(), utt_keep.begin(), utt_keep.end());
+        }
+        if (ok && !pad_input && T < min_chunk_size) {
+          CVX_WARN("Minimum chunk size of " << min_chunk_size << " is greater than the number of rows in utterance: " << utt);
+          ok = false;
+        }
+        if (ok) {
+          // nnet3-xvector-compute.cc main(): this_chunk_size, num_chunks, per-chunk offset
+          int32_t this_chunk = chunk_size;
+          if (chunk_size == -1 || T < chunk_size) this_chunk = T;
+          const int32_t num_chunks = (T + this_chunk - 1) / this_chunk;
+          HostBatch& b = hb[cur];
+          // rows this utterance adds to the batch: its own, or with --pad-input every chunk brought
+          // up to min-chunk-size (with --chunk-size < --min-chunk-size that is EVERY chunk)
+          int64_t need_rows = Traw;
+          if (pad_input) {
+            need_rows = 0;
+            for (int32_t ci = 0; ci < num_chunks; ++ci)
+              need_rows += std::max(std::min(this_chunk, T - ci * this_chunk), min_chunk_size);
+          }
+          b.Reserve(b.rows + std::max<int64_t>(need_rows, Traw) + std::max(min_chunk_size, 0));
+          const int64_t chunk_base = raw_mode ? b.kept_rows : b.rows;
+          const int32_t utt_index = static_cast<int32_t>(b.keys.size());
+          const size_t chunks_before = b.chunk_start.size();
+          const int64_t rows_before = b.rows;
+          // Fast path (no replicated rows needed): the utterance's rows go into the batch as one
+          // block -- or are already there when the reader placed them (single stream).
+          const bool tail_needs_pad = pad_input && (T - (num_chunks - 1) * this_chunk) < min_chunk_size;
+          bool block_copied = false;
+          if (!tail_needs_pad) {
+            for (int s = 0; s < num_inputs; ++s) {
+              float* dst = b.feats[s] + static_cast<size_t>(b.rows) * b.dims[s];
+              if (mats[s]->Data() != dst) std::memcpy(dst, mats[s]->Data(), static_cast<size_t>(Traw) * b.dims[s] * sizeof(float));
+            }
+            block_copied = true;
+          }
+          for (int32_t ci = 0; ci < num_chunks; ++ci) {
+            const int32_t begin = ci * this_chunk;
+            const int32_t offset = std::min(this_chunk, T - begin);
+            int32_t left_pad = 0, right_pad = 0;
+            bool use = true;
+            if (offset < min_chunk_size) {
+              if (!pad_input) use = false;
+              else {
+                left_pad = (min_chunk_size - offset) / 2;
+                right_pad = min_chunk_size - offset - left_pad;
+              }
+            }
+            const int32_t rows_here = left_pad + offset + right_pad;
+            if (use && rows_here < ctx) {
+              CVX_WARN("Chunk of " << rows_here << " frames of utterance " << utt << " is shorter than the network's context ("
+                                   << ctx << " frames); skipping it");
+              use = false;
+            }
+            const int64_t start = raw_mode ? chunk_base + begin : b.rows;
+            if (block_copied) {
+              if (!raw_mode) b.rows += offset;
+            } else {
+              auto put = [&](int32_t r) {
+                for (int s = 0; s < num_inputs; ++s) row_ptrs[s] = mats[s]->Row(r);
+                b.AppendRow(row_ptrs);
+              };
+              for (int32_t k = 0; k < left_pad; ++k) put(begin);
+              for (int32_t r = begin; r < begin + offset; ++r) put(r);
+              for (int32_t k = 0; k < right_pad; ++k) put(begin + offset - 1);
+            }
+            if (use) {
+              b.chunk_start.push_back(start);
+              b.chunk_len.push_back(rows_here);
+              b.chunk_utt.push_back(utt_index);
+              b.chunk_weight.push_back(static_cast<float>(offset));
+            }
+          }
+          if (b.chunk_start.size() == chunks_before) {
+            CVX_WARN("No usable chunk in utterance " << utt);
+            b.rows = rows_before;
+            ok = false;
+          } else {
+            b.keys.push_back(utt);
+            b.frames += T;
+            if (raw_mode) {
+              b.rows = rows_before + Traw;
+              b.kept_rows += T;
+              b.utt_raw_start.push_back(b.rows);
+              b.utt_kept_start.push_back(b.kept_rows);
+              b.keep.insert(b.keep.end(), utt_keep.begin(), utt_keep.end());
+            }
           }
         }
+        if (!ok) ++num_fail;
+        for (int i = 0; i < num_inputs; ++i) readers[i]->Next();
+        if (hb[cur].rows >= batch_rows) cur = launch(cur);
       }
-      if (!ok) ++num_fail;
-      for (int i = 0; i < num_inputs; ++i) readers[i]->Next();
-      if (vad_reader) vad_reader->Next();
-      if (hb[cur].rows >= batch_rows) cur = launch(cur);
-    }
-    for (int i = 1; i < num_inputs; ++i)
-      if (!readers[i]->Done()) CVX_WARN("feature stream " << (i + 1) << " has extra utterances after the first stream ended");
-    launch(cur);
-    while (!inflight.empty()) finish_oldest();
-    for (auto& r : readers) {
-      int st = r->Close();
-      if (st != 0) CVX_WARN("a feature input pipe exited with status " << st);
+      for (int i = 1; i < num_inputs; ++i)
+        if (!readers[i]->Done()) CVX_WARN("feature stream " << (i + 1) << " has extra utterances after the first stream ended");
+      launch(cur);
+      while (!inflight.empty()) finish_oldest();
+      for (auto& r : readers) {
+        int st = r->Close();
+        if (st != 0) CVX_WARN("a feature input pipe exited with status " << st);
+      }
+    };
+
+    VectorWriter writer(vector_wspecifier);
+    int64_t num_success = 0, num_fail = 0, frame_count = 0;
+    if (num_lanes == 1) {
+      LaneResult res;
+      std::function<bool(const std::string&)> keep;
+      if (num_bins > 1) keep = [&](const std::string& k) { return key_bin(k) == shard.first; };
+      run_lane(engines, keep, [&](const std::string& key, const float* v) { writer.Write(key, v, E); }, &res);
+      num_success = res.num_success;
+      num_fail = res.num_fail;
+      frame_count = res.frame_count;
+    } else {
+      // lanes run side by side, each on its own GPU and its own share of the scp; this thread merges
+      // their results back into table order (a lane emits in table order; an utterance missing at the
+      // head of its lane's queue failed there)
+      std::vector<LaneResult> res(num_lanes);
+      std::vector<std::unique_ptr<ResultQueue>> queues;
+      for (int g = 0; g < num_lanes; ++g) queues.emplace_back(new ResultQueue);
+      std::vector<std::thread> threads;
+      for (int g = 0; g < num_lanes; ++g)
+        threads.emplace_back([&, g] {
+          try {
+            const int32_t my_bin = shard.first * num_lanes + g;
+            run_lane({engines[g]}, [&, my_bin](const std::string& k) { return key_bin(k) == my_bin; },
+                     [&, g](const std::string& key, const float* v) { queues[g]->Push(key, v, E); }, &res[g]);
+          } catch (const std::exception& e) {
+            res[g].error = e.what();
+          }
+          queues[g]->Finish();
+        });
+      struct LaneJoiner {
+        std::vector<std::thread>& t;
+        ~LaneJoiner() {
+          for (std::thread& th : t)
+            if (th.joinable()) th.join();
+        }
+      } lane_joiner{threads};
+      for (const auto& kv : SequentialMatrixReader::ReadScpList(feat_specs[0].scp_name)) {
+        const int32_t bin = key_bin(kv.first);
+        if (bin / num_lanes != shard.first) continue;
+        ResultQueue& q = *queues[bin % num_lanes];
+        std::unique_lock<std::mutex> lk(q.mu);
+        q.cv.wait(lk, [&] { return !q.q.empty() || q.done; });
+        if (q.q.empty() || q.q.front().first != kv.first) continue;  // failed in its lane
+        std::pair<std::string, std::vector<float>> item = std::move(q.q.front());
+        q.q.pop_front();
+        lk.unlock();
+        writer.Write(item.first, item.second.data(), E);
+      }
+      for (std::thread& th : threads) th.join();
+      for (const LaneResult& r : res) {
+        if (!r.error.empty()) throw KaldiError(r.error);
+        num_success += r.num_success;
+        num_fail += r.num_fail;
+        frame_count += r.frame_count;
+      }
     }
     writer.Close();
 

@@ -102,9 +102,12 @@ int IvectorMeanMain(int argc, const char* const* argv) {
         "or: ivector-mean <ivector-rspecifier> <mean-wxfilename>\n"
         "e.g.: ivector-mean data/spk2utt exp/ivectors.ark exp/spk_ivectors.ark exp/spk_num_utts.ark\n"
         "or: ivector-mean exp/ivectors.ark exp/mean.vec\n");
-    bool binary_write = true;
-    po.Register("binary", &binary_write, "If true, write the mean vector in binary (2-argument form)");
+    // upstream: --binary-write, default false (mean.vec is a text vector)
+    bool binary_write = false, binary_alias = false;
+    po.Register("binary-write", &binary_write, "If true, write the mean vector in binary (2-argument form)");
+    po.Register("binary", &binary_alias, "alias of --binary-write");
     po.Read(argc, argv);
+    binary_write = binary_write || binary_alias;
     if (po.NumArgs() < 2 || po.NumArgs() > 4) {
       po.PrintUsage();
       return 1;
@@ -331,24 +334,26 @@ int PldaScoringMain(int argc, const char* const* argv) {
       po.PrintUsage();
       return 1;
     }
-    // <Plda> mean (vector) transform (matrix) psi (vector) </Plda>
-    std::vector<float> mean_f, psi_f;
-    Matrix tf_f;
+    // <Plda> mean (vector) transform (matrix) psi (vector) </Plda>: stored in double precision upstream
+    // (DV / DM) and kept in double here
+    std::vector<double> mean, psi, tf;
+    struct { int32_t rows = 0, cols = 0; } tf_f;
     {
       Input in(po.GetArg(1));
       const bool binary = ReadBinaryHeader(in);
       ExpectToken(in, "<Plda>");
-      ReadVector(in, binary, &mean_f);
-      ReadMatrix(in, binary, &tf_f);
-      ReadVector(in, binary, &psi_f);
+      int32_t r = 0, c = 0;
+      ReadVectorOrMatrixDouble(in, binary, &r, &c, &mean, nullptr);
+      if (r > 1) throw KaldiError("expected the PLDA mean vector in " + po.GetArg(1));
+      ReadVectorOrMatrixDouble(in, binary, &tf_f.rows, &tf_f.cols, &tf, nullptr);
+      ReadVectorOrMatrixDouble(in, binary, &r, &c, &psi, nullptr);
+      if (r > 1) throw KaldiError("expected the PLDA psi vector in " + po.GetArg(1));
       ExpectToken(in, "</Plda>");
       int st = in.Close();
       if (st != 0) throw KaldiError("the PLDA input pipe exited with status " + std::to_string(st));
     }
-    if (tf_f.cols != static_cast<int32_t>(mean_f.size()) || tf_f.rows != static_cast<int32_t>(psi_f.size()))
+    if (tf_f.cols != static_cast<int32_t>(mean.size()) || tf_f.rows != static_cast<int32_t>(psi.size()))
       throw KaldiError("inconsistent dimensions in the PLDA model " + po.GetArg(1));
-    std::vector<double> mean(mean_f.begin(), mean_f.end()), psi(psi_f.begin(), psi_f.end()),
-        tf(tf_f.Data(), tf_f.Data() + static_cast<size_t>(tf_f.rows) * tf_f.cols);
 
     VectorTable train = ReadVectorTable(po.GetArg(2)), test = ReadVectorTable(po.GetArg(3));
     if ((train.size() && train.dim != tf_f.cols) || (test.size() && test.dim != tf_f.cols))

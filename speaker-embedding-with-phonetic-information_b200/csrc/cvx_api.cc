@@ -7,6 +7,7 @@
 #include <string>
 
 #include "../../include/cvx.h"
+#include "api_error.h"
 #include "engine.h"
 #include "kaldi_io.h"
 #include "nnet3_model.h"
@@ -75,6 +76,10 @@ cvx::Layer CopyLayer(const cvx_layer& in, bool frame) {
 }
 
 }  // namespace
+
+namespace cvx {
+int SetApiError(int code, const std::string& msg) { return Fail(code, msg); }
+}  // namespace cvx
 
 extern "C" {
 

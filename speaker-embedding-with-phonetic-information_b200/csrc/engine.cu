@@ -22,6 +22,8 @@
 #include <cstdlib>
 #include <cstring>
 
+#include "engine_detail.h"
+
 namespace cvx {
 
 namespace {
@@ -43,8 +45,11 @@ EncodeTiledFn GetEncodeTiled() {
 
 // 2-D map over a row-major [rows, ld] matrix of 2-byte elements, box = box_cols x box_rows,
 // 128-byte swizzle (box_cols * 2 bytes == 128), out-of-bounds reads give zeros.
+}  // namespace
+
+namespace detail {
 void Encode2D(CUtensorMap* map, int32_t elem, void* base, int64_t rows, int64_t ld, uint32_t box_cols,
-              uint32_t box_rows, int64_t cols = -1, bool swizzle = true) {
+              uint32_t box_rows, int64_t cols, bool swizzle) {
   cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols < 0 ? ld : cols), static_cast<cuuint64_t>(rows)};
   cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * ElemSize(elem)};
   cuuint32_t box[2] = {box_cols, box_rows};
@@ -58,8 +63,6 @@ void Encode2D(CUtensorMap* map, int32_t elem, void* base, int64_t rows, int64_t 
                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) throw CudaError("cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r)));
 }
-
-inline int32_t RoundUp(int32_t v, int32_t m) { return (v + m - 1) / m * m; }
 
 void ConvertToElem(const float* src, size_t n, int32_t elem, void* dst) {
   if (elem == kF32) {
@@ -79,17 +82,18 @@ float ElemToFloat(const void* p, size_t i, int32_t elem) {
   return __bfloat162float(static_cast<const __nv_bfloat16*>(p)[i]);
 }
 
+}  // namespace detail
+
+namespace {
 const char* kProfNames[] = {"stage_input", "tdnn_gemm", "stats_pool_partial", "stats_pool_finalize",
                             "segment_affine", "utt_average"};
 
 }  // namespace
 
-template <typename T>
-T* Engine::DevAlloc(size_t n) {
-  void* p = nullptr;
-  CVX_CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
-  return static_cast<T*>(p);
-}
+using detail::ConvertToElem;
+using detail::ElemToFloat;
+using detail::Encode2D;
+using detail::RoundUp;
 
 void Engine::Grow(void** p, size_t* cap, size_t bytes) {
   if (bytes <= *cap) return;
@@ -762,827 +766,5 @@ double Engine::DebugBenchFrames(const float* const* feats, int64_t rows, int32_t
   return ms;
 }
 
-// -------------------------------------------------------------- extract ----
-void Engine::Extract(const float* const* feats, int32_t num_streams, int64_t total_rows, const int64_t* chunk_start,
-                     const int32_t* chunk_len, const int32_t* chunk_utt, const float* chunk_weight,
-                     int64_t num_chunks, int32_t num_utts, float* out, uint32_t flags) {
-  CVX_CUDA_CHECK(cudaSetDevice(opts_.device));
-  if (num_streams != static_cast<int32_t>(plan_.input_dims.size()))
-    throw InvalidArgument("model has " + std::to_string(plan_.input_dims.size()) + " input stream(s), got " +
-                          std::to_string(num_streams));
-  if (plan_.FrameOutput())
-    throw InvalidArgument("this engine was built from a frame-output model (cvx_model_load_frames); use cvx_compute_frames");
-  if (num_utts < 0 || num_chunks < 0 || total_rows < 0) throw InvalidArgument("negative size");
-  if (!out && num_utts > 0) throw InvalidArgument("out is NULL");
-  const int32_t E = plan_.EmbeddingDim();
-  const bool dev_in = (flags & CVX_FLAG_DEVICE_INPUT) != 0, dev_out = (flags & CVX_FLAG_DEVICE_OUTPUT) != 0;
-  if (num_utts == 0) return;
-  if (num_chunks == 0) {
-    if (dev_out) CVX_CUDA_CHECK(cudaMemset(out, 0, static_cast<size_t>(num_utts) * OutputDim() * 4));
-    else std::memset(out, 0, static_cast<size_t>(num_utts) * OutputDim() * 4);
-    return;
-  }
-  for (int32_t s = 0; s < num_streams; ++s)
-    if (!feats || !feats[s]) throw InvalidArgument("feats[" + std::to_string(s) + "] is NULL");
-
-  const Layer& PL = plan_.frame[plan_.pool_src];
-  const int32_t L = PL.left, R = PL.right;
-  const int32_t lc = plan_.pool_left_context, rc = plan_.pool_right_context;
-  (void)lc;  // left >= 0 >= -lc: the window's left edge never binds
-
-  // ---- validate chunks, cut batches, build pooling slabs ----
-  struct Batch {
-    int64_t c0, c1, row0, row1;
-    int64_t slab0, slab1;
-  };
-  std::vector<Batch> batches;
-  std::vector<PoolSlab> slabs;
-  std::vector<int64_t> utt_off(static_cast<size_t>(num_utts) + 1, 0);
-  std::vector<float> weights(num_chunks);
-  int64_t prev_end = 0;
-  int32_t prev_utt = 0;
-  int64_t max_chunk_rows = 0;
-  for (int64_t c = 0; c < num_chunks; ++c) {
-    const int64_t st = chunk_start[c];
-    const int32_t len = chunk_len[c];
-    if (st < prev_end || len <= 0 || st + len > total_rows)
-      throw InvalidArgument("chunk " + std::to_string(c) + " is out of order, overlapping or out of range");
-    if (chunk_utt[c] < prev_utt || chunk_utt[c] >= num_utts)
-      throw InvalidArgument("chunk_utt must be non-decreasing and < num_utts");
-    if (std::min<int64_t>(len - 1 - R, rc) < L)
-      throw InvalidArgument("chunk " + std::to_string(c) + " has " + std::to_string(len) + " rows but the network needs " +
-                            std::to_string(L + R + 1) + " (left " + std::to_string(L) + ", right " + std::to_string(R) + ")");
-    prev_end = st + len;
-    prev_utt = chunk_utt[c];
-    utt_off[chunk_utt[c] + 1] += 1;
-    weights[c] = chunk_weight ? chunk_weight[c] : static_cast<float>(len);
-    max_chunk_rows = std::max<int64_t>(max_chunk_rows, len);
-  }
-  for (int32_t u = 0; u < num_utts; ++u) utt_off[u + 1] += utt_off[u];
-  const int64_t cap = std::max(max_batch_rows_, (max_chunk_rows + kGemmBlockM - 1) / kGemmBlockM * kGemmBlockM);
-  // valid (poolable) rows of every chunk, relative to its batch; hi inclusive
-  std::vector<int32_t> chunk_lo(num_chunks), chunk_hi(num_chunks);
-  {
-    int64_t c = 0;
-    while (c < num_chunks) {
-      Batch b;
-      b.c0 = c;
-      b.row0 = chunk_start[c];
-      b.slab0 = b.slab1 = 0;
-      while (c < num_chunks && chunk_start[c] + chunk_len[c] - b.row0 <= cap) {
-        chunk_lo[c] = static_cast<int32_t>(chunk_start[c] - b.row0 + L);
-        chunk_hi[c] = static_cast<int32_t>(chunk_start[c] - b.row0 + std::min<int64_t>(chunk_len[c] - 1 - R, rc));
-        ++c;
-      }
-      b.c1 = c;
-      b.row1 = chunk_start[c - 1] + chunk_len[c - 1];
-      batches.push_back(b);
-    }
-  }
-  // ---- fused pooling: per batch, every 32-row group holds at most two runs of valid rows (tail of
-  // one chunk, head of the next); slot = one run.  The host only numbers the slots per chunk, the
-  // per-group table itself is built on the device (pool_meta_kernel), so this is O(chunks). ----
-  bool fused = fused_pool_;
-  std::vector<int32_t> slot_begin_packed;  // per batch: [nchunks + 1] slot offsets
-  std::vector<int64_t> meta_pos(batches.size()), slot_pos(batches.size()), slot_begin_pos(batches.size()),
-      batch_groups(batches.size());
-  int64_t max_slots = 0, total_groups = 0, total_slots = 0;
-  for (size_t bi = 0; bi < batches.size() && fused; ++bi) {
-    const Batch& b = batches[bi];
-    const int64_t rows = b.row1 - b.row0;
-    batch_groups[bi] = (rows + 2 * kGemmBlockM - 1) / (2 * kGemmBlockM) * (2 * kGemmBlockM) / 32;
-    meta_pos[bi] = total_groups;
-    slot_pos[bi] = total_slots;
-    slot_begin_pos[bi] = static_cast<int64_t>(slot_begin_packed.size());
-    int32_t nslots = 0;
-    for (int64_t c = b.c0; c < b.c1; ++c) {
-      // three runs in one group (tiny chunks): use the stand-alone pooling kernels
-      if (c + 2 < b.c1 && chunk_lo[c + 2] / 32 == chunk_hi[c] / 32) fused = false;
-      slot_begin_packed.push_back(nslots);
-      nslots += chunk_hi[c] / 32 - chunk_lo[c] / 32 + 1;
-    }
-    slot_begin_packed.push_back(nslots);
-    max_slots = std::max<int64_t>(max_slots, nslots);
-    total_groups += batch_groups[bi];
-    total_slots += nslots;
-  }
-
-  // stand-alone pooling: slabs of <= kPoolSlabRows valid rows cut relative to each chunk;
-  // chunk_slab_off is stored per batch as [c1-c0+1] entries relative to the batch's first slab
-  std::vector<int32_t> slab_off_packed;
-  std::vector<int64_t> slab_off_pos(batches.size());
-  if (!fused) {
-    for (size_t bi = 0; bi < batches.size(); ++bi) {
-      Batch& b = batches[bi];
-      b.slab0 = static_cast<int64_t>(slabs.size());
-      slab_off_pos[bi] = static_cast<int64_t>(slab_off_packed.size());
-      for (int64_t c = b.c0; c < b.c1; ++c) {
-        slab_off_packed.push_back(static_cast<int32_t>(slabs.size() - b.slab0));
-        for (int64_t r = chunk_lo[c]; r <= chunk_hi[c]; r += kPoolSlabRows) {
-          PoolSlab sl;
-          sl.row_begin = r;
-          sl.nrows = static_cast<int32_t>(std::min<int64_t>(kPoolSlabRows, chunk_hi[c] - r + 1));
-          sl.chunk = static_cast<int32_t>(c - b.c0);
-          slabs.push_back(sl);
-        }
-      }
-      b.slab1 = static_cast<int64_t>(slabs.size());
-      slab_off_packed.push_back(static_cast<int32_t>(b.slab1 - b.slab0));
-    }
-  }
-
-  // ---- device scratch ----
-  int64_t max_rows = 0, max_chunks = 0, max_slabs = 0;
-  for (const Batch& b : batches) {
-    max_rows = std::max(max_rows, b.row1 - b.row0);
-    max_chunks = std::max(max_chunks, b.c1 - b.c0);
-    max_slabs = std::max(max_slabs, b.slab1 - b.slab0);
-  }
-  EnsureRows(max_rows);
-  const Buffer& pool_buf = buffers_[layer_buffer_[plan_.pool_src]];
-  const int32_t D = PL.out_dim, pooled = plan_.PooledDim();
-  Grow(&d_slabs_, &slabs_cap_, std::max<size_t>(slabs.size(), 1) * sizeof(PoolSlab));
-  Grow(&d_chunk_slab_off_, &chunk_slab_off_cap_, std::max<size_t>(slab_off_packed.size(), 1) * 4);
-  Grow(&d_weights_, &weights_cap_, weights.size() * 4);
-  Grow(&d_utt_off_, &utt_off_cap_, utt_off.size() * 8);
-  Grow(&d_partials_, &partials_cap_, static_cast<size_t>(std::max(max_slabs, fused ? max_slots : 0)) * 2 * pool_buf.ld * 4);
-  if (fused) {
-    Grow(&d_pool_meta_, &pool_meta_cap_, static_cast<size_t>(total_groups) * sizeof(PoolGroupMeta));
-    Grow(&d_slot_n_, &slot_n_cap_, static_cast<size_t>(std::max<int64_t>(total_slots, 1)) * 4);
-    Grow(&d_slot_begin_, &slot_begin_cap_, slot_begin_packed.size() * 4);
-    Grow(&d_chunk_rng_, &chunk_rng_cap_, static_cast<size_t>(num_chunks) * 8);
-  }
-  // pooled statistics of several device batches are collected and the segment layers run on
-  // up to kSegFlushChunks chunks at once (a [few chunks, 3000] GEMM per batch is latency bound)
-  constexpr int64_t kSegFlushChunks = 16384;
-  const int64_t seg_cap_chunks = std::max(max_chunks, std::min<int64_t>(num_chunks, kSegFlushChunks));
-  Grow(&d_stats_, &stats_cap_, static_cast<size_t>(seg_cap_chunks) * pooled * 4);
-  int32_t max_seg = 0;
-  for (size_t i = 0; i + 1 < seg_ops_.size(); ++i) max_seg = std::max(max_seg, seg_ops_[i].out_dim);
-  for (int i = 0; i < 2; ++i) Grow(&d_seg_[i], &seg_cap_[i], static_cast<size_t>(seg_cap_chunks) * std::max(max_seg, 1) * 4);
-  int32_t max_kp = 0;
-  for (const SegOp& so : seg_ops_)
-    if (so.tensor) max_kp = std::max(max_kp, so.kp);
-  if (max_kp > 0) {
-    const int64_t split_rows = (seg_cap_chunks + 2 * kGemmBlockM - 1) / (2 * kGemmBlockM) * (2 * kGemmBlockM);
-    Grow(&d_seg_hi_, &seg_hi_cap_, static_cast<size_t>(split_rows) * max_kp * 2);
-    Grow(&d_seg_lo_, &seg_lo_cap_, static_cast<size_t>(split_rows) * max_kp * 2);
-    seg_split_rows_ = split_rows;
-  }
-  Grow(&d_chunk_emb_, &chunk_emb_cap_, static_cast<size_t>(num_chunks) * E * 4);
-  Grow(&d_out_, &out_cap_, static_cast<size_t>(num_utts) * E * 4);
-  if (!dev_in)
-    for (int i = 0; i < 2; ++i)
-      for (int32_t s = 0; s < num_streams; ++s)
-        Grow(&d_feat_[i][s], &d_feat_cap_[i][s], static_cast<size_t>(max_rows) * plan_.input_dims[s] * 4);
-
-  if (fused) {
-    int32_t* rng = static_cast<int32_t*>(d_chunk_rng_);
-    CVX_CUDA_CHECK(cudaMemcpyAsync(rng, chunk_lo.data(), static_cast<size_t>(num_chunks) * 4, cudaMemcpyHostToDevice, compute_));
-    CVX_CUDA_CHECK(cudaMemcpyAsync(rng + num_chunks, chunk_hi.data(), static_cast<size_t>(num_chunks) * 4, cudaMemcpyHostToDevice, compute_));
-    CVX_CUDA_CHECK(cudaMemcpyAsync(d_slot_begin_, slot_begin_packed.data(), slot_begin_packed.size() * 4, cudaMemcpyHostToDevice, compute_));
-  } else {
-    CVX_CUDA_CHECK(cudaMemcpyAsync(d_slabs_, slabs.data(), slabs.size() * sizeof(PoolSlab), cudaMemcpyHostToDevice, compute_));
-    CVX_CUDA_CHECK(cudaMemcpyAsync(d_chunk_slab_off_, slab_off_packed.data(), slab_off_packed.size() * 4,
-                                   cudaMemcpyHostToDevice, compute_));
-  }
-  CVX_CUDA_CHECK(cudaMemcpyAsync(d_weights_, weights.data(), weights.size() * 4, cudaMemcpyHostToDevice, compute_));
-  CVX_CUDA_CHECK(cudaMemcpyAsync(d_utt_off_, utt_off.data(), utt_off.size() * 8, cudaMemcpyHostToDevice, compute_));
-  // the pageable host vectors above must stay alive until these copies ran
-  CVX_CUDA_CHECK(cudaStreamSynchronize(compute_));
-
-  // ---- batches ----
-  CVX_CUDA_CHECK(cudaEventRecord(call_begin_, compute_));
-  int64_t pending = 0, pending_c0 = 0;  // chunks whose statistics wait for the segment layers
-  for (size_t bi = 0; bi < batches.size(); ++bi) {
-    const Batch& b = batches[bi];
-    const int64_t rows = b.row1 - b.row0;
-    const int fb = static_cast<int>(bi & 1);
-    const float* dev[kMaxASources] = {};
-    int64_t src_min, src_max;
-    if (dev_in) {
-      if (before_batch_) before_batch_(b.row1);  // cvx_extract_raw: pre-step of the pieces this batch reads
-      for (int32_t s = 0; s < num_streams; ++s) dev[s] = feats[s] + b.row0 * plan_.input_dims[s];
-      src_min = -b.row0;
-      src_max = total_rows - b.row0;
-    } else {
-      // H2D of this batch on the copy stream, overlapping the previous batch's compute
-      if (bi >= 2) CVX_CUDA_CHECK(cudaStreamWaitEvent(copy_, feat_free_[fb], 0));
-      for (int32_t s = 0; s < num_streams; ++s) {
-        CVX_CUDA_CHECK(cudaMemcpyAsync(d_feat_[fb][s], feats[s] + b.row0 * plan_.input_dims[s],
-                                       static_cast<size_t>(rows) * plan_.input_dims[s] * 4, cudaMemcpyHostToDevice, copy_));
-        dev[s] = static_cast<const float*>(d_feat_[fb][s]);
-      }
-      CVX_CUDA_CHECK(cudaEventRecord(feat_ready_[fb], copy_));
-      CVX_CUDA_CHECK(cudaStreamWaitEvent(compute_, feat_ready_[fb], 0));
-      src_min = 0;
-      src_max = rows;
-    }
-    if (fused) {
-      // per-group run table and rows per slot of this batch, from the chunk ranges
-      const int32_t* rng = static_cast<const int32_t*>(d_chunk_rng_);
-      ProfBegin(kProfPoolFin, 0, static_cast<double>(batch_groups[bi]) * sizeof(PoolGroupMeta));
-      CVX_CUDA_CHECK(LaunchPoolMeta(rng + b.c0, rng + num_chunks + b.c0,
-                                    static_cast<const int32_t*>(d_slot_begin_) + slot_begin_pos[bi],
-                                    static_cast<int32_t>(b.c1 - b.c0), batch_groups[bi],
-                                    static_cast<PoolGroupMeta*>(d_pool_meta_) + meta_pos[bi],
-                                    static_cast<int32_t*>(d_slot_n_) + slot_pos[bi], compute_));
-      ProfEnd();
-    }
-    const int32_t batch_slots = fused ? slot_begin_packed[slot_begin_pos[bi] + (b.c1 - b.c0)] : 0;
-    RunFrames(dev, rows, src_min, src_max, fused ? static_cast<const PoolGroupMeta*>(d_pool_meta_) + meta_pos[bi] : nullptr,
-              nullptr, 0, batch_slots);
-    if (!dev_in) CVX_CUDA_CHECK(cudaEventRecord(feat_free_[fb], compute_));
-
-    const int32_t nslabs = static_cast<int32_t>(b.slab1 - b.slab0);
-    const int32_t nchunks = static_cast<int32_t>(b.c1 - b.c0);
-    const PoolSlab* dsl = static_cast<const PoolSlab*>(d_slabs_) + b.slab0;
-    double pooled_rows = 0;
-    for (int64_t c = b.c0; c < b.c1; ++c) pooled_rows += chunk_hi[c] - chunk_lo[c] + 1;
-    if (fused) {
-      // the pooled layer's epilogue already left per-slot sums in d_partials_
-      const int32_t bslots = slot_begin_packed[slot_begin_pos[bi] + nchunks];
-      ProfBegin(kProfPoolFin, 0, static_cast<double>(bslots) * 2 * D * 4 + static_cast<double>(nchunks) * pooled * 4);
-      CVX_CUDA_CHECK(LaunchStatsPoolFinalizeFused(static_cast<const float*>(d_partials_), pool_buf.ld,
-                                                  static_cast<const int32_t*>(d_slot_begin_) + slot_begin_pos[bi],
-                                                  static_cast<const int32_t*>(d_slot_n_) + slot_pos[bi], nchunks, bslots, D, 1,
-                                                  plan_.pool_variance_floor,
-                                                  static_cast<float*>(d_stats_) + pending * pooled, pooled, compute_));
-      ProfEnd();
-    } else {
-      ProfBegin(kProfPool, 0, pooled_rows * D * ElemSize(elem_));
-      CVX_CUDA_CHECK(LaunchStatsPoolPartial(pool_buf.ptr, elem_, pool_buf.ld, dsl, nslabs,
-                                            static_cast<float*>(d_partials_), compute_));
-      ProfEnd();
-      ProfBegin(kProfPoolFin, 0, static_cast<double>(nslabs) * 2 * D * 4 + static_cast<double>(nchunks) * pooled * 4);
-      CVX_CUDA_CHECK(LaunchStatsPoolFinalize(static_cast<const float*>(d_partials_), pool_buf.ld, dsl,
-                                             static_cast<const int32_t*>(d_chunk_slab_off_) + slab_off_pos[bi], nchunks, D,
-                                             plan_.pool_output_stddevs ? 1 : 0, plan_.pool_variance_floor,
-                                             static_cast<float*>(d_stats_) + pending * pooled, pooled, compute_));
-      ProfEnd();
-    }
-
-    pending += nchunks;
-    const bool last_batch = bi + 1 == batches.size();
-    if (last_batch || pending + (batches[bi + 1].c1 - batches[bi + 1].c0) > seg_cap_chunks) {
-      const float* cur = static_cast<const float*>(d_stats_);
-      int32_t cur_ld = pooled;
-      float* emb = static_cast<float*>(d_chunk_emb_) + pending_c0 * E;
-      if (seg_ops_.empty())
-        CVX_CUDA_CHECK(cudaMemcpyAsync(emb, cur, static_cast<size_t>(pending) * E * 4, cudaMemcpyDeviceToDevice, compute_));
-      for (size_t si = 0; si < seg_ops_.size(); ++si) {
-        const SegOp& s = seg_ops_[si];
-        const bool last = si + 1 == seg_ops_.size();
-        float* dst = last ? emb : static_cast<float*>(d_seg_[si & 1]);
-        const int32_t dst_ld = s.out_dim;
-        ProfBegin(kProfSegment, 2.0 * pending * s.in_dim * s.out_dim, 0);
-        if (s.tensor) {
-          CVX_CUDA_CHECK(LaunchSplitF32(cur, cur_ld, pending, s.in_dim, d_seg_hi_, d_seg_lo_, s.kp, elem_, compute_));
-          TdnnGemmArgs a;
-          std::memset(&a, 0, sizeof(a));
-          Encode2D(&a.a_maps[0], elem_, d_seg_hi_, seg_split_rows_, s.kp, kGemmBlockK, kGemmBlockM);
-          Encode2D(&a.a_maps[1], elem_, d_seg_lo_, seg_split_rows_, s.kp, kGemmBlockK, kGemmBlockM);
-          a.a_maps[2] = a.a_maps[3] = a.a_maps[0];
-          a.b_box_rows = std::min(kGemmBlockN, s.n_pad);
-          a.b_box_rows_pair = std::min(kGemmBlockN / 2, s.n_pad);
-          Encode2D(&a.b_map, elem_, s.d_wcat, s.n_pad, 3 * s.kp, kGemmBlockK, a.b_box_rows);
-          Encode2D(&a.b_map_pair, elem_, s.d_wcat, s.n_pad, 3 * s.kp, kGemmBlockK, a.b_box_rows_pair);
-          // fp32 output; rows beyond `pending` and columns beyond out_dim are clipped by the map
-          Encode2D(&a.c_map, kF32, dst, pending, dst_ld, 32, 32, s.out_dim);
-          a.num_kb = static_cast<int32_t>(s.kb.size());
-          for (size_t i = 0; i < s.kb.size(); ++i) a.kb[i] = s.kb[i];
-          a.n_pad = s.n_pad;
-          a.n_mma = RoundUp(s.out_dim, 32);
-          a.tile_n = kGemmBlockN;
-          a.c_map_half = a.c_map;
-          a.num_m_tiles = static_cast<int32_t>((pending + kGemmBlockM - 1) / kGemmBlockM);
-          a.num_n_tiles = (a.n_mma + kGemmBlockN - 1) / kGemmBlockN;
-          a.post = s.d_post;
-          a.relu = s.relu ? 1 : 0;
-          a.ab_format = elem_ == kBF16 ? 1 : 0;
-          a.out_f32 = 1;
-          a.num_stages = 64;
-          CVX_CUDA_CHECK(LaunchTdnnGemmPair(a, num_sms_, compute_));
-        } else {
-          CVX_CUDA_CHECK(LaunchSegmentAffine(cur, cur_ld, pending, s.in_dim, s.d_w, s.d_b, s.relu ? 1 : 0, s.d_scale,
-                                             s.d_offset, s.out_dim, dst, dst_ld, compute_));
-        }
-        ProfEnd();
-        cur = dst;
-        cur_ld = dst_ld;
-      }
-      pending_c0 += pending;
-      pending = 0;
-    }
-  }
-  ProfBegin(kProfAverage, 0, static_cast<double>(num_chunks + num_utts) * E * 4);
-  CVX_CUDA_CHECK(LaunchUttAverage(static_cast<const float*>(d_chunk_emb_), E, static_cast<const int64_t*>(d_utt_off_),
-                                  static_cast<const float*>(d_weights_), num_utts,
-                                  dev_out && !chain_on_ ? out : static_cast<float*>(d_out_), compute_));
-  ProfEnd();
-  const void* result = d_out_;
-  if (chain_on_) {
-    // post-step on the device: the vectors leave as the back-end wants them
-    Grow(&d_chain_out_, &chain_out_cap_, static_cast<size_t>(num_utts) * chain_out_dim_ * 4);
-    float* dst = dev_out ? out : static_cast<float*>(d_chain_out_);
-    ProfBegin(kProfAverage, 0, static_cast<double>(num_utts) * (E + chain_out_dim_) * 4);
-    CVX_CUDA_CHECK(LaunchVectorChain(static_cast<const float*>(d_out_), num_utts, E, d_chain_mean_, d_chain_tf_,
-                                     chain_.transform_rows, chain_.transform_cols, chain_.normalize_length,
-                                     chain_.scaleup, /*keep_zero=*/1, dst, nullptr, compute_));
-    ProfEnd();
-    result = d_chain_out_;
-  }
-  if (!dev_out)
-    CVX_CUDA_CHECK(cudaMemcpyAsync(out, result, static_cast<size_t>(num_utts) * OutputDim() * 4, cudaMemcpyDeviceToHost, compute_));
-  CVX_CUDA_CHECK(cudaEventRecord(call_end_, compute_));
-  CVX_CUDA_CHECK(cudaStreamSynchronize(compute_));
-  CVX_CUDA_CHECK(cudaEventElapsedTime(&last_call_ms_, call_begin_, call_end_));
-  ProfResolve();
-  last_num_chunks_ = num_chunks;
-}
-
-// ---------------------------------------------------------- post-step ----
-void ValidateVectorChain(const cvx_vector_chain& c, int32_t dim) {
-  if (c.transform) {
-    if (c.transform_rows <= 0) throw InvalidArgument("vector chain: transform_rows <= 0");
-    if (c.transform_cols != dim && c.transform_cols != dim + 1)
-      throw InvalidArgument("vector chain: the transform has " + std::to_string(c.transform_cols) + " columns, the vectors have dim " +
-                            std::to_string(dim) + " (expected dim or dim + 1)");
-  }
-  if (static_cast<size_t>(dim + (c.transform ? c.transform_rows : dim)) * 4 > 200 * 1024)
-    throw InvalidArgument("vector chain: dimensions too large");
-}
-
-void Engine::SetVectorChain(const cvx_vector_chain* chain) {
-  CVX_CUDA_CHECK(cudaSetDevice(opts_.device));
-  CVX_CUDA_CHECK(cudaStreamSynchronize(compute_));
-  if (plan_.FrameOutput()) throw InvalidArgument("the vector chain applies to extraction engines only");
-  cudaFree(d_chain_mean_);
-  cudaFree(d_chain_tf_);
-  d_chain_mean_ = d_chain_tf_ = nullptr;
-  chain_on_ = false;
-  if (!chain) return;
-  const int32_t E = plan_.EmbeddingDim();
-  ValidateVectorChain(*chain, E);
-  chain_ = *chain;
-  if (chain->mean) {
-    d_chain_mean_ = DevAlloc<float>(E);
-    CVX_CUDA_CHECK(cudaMemcpy(d_chain_mean_, chain->mean, static_cast<size_t>(E) * 4, cudaMemcpyHostToDevice));
-  }
-  if (chain->transform) {
-    const size_t n = static_cast<size_t>(chain->transform_rows) * chain->transform_cols;
-    d_chain_tf_ = DevAlloc<float>(n);
-    CVX_CUDA_CHECK(cudaMemcpy(d_chain_tf_, chain->transform, n * 4, cudaMemcpyHostToDevice));
-  }
-  chain_.mean = chain_.transform = nullptr;  // host pointers are not kept
-  chain_out_dim_ = chain->transform ? chain->transform_rows : E;
-  chain_on_ = true;
-}
-
-void TransformVectors(int32_t device, const float* in, int64_t n, int32_t dim, const cvx_vector_chain& c, float* out,
-                      float* ratios) {
-  int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
-    throw CudaError("no usable CUDA device; this path has no CPU fallback");
-  if (device < 0 || device >= ndev) throw InvalidArgument("device ordinal out of range");
-  if (n < 0 || dim <= 0) throw InvalidArgument("bad vector count / dim");
-  if (n == 0) return;
-  ValidateVectorChain(c, dim);
-  CVX_CUDA_CHECK(cudaSetDevice(device));
-  const int32_t od = c.transform ? c.transform_rows : dim;
-  float *d_in = nullptr, *d_out = nullptr, *d_mean = nullptr, *d_tf = nullptr, *d_ratio = nullptr;
-  auto cleanup = [&] {
-    cudaFree(d_in);
-    cudaFree(d_out);
-    cudaFree(d_mean);
-    cudaFree(d_tf);
-    cudaFree(d_ratio);
-  };
-  try {
-    CVX_CUDA_CHECK(cudaMalloc(&d_in, static_cast<size_t>(n) * dim * 4));
-    CVX_CUDA_CHECK(cudaMalloc(&d_out, static_cast<size_t>(n) * od * 4));
-    CVX_CUDA_CHECK(cudaMemcpy(d_in, in, static_cast<size_t>(n) * dim * 4, cudaMemcpyHostToDevice));
-    if (c.mean) {
-      CVX_CUDA_CHECK(cudaMalloc(&d_mean, static_cast<size_t>(dim) * 4));
-      CVX_CUDA_CHECK(cudaMemcpy(d_mean, c.mean, static_cast<size_t>(dim) * 4, cudaMemcpyHostToDevice));
-    }
-    if (c.transform) {
-      const size_t sz = static_cast<size_t>(c.transform_rows) * c.transform_cols * 4;
-      CVX_CUDA_CHECK(cudaMalloc(&d_tf, sz));
-      CVX_CUDA_CHECK(cudaMemcpy(d_tf, c.transform, sz, cudaMemcpyHostToDevice));
-    }
-    if (ratios) CVX_CUDA_CHECK(cudaMalloc(&d_ratio, static_cast<size_t>(n) * 4));
-    CVX_CUDA_CHECK(LaunchVectorChain(d_in, n, dim, d_mean, d_tf, c.transform_rows, c.transform_cols, c.normalize_length,
-                                     c.scaleup, /*keep_zero=*/0, d_out, d_ratio, nullptr));
-    CVX_CUDA_CHECK(cudaMemcpy(out, d_out, static_cast<size_t>(n) * od * 4, cudaMemcpyDeviceToHost));
-    if (ratios) CVX_CUDA_CHECK(cudaMemcpy(ratios, d_ratio, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost));
-  } catch (...) {
-    cleanup();
-    throw;
-  }
-  cleanup();
-}
-
-namespace {
-// RAII for the few device buffers of the stand-alone entry points
-struct DevBuf {
-  void* p = nullptr;
-  ~DevBuf() { cudaFree(p); }
-  template <typename T>
-  T* Upload(const T* host, size_t n) {
-    CVX_CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
-    if (host && n) CVX_CUDA_CHECK(cudaMemcpy(p, host, n * sizeof(T), cudaMemcpyHostToDevice));
-    return static_cast<T*>(p);
-  }
-};
-}  // namespace
-
-void PldaScore(int32_t device, const cvx_plda& plda, const float* train, const int32_t* train_num_utts, int32_t num_train,
-               const float* test, int32_t num_test, const int32_t* trial_train, const int32_t* trial_test, int64_t num_trials,
-               float* scores) {
-  int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
-    throw CudaError("no usable CUDA device; this path has no CPU fallback");
-  if (device < 0 || device >= ndev) throw InvalidArgument("device ordinal out of range");
-  if (plda.dim_in <= 0 || plda.dim <= 0 || num_train < 0 || num_test < 0 || num_trials < 0) throw InvalidArgument("bad PLDA sizes");
-  if (num_trials == 0) return;
-  for (int64_t t = 0; t < num_trials; ++t)
-    if (trial_train[t] < 0 || trial_train[t] >= num_train || trial_test[t] < 0 || trial_test[t] >= num_test)
-      throw InvalidArgument("trial " + std::to_string(t) + " refers to a vector that does not exist");
-  for (int32_t i = 0; train_num_utts && i < num_train; ++i)
-    if (train_num_utts[i] <= 0) throw InvalidArgument("train_num_utts must be positive");
-  CVX_CUDA_CHECK(cudaSetDevice(device));
-  const size_t di = plda.dim_in, d = plda.dim;
-  DevBuf b_mean, b_tf, b_psi, b_train, b_test, b_n, b_ytrain, b_ytest, b_ti, b_tj, b_scores;
-  const double* d_mean = b_mean.Upload(plda.mean, di);
-  const double* d_tf = b_tf.Upload(plda.transform, d * di);
-  const double* d_psi = b_psi.Upload(plda.psi, d);
-  const float* d_train = b_train.Upload(train, static_cast<size_t>(num_train) * di);
-  const float* d_test = b_test.Upload(test, static_cast<size_t>(num_test) * di);
-  const int32_t* d_n = train_num_utts ? b_n.Upload(train_num_utts, static_cast<size_t>(num_train)) : nullptr;
-  double* d_ytrain = b_ytrain.Upload<double>(nullptr, static_cast<size_t>(num_train) * d);
-  double* d_ytest = b_ytest.Upload<double>(nullptr, static_cast<size_t>(num_test) * d);
-  const int32_t* d_ti = b_ti.Upload(trial_train, static_cast<size_t>(num_trials));
-  const int32_t* d_tj = b_tj.Upload(trial_test, static_cast<size_t>(num_trials));
-  float* d_scores = b_scores.Upload<float>(nullptr, static_cast<size_t>(num_trials));
-  CVX_CUDA_CHECK(LaunchPldaTransform(d_train, num_train, plda.dim_in, d_mean, d_tf, plda.dim, d_psi, d_n, plda.normalize_length,
-                                     plda.simple_length_norm, d_ytrain, nullptr));
-  CVX_CUDA_CHECK(LaunchPldaTransform(d_test, num_test, plda.dim_in, d_mean, d_tf, plda.dim, d_psi, nullptr, plda.normalize_length,
-                                     plda.simple_length_norm, d_ytest, nullptr));
-  CVX_CUDA_CHECK(LaunchPldaScore(d_ytrain, d_n, d_ytest, d_psi, plda.dim, d_ti, d_tj, num_trials, d_scores, nullptr));
-  CVX_CUDA_CHECK(cudaMemcpy(scores, d_scores, static_cast<size_t>(num_trials) * 4, cudaMemcpyDeviceToHost));
-}
-
-// -------------------------------------------------------- frame outputs ----
-// nnet3-compute's product: the output layer at every frame of every utterance.
-// Utterances are packed back to back with `left` + `right` replicated edge frames each, so every
-// real frame is an interior row of its padded utterance and one frame pass serves the whole batch.
-void Engine::ComputeFrames(const float* const* feats, int32_t num_streams, int64_t total_rows, const int64_t* utt_start,
-                           int32_t num_utts, float* out, uint32_t flags) {
-  CVX_CUDA_CHECK(cudaSetDevice(opts_.device));
-  if (!plan_.FrameOutput())
-    throw InvalidArgument("this engine was built from an extraction model; load it with cvx_model_load_frames");
-  if (num_streams != static_cast<int32_t>(plan_.input_dims.size()))
-    throw InvalidArgument("model has " + std::to_string(plan_.input_dims.size()) + " input stream(s), got " +
-                          std::to_string(num_streams));
-  if (num_utts < 0 || total_rows < 0) throw InvalidArgument("negative size");
-  if (num_utts == 0) return;
-  if (utt_start[0] < 0 || utt_start[num_utts] > total_rows) throw InvalidArgument("utt_start outside [0, total_rows]");
-  for (int32_t u = 0; u < num_utts; ++u)
-    if (utt_start[u + 1] <= utt_start[u]) throw InvalidArgument("utterance " + std::to_string(u) + " has no frames");
-  for (int32_t s = 0; s < num_streams; ++s)
-    if (!feats[s]) throw InvalidArgument("feats[" + std::to_string(s) + "] is NULL");
-  const bool dev_in = (flags & CVX_FLAG_DEVICE_INPUT) != 0, dev_out = (flags & CVX_FLAG_DEVICE_OUTPUT) != 0;
-  const Layer& OL = plan_.frame[plan_.frame_out];
-  const int32_t left = OL.left, right = OL.right, pad = left + right, E = OL.out_dim;
-  const int32_t ld32 = RoundUp(E, 4);
-  // batch = whole utterances; padded rows per batch bounded by max_batch_rows and by 4 GB of fp32 output
-  const int64_t cap = std::min<int64_t>(max_batch_rows_, std::max<int64_t>((int64_t{1} << 30) / ld32, kGemmBlockM));
-  struct FBatch {
-    int32_t u0, u1;
-    int64_t rows_c, rows_p;
-    size_t off_pos;  // position of its utt_start copy in `rel`
-  };
-  std::vector<FBatch> batches;
-  std::vector<int64_t> rel;  // per batch: utterance starts relative to the batch, n + 1 entries
-  int64_t max_c = 0, max_p = 0;
-  for (int32_t u0 = 0; u0 < num_utts;) {
-    int32_t u1 = u0;
-    int64_t rows_p = 0;
-    while (u1 < num_utts) {
-      const int64_t add = utt_start[u1 + 1] - utt_start[u1] + pad;
-      if (u1 > u0 && rows_p + add > cap) break;
-      rows_p += add;
-      ++u1;
-    }
-    FBatch fb{u0, u1, utt_start[u1] - utt_start[u0], rows_p, rel.size()};
-    for (int32_t u = u0; u <= u1; ++u) rel.push_back(utt_start[u] - utt_start[u0]);
-    max_c = std::max(max_c, fb.rows_c);
-    max_p = std::max(max_p, fb.rows_p);
-    batches.push_back(fb);
-    u0 = u1;
-  }
-  EnsureRows(max_p);
-  if (!d2h_) {
-    CVX_CUDA_CHECK(cudaStreamCreateWithFlags(&d2h_, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; ++i) {
-      CVX_CUDA_CHECK(cudaEventCreateWithFlags(&out_ready_[i], cudaEventDisableTiming));
-      CVX_CUDA_CHECK(cudaEventCreateWithFlags(&out_free_[i], cudaEventDisableTiming));
-    }
-  }
-  Grow(&d_utt_off_, &utt_off_cap_, rel.size() * 8);
-  CVX_CUDA_CHECK(cudaMemcpyAsync(d_utt_off_, rel.data(), rel.size() * 8, cudaMemcpyHostToDevice, compute_));
-  for (int32_t s = 0; s < num_streams; ++s) {
-    if (!dev_in)
-      for (int i = 0; i < 2; ++i) Grow(&d_feat_[i][s], &d_feat_cap_[i][s], static_cast<size_t>(max_c) * plan_.input_dims[s] * 4);
-    if (pad > 0) Grow(&d_sel_[s], &sel_cap_[s], static_cast<size_t>(max_p) * plan_.input_dims[s] * 4);
-  }
-  if (elem_ != kF32) Grow(&d_stats_, &stats_cap_, static_cast<size_t>(max_p) * ld32 * 4);
-  if (!dev_out)
-    for (int i = 0; i < 2; ++i) Grow(&d_frame_out_[i], &frame_out_cap_[i], static_cast<size_t>(max_c) * E * 4);
-  CVX_CUDA_CHECK(cudaStreamSynchronize(compute_));  // `rel` is pageable: its copy must have run
-
-  // Three streams: H2D of batch i+1 and D2H of batch i-1 overlap the frame pass of batch i.
-  CVX_CUDA_CHECK(cudaEventRecord(call_begin_, compute_));
-  for (size_t bi = 0; bi < batches.size(); ++bi) {
-    const FBatch& b = batches[bi];
-    const int slot = static_cast<int>(bi & 1);
-    const int32_t nu = b.u1 - b.u0;
-    const int64_t r0 = utt_start[b.u0];
-    const int64_t* d_rel = static_cast<const int64_t*>(d_utt_off_) + b.off_pos;
-    const float* dev[kMaxASources] = {};
-    if (!dev_in) {
-      if (bi >= 2) CVX_CUDA_CHECK(cudaStreamWaitEvent(copy_, feat_free_[slot], 0));
-      for (int32_t s = 0; s < num_streams; ++s) {
-        const int32_t dim = plan_.input_dims[s];
-        CVX_CUDA_CHECK(cudaMemcpyAsync(d_feat_[slot][s], feats[s] + r0 * dim, static_cast<size_t>(b.rows_c) * dim * 4,
-                                       cudaMemcpyHostToDevice, copy_));
-      }
-      CVX_CUDA_CHECK(cudaEventRecord(feat_ready_[slot], copy_));
-      CVX_CUDA_CHECK(cudaStreamWaitEvent(compute_, feat_ready_[slot], 0));
-    }
-    for (int32_t s = 0; s < num_streams; ++s) {
-      const int32_t dim = plan_.input_dims[s];
-      const float* src = dev_in ? feats[s] + r0 * dim : static_cast<const float*>(d_feat_[slot][s]);
-      if (pad > 0) {
-        ProfBegin(kProfStage, 0, static_cast<double>(b.rows_c + b.rows_p) * dim * 4.0);
-        CVX_CUDA_CHECK(LaunchPadEdges(src, dim, d_rel, nu, left, right, b.rows_p, static_cast<float*>(d_sel_[s]), compute_));
-        ProfEnd();
-        src = static_cast<const float*>(d_sel_[s]);
-      }
-      dev[s] = src;
-    }
-    // with padding the frame pass reads d_sel_, so the raw rows are free as soon as the pad kernels ran
-    if (!dev_in && pad > 0) CVX_CUDA_CHECK(cudaEventRecord(feat_free_[slot], compute_));
-    const float* act = nullptr;
-    int32_t act_ld = 0;
-    if (elem_ == kF32) {
-      RunFrames(dev, b.rows_p, 0, b.rows_p);
-      const Buffer& ob = buffers_[frame_ops_.back().out_buffer];
-      act = static_cast<const float*>(ob.ptr);
-      act_ld = ob.ld;
-    } else {
-      RunFrames(dev, b.rows_p, 0, b.rows_p, nullptr, static_cast<float*>(d_stats_), ld32);
-      act = static_cast<const float*>(d_stats_);
-      act_ld = ld32;
-    }
-    if (!dev_in && pad == 0) CVX_CUDA_CHECK(cudaEventRecord(feat_free_[slot], compute_));
-    float* dst = dev_out ? out + r0 * E : static_cast<float*>(d_frame_out_[slot]);
-    if (!dev_out && bi >= 2) CVX_CUDA_CHECK(cudaStreamWaitEvent(compute_, out_free_[slot], 0));
-    ProfBegin(kProfAverage, 0, static_cast<double>(b.rows_c) * E * 8.0);
-    CVX_CUDA_CHECK(LaunchFrameOutput(act, act_ld, E, d_rel, nu, left, right, b.rows_c, plan_.frame_log_softmax ? 1 : 0,
-                                     (flags & CVX_FLAG_APPLY_EXP) ? 1 : 0, dst, compute_));
-    ProfEnd();
-    if (!dev_out) {
-      CVX_CUDA_CHECK(cudaEventRecord(out_ready_[slot], compute_));
-      CVX_CUDA_CHECK(cudaStreamWaitEvent(d2h_, out_ready_[slot], 0));
-      CVX_CUDA_CHECK(cudaMemcpyAsync(out + r0 * E, d_frame_out_[slot], static_cast<size_t>(b.rows_c) * E * 4,
-                                     cudaMemcpyDeviceToHost, d2h_));
-      CVX_CUDA_CHECK(cudaEventRecord(out_free_[slot], d2h_));
-    }
-  }
-  if (!dev_out) {  // the call ends when the last results are on the host
-    CVX_CUDA_CHECK(cudaEventRecord(out_ready_[0], d2h_));
-    CVX_CUDA_CHECK(cudaStreamWaitEvent(compute_, out_ready_[0], 0));
-  }
-  CVX_CUDA_CHECK(cudaEventRecord(call_end_, compute_));
-  CVX_CUDA_CHECK(cudaStreamSynchronize(compute_));
-  CVX_CUDA_CHECK(cudaStreamSynchronize(copy_));
-  CVX_CUDA_CHECK(cudaStreamSynchronize(d2h_));
-  CVX_CUDA_CHECK(cudaEventElapsedTime(&last_call_ms_, call_begin_, call_end_));
-  ProfResolve();
-}
-
-// ------------------------------------------------------------ pre-step ----
-// Pre-step kernels of utterances [u0, u1) (raw rows already on the device): the selected /
-// normalised rows [kept0, kept0 + num_kept) of stream s.
-void Engine::RunPrestep(int32_t s, int32_t dim, const cvx_prestep& pre, int32_t u0, int32_t u1, int64_t run0, int64_t num_runs,
-                        int64_t kept0, int64_t num_kept, bool has_keep) {
-  const int32_t* d_keep = has_keep ? static_cast<const int32_t*>(d_pre_keep_) : nullptr;
-  const int64_t* aux = static_cast<const int64_t*>(d_pre_aux_);  // [n + 1] run starts, then [n + 1] kept starts
-  ProfBegin(kProfStage, 0, static_cast<double>(num_runs) * CmnRunFrames() * dim * 4.0 + static_cast<double>(num_kept) * dim * 4.0);
-  if (pre.cmn_window > 0)
-    CVX_CUDA_CHECK(LaunchCmnSliding(static_cast<const float*>(d_raw_[s]), dim, static_cast<const int64_t*>(d_pre_utt_start_), aux,
-                                    aux + pre_num_utts_ + 1, d_keep, u0, u1 - u0, run0, num_runs, pre.cmn_window,
-                                    pre.cmn_center, pre.min_cmn_window, static_cast<float*>(d_sel_[s]), compute_));
-  else
-    CVX_CUDA_CHECK(LaunchCmnSelect(static_cast<const float*>(d_raw_[s]), dim, static_cast<const int64_t*>(d_pre_utt_start_),
-                                   static_cast<const int32_t*>(d_pre_kept_utt_), d_keep, kept0, num_kept,
-                                   static_cast<float*>(d_sel_[s]), compute_));
-  ProfEnd();
-}
-
-// Uploads the per-call index arrays of the pre-step; returns the run offsets (host copy).
-std::vector<int64_t> Engine::UploadPrestepIndex(const int64_t* utt_raw_start, const int32_t* keep, const int64_t* utt_kept_start,
-                                                int32_t num_utts, const std::vector<int32_t>& kept_utt) {
-  const int64_t total_kept = utt_kept_start[num_utts];
-  const int32_t run = CmnRunFrames();
-  std::vector<int64_t> aux(2 * (static_cast<size_t>(num_utts) + 1));
-  aux[0] = 0;
-  for (int32_t u = 0; u < num_utts; ++u) aux[u + 1] = aux[u] + (utt_raw_start[u + 1] - utt_raw_start[u] + run - 1) / run;
-  for (int32_t u = 0; u <= num_utts; ++u) aux[num_utts + 1 + u] = utt_kept_start[u];
-  pre_num_utts_ = num_utts;
-  Grow(&d_pre_utt_start_, &pre_utt_start_cap_, static_cast<size_t>(num_utts + 1) * 8);
-  Grow(&d_pre_kept_utt_, &pre_kept_utt_cap_, std::max<size_t>(kept_utt.size(), 1) * 4);
-  Grow(&d_pre_aux_, &pre_aux_cap_, aux.size() * 8);
-  CVX_CUDA_CHECK(cudaMemcpyAsync(d_pre_utt_start_, utt_raw_start, static_cast<size_t>(num_utts + 1) * 8, cudaMemcpyHostToDevice, compute_));
-  CVX_CUDA_CHECK(cudaMemcpyAsync(d_pre_kept_utt_, kept_utt.data(), kept_utt.size() * 4, cudaMemcpyHostToDevice, compute_));
-  CVX_CUDA_CHECK(cudaMemcpyAsync(d_pre_aux_, aux.data(), aux.size() * 8, cudaMemcpyHostToDevice, compute_));
-  if (keep) {
-    Grow(&d_pre_keep_, &pre_keep_cap_, std::max<size_t>(static_cast<size_t>(total_kept), 1) * 4);
-    CVX_CUDA_CHECK(cudaMemcpyAsync(d_pre_keep_, keep, static_cast<size_t>(total_kept) * 4, cudaMemcpyHostToDevice, compute_));
-  }
-  CVX_CUDA_CHECK(cudaStreamSynchronize(compute_));  // the host vectors have been consumed
-  aux.resize(static_cast<size_t>(num_utts) + 1);
-  return aux;
-}
-
-static void CheckPrestepIndex(int64_t total_raw_rows, const int64_t* utt_raw_start, const int32_t* keep,
-                              const int64_t* utt_kept_start, int32_t num_utts, std::vector<int32_t>* kept_utt) {
-  if (num_utts < 0 || !utt_raw_start || !utt_kept_start) throw InvalidArgument("pre-step: NULL utterance offsets");
-  if (utt_raw_start[0] != 0 || utt_kept_start[0] != 0 || utt_raw_start[num_utts] != total_raw_rows)
-    throw InvalidArgument("pre-step: utterance offsets must start at 0 and end at the row count");
-  kept_utt->clear();
-  kept_utt->reserve(static_cast<size_t>(utt_kept_start[num_utts]));
-  for (int32_t u = 0; u < num_utts; ++u) {
-    const int64_t T = utt_raw_start[u + 1] - utt_raw_start[u], K = utt_kept_start[u + 1] - utt_kept_start[u];
-    if (T < 0 || K < 0 || K > T || T > INT32_MAX) throw InvalidArgument("pre-step: bad offsets for utterance " + std::to_string(u));
-    if (!keep && K != T) throw InvalidArgument("pre-step: keep == NULL requires kept == raw row counts");
-    int32_t prev = -1;
-    for (int64_t j = utt_kept_start[u]; j < utt_kept_start[u + 1]; ++j) {
-      if (keep) {
-        if (keep[j] <= prev || keep[j] >= T) throw InvalidArgument("pre-step: keep[] must be increasing frame indices inside the utterance");
-        prev = keep[j];
-      }
-      kept_utt->push_back(u);
-    }
-  }
-}
-
-void Engine::ExtractRaw(const float* const* raw, const cvx_prestep* pre, int32_t num_streams, int64_t total_raw_rows,
-                        const int64_t* utt_raw_start, const int32_t* keep, const int64_t* utt_kept_start, int32_t num_utts,
-                        const int64_t* chunk_start, const int32_t* chunk_len, const int32_t* chunk_utt,
-                        const float* chunk_weight, int64_t num_chunks, float* out, uint32_t flags) {
-  CVX_CUDA_CHECK(cudaSetDevice(opts_.device));
-  if (flags & CVX_FLAG_DEVICE_INPUT) throw InvalidArgument("cvx_extract_raw takes host features");
-  if (num_streams != static_cast<int32_t>(plan_.input_dims.size())) throw InvalidArgument("wrong number of input streams");
-  if (!raw || !pre) throw InvalidArgument("pre-step: NULL argument");
-  std::vector<int32_t> kept_utt;
-  CheckPrestepIndex(total_raw_rows, utt_raw_start, keep, utt_kept_start, num_utts, &kept_utt);
-  const int64_t total_kept = utt_kept_start[num_utts];
-  const std::vector<int64_t> run_start = UploadPrestepIndex(utt_raw_start, keep, utt_kept_start, num_utts, kept_utt);
-  // all Grow()s first: they synchronise and may free buffers earlier kernels of this call read
-  for (int32_t s = 0; s < num_streams; ++s) {
-    if (plan_.input_dims[s] > 128 && pre[s].cmn_window > 0) throw InvalidArgument("sliding CMN supports feature dims up to 128");
-    Grow(&d_raw_[s], &raw_cap_[s], static_cast<size_t>(total_raw_rows) * plan_.input_dims[s] * 4);
-    Grow(&d_sel_[s], &sel_cap_[s], static_cast<size_t>(std::max<int64_t>(total_kept, 1)) * plan_.input_dims[s] * 4);
-  }
-  const float* sel[kMaxASources] = {};
-  for (int32_t s = 0; s < num_streams; ++s) {
-    if (!raw[s]) throw InvalidArgument("pre-step: NULL feature stream");
-    if (pre[s].norm_vars) throw InvalidArgument("sliding CMN with --norm-vars=true is not on this path (the recipes use false)");
-    if (pre[s].cmn_window < 0) throw InvalidArgument("negative cmn_window");
-    sel[s] = static_cast<const float*>(d_sel_[s]);
-  }
-
-  // Pieces of whole utterances (>= kPieceRows raw rows each): all raw copies are queued on the copy
-  // stream now; the pre-step kernels of a piece are queued on the compute stream right before the
-  // first device batch that reads its rows, so the copy of piece p+1 overlaps the GEMMs of piece p.
-  struct Piece {
-    int32_t u0, u1;
-  };
-  constexpr int64_t kPieceRows = 1 << 18;
-  std::vector<Piece> pieces;
-  for (int32_t u = 0; u < num_utts;) {
-    int32_t v = u;
-    while (v < num_utts && utt_raw_start[v] - utt_raw_start[u] < kPieceRows) ++v;
-    pieces.push_back({u, v});
-    u = v;
-  }
-  while (piece_events_.size() < pieces.size()) {
-    cudaEvent_t ev;
-    CVX_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    piece_events_.push_back(ev);
-  }
-  for (size_t p = 0; p < pieces.size(); ++p) {
-    const int64_t r0 = utt_raw_start[pieces[p].u0], r1 = utt_raw_start[pieces[p].u1];
-    for (int32_t s = 0; s < num_streams; ++s) {
-      const int32_t dim = plan_.input_dims[s];
-      CVX_CUDA_CHECK(cudaMemcpyAsync(static_cast<float*>(d_raw_[s]) + r0 * dim, raw[s] + r0 * dim,
-                                     static_cast<size_t>(r1 - r0) * dim * 4, cudaMemcpyHostToDevice, copy_));
-    }
-    CVX_CUDA_CHECK(cudaEventRecord(piece_events_[p], copy_));
-  }
-  size_t next_piece = 0;
-  before_batch_ = [&](int64_t row_end) {
-    while (next_piece < pieces.size() && utt_kept_start[pieces[next_piece].u0] < row_end) {
-      const Piece& pc = pieces[next_piece];
-      CVX_CUDA_CHECK(cudaStreamWaitEvent(compute_, piece_events_[next_piece], 0));
-      const int64_t k0 = utt_kept_start[pc.u0], k1 = utt_kept_start[pc.u1];
-      for (int32_t s = 0; s < num_streams; ++s)
-        RunPrestep(s, plan_.input_dims[s], pre[s], pc.u0, pc.u1, run_start[pc.u0], run_start[pc.u1] - run_start[pc.u0], k0,
-                   k1 - k0, keep != nullptr);
-      ++next_piece;
-    }
-  };
-  try {
-    Extract(sel, num_streams, total_kept, chunk_start, chunk_len, chunk_utt, chunk_weight, num_chunks, num_utts, out,
-            flags | CVX_FLAG_DEVICE_INPUT);
-  } catch (...) {
-    before_batch_ = nullptr;
-    cudaStreamSynchronize(copy_);
-    throw;
-  }
-  before_batch_ = nullptr;
-  CVX_CUDA_CHECK(cudaStreamSynchronize(copy_));  // pieces no batch needed (utterances without chunks)
-}
-
-void Engine::DebugPrestep(const float* raw, int32_t dim, const cvx_prestep& pre, int64_t total_raw_rows,
-                          const int64_t* utt_raw_start, const int32_t* keep, const int64_t* utt_kept_start,
-                          int32_t num_utts, float* out) {
-  CVX_CUDA_CHECK(cudaSetDevice(opts_.device));
-  std::vector<int32_t> kept_utt;
-  CheckPrestepIndex(total_raw_rows, utt_raw_start, keep, utt_kept_start, num_utts, &kept_utt);
-  const int64_t total_kept = utt_kept_start[num_utts];
-  const std::vector<int64_t> run_start = UploadPrestepIndex(utt_raw_start, keep, utt_kept_start, num_utts, kept_utt);
-  if (dim > 128 && pre.cmn_window > 0) throw InvalidArgument("sliding CMN supports feature dims up to 128");
-  Grow(&d_raw_[0], &raw_cap_[0], static_cast<size_t>(total_raw_rows) * dim * 4);
-  Grow(&d_sel_[0], &sel_cap_[0], static_cast<size_t>(std::max<int64_t>(total_kept, 1)) * dim * 4);
-  if (pre.norm_vars) throw InvalidArgument("sliding CMN with --norm-vars=true is not on this path (the recipes use false)");
-  if (pre.cmn_window < 0) throw InvalidArgument("negative cmn_window");
-  CVX_CUDA_CHECK(cudaMemcpyAsync(d_raw_[0], raw, static_cast<size_t>(total_raw_rows) * dim * 4, cudaMemcpyHostToDevice, compute_));
-  RunPrestep(0, dim, pre, 0, num_utts, 0, run_start[num_utts], 0, total_kept, keep != nullptr);
-  CVX_CUDA_CHECK(cudaMemcpyAsync(out, d_sel_[0], static_cast<size_t>(total_kept) * dim * 4, cudaMemcpyDeviceToHost, compute_));
-  CVX_CUDA_CHECK(cudaStreamSynchronize(compute_));
-  ProfResolve();
-}
-
-void Engine::LastChunkEmbeddings(float* out, int64_t num_chunks) {
-  CVX_CUDA_CHECK(cudaSetDevice(opts_.device));
-  if (num_chunks != last_num_chunks_) throw InvalidArgument("num_chunks does not match the last cvx_extract call");
-  CVX_CUDA_CHECK(cudaMemcpy(out, d_chunk_emb_, static_cast<size_t>(num_chunks) * plan_.EmbeddingDim() * 4,
-                            cudaMemcpyDeviceToHost));
-}
-
-// ------------------------------------------------------------ test hook ----
-void TestStatsPool(int32_t device, int32_t precision, const float* in, int64_t rows, int32_t dim, const int64_t* begin,
-                   const int64_t* end, int64_t num_chunks, float variance_floor, float* out) {
-  CVX_CUDA_CHECK(cudaSetDevice(device));
-  const int32_t elem = precision == CVX_PRECISION_FP16 ? kF16 : precision == CVX_PRECISION_BF16 ? kBF16 : kF32;
-  const int32_t ld = RoundUp(dim, 64);
-  std::vector<float> padded(static_cast<size_t>(rows) * ld, 0.f);
-  for (int64_t r = 0; r < rows; ++r) std::memcpy(&padded[r * ld], in + r * dim, static_cast<size_t>(dim) * 4);
-  std::vector<uint8_t> conv(padded.size() * ElemSize(elem));
-  ConvertToElem(padded.data(), padded.size(), elem, conv.data());
-  std::vector<PoolSlab> slabs;
-  std::vector<int32_t> off(num_chunks + 1, 0);
-  for (int64_t c = 0; c < num_chunks; ++c) {
-    if (begin[c] < 0 || end[c] > rows || end[c] <= begin[c]) throw InvalidArgument("bad pooling range");
-    off[c] = static_cast<int32_t>(slabs.size());
-    for (int64_t r = begin[c]; r < end[c]; r += kPoolSlabRows)
-      slabs.push_back({r, static_cast<int32_t>(std::min<int64_t>(kPoolSlabRows, end[c] - r)), static_cast<int32_t>(c)});
-  }
-  off[num_chunks] = static_cast<int32_t>(slabs.size());
-  void *d_act = nullptr, *d_slabs = nullptr, *d_off = nullptr, *d_part = nullptr, *d_stats = nullptr;
-  CVX_CUDA_CHECK(cudaMalloc(&d_act, std::max<size_t>(conv.size(), 16)));
-  CVX_CUDA_CHECK(cudaMalloc(&d_slabs, std::max<size_t>(slabs.size(), 1) * sizeof(PoolSlab)));
-  CVX_CUDA_CHECK(cudaMalloc(&d_off, off.size() * 4));
-  CVX_CUDA_CHECK(cudaMalloc(&d_part, std::max<size_t>(slabs.size(), 1) * 2 * ld * 4));
-  CVX_CUDA_CHECK(cudaMalloc(&d_stats, std::max<size_t>(num_chunks, 1) * 2 * dim * 4));
-  CVX_CUDA_CHECK(cudaMemcpy(d_act, conv.data(), conv.size(), cudaMemcpyHostToDevice));
-  CVX_CUDA_CHECK(cudaMemcpy(d_slabs, slabs.data(), slabs.size() * sizeof(PoolSlab), cudaMemcpyHostToDevice));
-  CVX_CUDA_CHECK(cudaMemcpy(d_off, off.data(), off.size() * 4, cudaMemcpyHostToDevice));
-  CVX_CUDA_CHECK(LaunchStatsPoolPartial(d_act, elem, ld, static_cast<PoolSlab*>(d_slabs), static_cast<int32_t>(slabs.size()),
-                                        static_cast<float*>(d_part), nullptr));
-  CVX_CUDA_CHECK(LaunchStatsPoolFinalize(static_cast<float*>(d_part), ld, static_cast<PoolSlab*>(d_slabs),
-                                         static_cast<int32_t*>(d_off), static_cast<int32_t>(num_chunks), dim, 1,
-                                         variance_floor, static_cast<float*>(d_stats), 2 * dim, nullptr));
-  CVX_CUDA_CHECK(cudaMemcpy(out, d_stats, static_cast<size_t>(num_chunks) * 2 * dim * 4, cudaMemcpyDeviceToHost));
-  cudaFree(d_act);
-  cudaFree(d_slabs);
-  cudaFree(d_off);
-  cudaFree(d_part);
-  cudaFree(d_stats);
-}
 
 }  // namespace cvx

@@ -206,6 +206,13 @@ class Engine {
   int64_t launches_ = 0;
 };
 
+template <typename T>
+T* Engine::DevAlloc(size_t n) {
+  void* p = nullptr;
+  CVX_CUDA_CHECK(cudaMalloc(&p, (n > 0 ? n : 1) * sizeof(T)));
+  return static_cast<T*>(p);
+}
+
 // Stand-alone post-step on host vectors (cvx_transform_vectors).
 void TransformVectors(int32_t device, const float* in, int64_t num_vectors, int32_t dim, const cvx_vector_chain& chain,
                       float* out, float* ratios);

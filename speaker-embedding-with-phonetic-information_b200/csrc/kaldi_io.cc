@@ -422,6 +422,61 @@ void ReadVectorOrMatrix(Input& in, bool binary, Matrix* m, bool* was_vector) {
   throw KaldiError("unknown matrix/vector tag '" + tag + "' in " + in.Name());
 }
 
+void ReadVectorOrMatrixDouble(Input& in, bool binary, int32_t* rows, int32_t* cols, std::vector<double>* data,
+                              bool* was_vector) {
+  data->clear();
+  if (!binary) {
+    // text "[ ... ]": rows end at '\n' (or at ']'); parsed in double
+    in.SkipSpace();
+    if (in.Get() != '[') throw KaldiError("expected '[' in " + in.Name());
+    int32_t r = 0, c = 0, cur = 0;
+    std::string tok;
+    while (true) {
+      int ch = in.Get();
+      if (ch < 0) throw KaldiError("unterminated text matrix in " + in.Name());
+      if (std::isspace(ch) || ch == ']') {
+        if (!tok.empty()) {
+          char* e = nullptr;
+          double v = std::strtod(tok.c_str(), &e);
+          if (*e) throw KaldiError("bad number '" + tok + "' in " + in.Name());
+          data->push_back(v);
+          tok.clear();
+          ++cur;
+        }
+        if ((ch == '\n' || ch == ']') && cur > 0) {
+          if (r == 0) c = cur;
+          if (cur != c) throw KaldiError("ragged text matrix in " + in.Name());
+          ++r;
+          cur = 0;
+        }
+        if (ch == ']') break;
+      } else {
+        tok.push_back(static_cast<char>(ch));
+      }
+    }
+    *rows = r;
+    *cols = c;
+    if (was_vector) *was_vector = r <= 1;
+    return;
+  }
+  const std::string tag = in.ReadToken();
+  const bool vec = tag == "FV" || tag == "DV";
+  if (!vec && tag != "FM" && tag != "DM") throw KaldiError("unknown matrix/vector tag '" + tag + "' in " + in.Name());
+  *rows = vec ? 1 : ReadInt32(in, true);
+  *cols = ReadInt32(in, true);
+  if (*rows < 0 || *cols < 0) throw KaldiError("negative size in " + in.Name());
+  const size_t n = static_cast<size_t>(*rows) * *cols;
+  data->resize(n);
+  if (tag[0] == 'D') {
+    in.Read(data->data(), n * 8);
+  } else {
+    std::vector<float> f(n);
+    in.Read(f.data(), n * 4);
+    for (size_t i = 0; i < n; ++i) (*data)[i] = f[i];
+  }
+  if (was_vector) *was_vector = vec;
+}
+
 void ReadMatrix(Input& in, bool binary, Matrix* m) {
   bool was_vector = false;
   ReadVectorOrMatrix(in, binary, m, &was_vector);
@@ -548,8 +603,9 @@ static TableSpec ParseSpec(const std::string& spec, bool is_write) {
 TableSpec ParseRspecifier(const std::string& s) { return ParseSpec(s, false); }
 TableSpec ParseWspecifier(const std::string& s) { return ParseSpec(s, true); }
 
-SequentialMatrixReader::SequentialMatrixReader(const std::string& rspecifier, bool allow_vectors)
-    : spec_(ParseRspecifier(rspecifier)), allow_vectors_(allow_vectors) {
+SequentialMatrixReader::SequentialMatrixReader(const std::string& rspecifier, bool allow_vectors,
+                                               std::function<bool(const std::string&)> keep)
+    : keep_(std::move(keep)), spec_(ParseRspecifier(rspecifier)), allow_vectors_(allow_vectors) {
   if (spec_.is_ark) ark_.Open(spec_.ark_name);
   else scp_.Open(spec_.scp_name);
   Advance();
@@ -558,14 +614,21 @@ SequentialMatrixReader::SequentialMatrixReader(const std::string& rspecifier, bo
 void SequentialMatrixReader::Advance() {
   have_ = false;
   if (spec_.is_ark) {
-    ark_.SkipSpace();
-    if (ark_.Eof()) { done_ = true; return; }
-    key_ = ark_.ReadToken();
-    bool binary = ReadBinaryHeader(ark_);
-    if (allow_vectors_) ReadVectorOrMatrix(ark_, binary, &value_, nullptr);
-    else ReadMatrix(ark_, binary, &value_);
-    have_ = true;
-    return;
+    while (true) {
+      ark_.SkipSpace();
+      if (ark_.Eof()) { done_ = true; return; }
+      key_ = ark_.ReadToken();
+      bool binary = ReadBinaryHeader(ark_);
+      const bool keep = !keep_ || keep_(key_);
+      auto placer = value_.placer;
+      if (!keep) value_.placer = nullptr;  // a skipped entry must not land in the caller's buffer
+      if (allow_vectors_) ReadVectorOrMatrix(ark_, binary, &value_, nullptr);
+      else ReadMatrix(ark_, binary, &value_);
+      value_.placer = placer;
+      if (!keep) continue;
+      have_ = true;
+      return;
+    }
   }
   while (true) {
     if (scp_.Eof()) { done_ = true; return; }
@@ -574,6 +637,7 @@ void SequentialMatrixReader::Advance() {
     size_t sp = line.find_first_of(" \t");
     if (sp == std::string::npos) throw KaldiError("bad scp line: " + line);
     key_ = line.substr(0, sp);
+    if (keep_ && !keep_(key_)) continue;
     std::string rx = Trim(line.substr(sp + 1));
     if (!rx.empty() && rx.back() == ']') throw KaldiError("scp range specifiers are not supported: " + line);
     Input in(rx);
@@ -583,6 +647,20 @@ void SequentialMatrixReader::Advance() {
     have_ = true;
     return;
   }
+}
+
+std::vector<std::pair<std::string, std::string>> SequentialMatrixReader::ReadScpList(const std::string& scp_rxfilename) {
+  std::vector<std::pair<std::string, std::string>> out;
+  Input in(scp_rxfilename);
+  while (!in.Eof()) {
+    std::string line = Trim(in.ReadLine());
+    if (line.empty()) continue;
+    size_t sp = line.find_first_of(" \t");
+    if (sp == std::string::npos) throw KaldiError("bad scp line: " + line);
+    out.emplace_back(line.substr(0, sp), Trim(line.substr(sp + 1)));
+  }
+  in.Close();
+  return out;
 }
 
 bool SequentialMatrixReader::Done() { return done_ && !have_; }

@@ -130,6 +130,12 @@ void ReadVector(Input& in, bool binary, std::vector<float>* v);
 // Reads FV/DV/FM/DM/[..] without knowing which; vectors come back as 1 x n.
 void ReadVectorOrMatrix(Input& in, bool binary, Matrix* m, bool* was_vector);
 
+// Double-preserving read of a vector (1 x n) or matrix: DV/DM stay doubles, FV/FM and text are
+// widened (text is parsed with strtod).  What Kaldi's Vector<double>/Matrix<double>::Read does for
+// objects stored in double precision, e.g. <Plda>.
+void ReadVectorOrMatrixDouble(Input& in, bool binary, int32_t* rows, int32_t* cols, std::vector<double>* data,
+                              bool* was_vector);
+
 void WriteToken(Output& out, const std::string& tok);
 void WriteVector(Output& out, bool binary, const float* v, int32_t n);
 void WriteMatrix(Output& out, bool binary, const Matrix& m);
@@ -149,16 +155,23 @@ TableSpec ParseWspecifier(const std::string& wspecifier);
 class SequentialMatrixReader {
  public:
   // allow_vectors: entries may be Kaldi vectors (returned as 1 x n), e.g. a vad.scp table
-  explicit SequentialMatrixReader(const std::string& rspecifier, bool allow_vectors = false);
+  explicit SequentialMatrixReader(const std::string& rspecifier, bool allow_vectors = false,
+                                  std::function<bool(const std::string&)> keep = nullptr);
   bool Done();            // true when no more entries
   const std::string& Key() const { return key_; }
   Matrix& Value() { return value_; }
   void Next();
   // Exit status problems of the feeding pipe are reported at Close().
   int Close();
+  // (`keep` of the constructor: entries whose key it rejects are skipped -- scp lines without opening
+  // their file, archive entries after reading them.)
+  // scp only: (key, rxfilename) of every line, without reading any entry
+  static std::vector<std::pair<std::string, std::string>> ReadScpList(const std::string& scp_rxfilename);
+  const TableSpec& Spec() const { return spec_; }
 
  private:
   void Advance();
+  std::function<bool(const std::string&)> keep_;
   TableSpec spec_;
   Input ark_;                 // for ark
   Input scp_;                 // for scp: the list itself

@@ -10,6 +10,7 @@ test / bench input is produced here with fixed seeds.  Layer stacks are copied
   v4  AM           egs/sre/v4/local/nnet3_cvector/cvector/train_am.sh:30-38
   v4  c-vector     egs/sre/v4/local/nnet3_cvector/cvector/train_xvector_with_am.sh:44-57
   v5  c-vector     egs/sre/v5/local/nnet3_cvector/cvector/train_cvector_with_am.sh:65-89
+  v5  "expand"     egs/sre/v5/sid/nnet3_cvector/cvector/train_cvector_with_am_expand.sh:73-96
 
 and turned into nnet3 node/component lines the way
 egs/sre/v5/steps/libs/nnet3/xconfig/basic_layers.py:758-834 and
@@ -239,7 +240,8 @@ def _am_stack(b: _Builder, prefix: str = "tdnn", suffix: str = "", inp: str = "i
 
 
 TOPOLOGIES = ("v2_xvector", "v3_multitask", "v3_multitask_2share", "v3_multitask_3share",
-              "v3_multitask_4share", "v4_cvector", "v4_two_input", "v4_pa_wo_pretrain", "v5_cvector")
+              "v3_multitask_4share", "v4_cvector", "v4_two_input", "v4_pa_wo_pretrain", "v5_cvector",
+              "v5_expand")
 
 #: node that extract_xvectors_new.sh redirects `output` to, per topology
 EMBEDDING_NODE = {
@@ -252,6 +254,7 @@ EMBEDDING_NODE = {
     "v4_two_input": "tdnn6_xvec.affine",
     "v4_pa_wo_pretrain": "tdnn6.affine",          # v4/run_sre10_pa_wo_pretrain.sh:199-201
     "v5_cvector": "tdnn6_xvec.affine",            # v5/run_sre10.sh:83
+    "v5_expand": "tdnn6_xvec.affine",
 }
 
 #: frame-level multiply-accumulates per input frame of the extracted sub-graph
@@ -260,6 +263,8 @@ MAC_PER_FRAME = {
     "v3_multitask_3share": 2_661_888, "v3_multitask_4share": 2_661_888,
     "v4_cvector": 6_980_738, "v4_pa_wo_pretrain": 6_980_738, "v5_cvector": 6_980_738,
     "v4_two_input": 7_035_988,
+    # AM stack 4 126 850 + tdnn1_share 755*512 + tdnn2_share/tdnn3_xvec 2*1536*512 + tdnn4/5_xvec 2*512*512
+    "v5_expand": 6_610_562,
 }
 SEGMENT_MAC_PER_CHUNK = 3000 * 512
 
@@ -355,6 +360,26 @@ def make_model(topology: str, seed: int = 42, feat_dim: int = 23, am_feat_dim: i
         b.relu_batchnorm_layer("tdnn3_xvec", H, "Append(tdnn2_xvec@-3,tdnn2_xvec@0,tdnn2_xvec@3)")
         b.relu_batchnorm_layer("tdnn4_xvec", H, "tdnn3_xvec")
         b.relu_batchnorm_layer("tdnn5_xvec", S, f"Append(tdnn4_xvec,{am_node})")
+        b.stats_layer("stats_xvec", 0, max_chunk, "tdnn5_xvec")
+        b.relu_batchnorm_layer("tdnn6_xvec", H)
+        b.relu_batchnorm_layer("tdnn7_xvec", H, "tdnn6_xvec")
+        b.output_layer("output", num_speakers, "tdnn7_xvec")
+    elif topology == "v5_expand":
+        # train_cvector_with_am_expand.sh:73-96: the phonetic bottleneck is spliced into the FIRST
+        # speaker layer, tap by tap, next to the raw features; the pooled layer is 512 wide
+        b.input("input", feat_dim)
+        am_node = _am_stack(b, **am)
+        b.relu_batchnorm_layer("tdnn1_share", H, "Append(" + ",".join(
+            f"input@{k},{am_node}@{k}" for k in (-2, -1, 0, 1, 2)) + ")")
+        b.relu_batchnorm_layer("tdnn2_share", H, "Append(tdnn1_share@-2,tdnn1_share@0,tdnn1_share@2)")
+        last = "tdnn2_share"
+        for i, sp in ((3, "Append({p}@-3,{p}@0,{p}@3)"), (4, "{p}"), (5, "{p}"), (6, "{p}"), (7, "{p}")):
+            b.relu_batchnorm_layer(f"tdnn{i}_am", H, sp.format(p=last))
+            last = f"tdnn{i}_am"
+        b.output_layer("output_am", num_senones, "tdnn7_am")
+        b.relu_batchnorm_layer("tdnn3_xvec", H, "Append(tdnn2_share@-3,tdnn2_share@0,tdnn2_share@3)")
+        b.relu_batchnorm_layer("tdnn4_xvec", H, "tdnn3_xvec")
+        b.relu_batchnorm_layer("tdnn5_xvec", H, "tdnn4_xvec")
         b.stats_layer("stats_xvec", 0, max_chunk, "tdnn5_xvec")
         b.relu_batchnorm_layer("tdnn6_xvec", H)
         b.relu_batchnorm_layer("tdnn7_xvec", H, "tdnn6_xvec")

@@ -86,9 +86,10 @@ def test_cpp_loader_reads_python_written_models(cvx, synth, model_dir, binary):
         path, _ = model_dir(topology, binary)
         mod = cvx.Model(path, synth.EMBEDDING_NODE[topology])
         assert mod.info.mac_per_frame == synth.MAC_PER_FRAME[topology]
-        assert mod.info.mac_per_chunk == synth.SEGMENT_MAC_PER_CHUNK
-        assert mod.info.embedding_dim == 512 and mod.info.pooled_dim == 3000
-        want_ctx = (7, 7) if topology.startswith(("v2", "v3")) else (13, 7)
+        assert mod.info.mac_per_chunk == (1024 * 512 if topology == "v5_expand" else synth.SEGMENT_MAC_PER_CHUNK)
+        assert mod.info.embedding_dim == 512 and mod.info.pooled_dim == (1024 if topology == "v5_expand" else 3000)
+        # "expand": the bottleneck (left 13, right 7) is spliced {-2..2} into tdnn1_share, then {-2,0,2}, {-3,0,3}
+        want_ctx = (7, 7) if topology.startswith(("v2", "v3")) else (20, 14) if topology == "v5_expand" else (13, 7)
         assert (mod.info.left_context, mod.info.right_context) == want_ctx
         assert mod.input_names == (["input", "input_am"] if topology == "v4_two_input" else ["input"])
         assert mod.input_dims == ([23, 40] if topology == "v4_two_input" else [23])

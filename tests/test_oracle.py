@@ -80,7 +80,8 @@ def test_fp32_mode_agrees_with_fp64(synth, topology):
     assert r < 1e-5 and c > 0.9999999
 
 
-@pytest.mark.parametrize("topology", ["v2_xvector", "v3_multitask", "v4_cvector", "v4_two_input", "v5_cvector"])
+@pytest.mark.parametrize("topology", ["v2_xvector", "v3_multitask", "v3_multitask_2share", "v3_multitask_4share",
+                                      "v4_cvector", "v4_two_input", "v5_cvector", "v5_expand"])
 def test_second_route_agrees(synth, topology):
     """conv1d / batch_norm / var route vs splice+matmul route, both fp64."""
     m = synth.make_model(topology)
@@ -94,7 +95,7 @@ def test_second_route_agrees(synth, topology):
 
 
 @pytest.mark.parametrize("topology,ctx", [("v2_xvector", (7, 7)), ("v3_multitask_3share", (7, 7)),
-                                          ("v4_cvector", (13, 7)), ("v5_cvector", (13, 7))])
+                                          ("v4_cvector", (13, 7)), ("v5_cvector", (13, 7)), ("v5_expand", (20, 14))])
 def test_context_and_valid_frame_count(synth, topology, ctx):
     m = synth.make_model(topology, hidden=32, stats_dim=40, am_hidden=24, am_bottleneck=8)
     o = Oracle(m, synth.EMBEDDING_NODE[topology], np.float64)
