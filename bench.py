@@ -312,7 +312,9 @@ def main() -> None:
         assert lib.cvx_memcpy_h2d(local_rank, dp, pa.array.ctypes.data_as(C.c_void_p), nb) == 0
         dptrs.append(dp.value)
         nbytes += nb
-    out = np.zeros((n_utts, info.embedding_dim), np.float32)
+    out_pinned = cvx.PinnedArray((n_utts, info.embedding_dim))     # results come back with an asynchronous copy
+    out = out_pinned.array
+    out[:] = 0
 
     def step_device():
         ex.extract_chunks(dptrs, total_rows, wl.starts, wl.lens, wl.utts, None, n_utts, out=out, flags=cvx.FLAG_DEVICE_INPUT)
@@ -398,7 +400,9 @@ def main() -> None:
             g = torch.Generator(device="cuda").manual_seed(w2.seed)
             dev = [torch.randn((w2.total_rows, d), generator=g, device="cuda", dtype=torch.float32) for d in w2.model.input_dims]
             ex2 = cvx.Extractor(w2.model, device=local_rank, precision=args.precision, profile=True)
-            o2 = np.zeros((w2.n_utts, w2.model.info.embedding_dim), np.float32)
+            o2_pinned = cvx.PinnedArray((w2.n_utts, w2.model.info.embedding_dim))
+            o2 = o2_pinned.array
+            o2[:] = 0
             ms = []
             for i in range(3 + 3):
                 if i == 3:
@@ -414,7 +418,8 @@ def main() -> None:
                           "topology": w2.topology, "frames": w2.total_rows, "utts": w2.n_utts,
                           "outputs_finite": bool(np.isfinite(o2).all() and np.abs(o2).sum() > 0)}
             ex2.close()
-            del dev
+            del dev, o2
+            o2_pinned.close()
             w2.model.close()
             w2.cleanup()
             torch.cuda.empty_cache()

@@ -142,7 +142,9 @@ typedef struct cvx_engine_options {
   int32_t precision;       /* CVX_PRECISION_* */
   int64_t max_batch_rows;  /* rows (frames) per packed ragged batch; 0 = default */
   int32_t profile;         /* 1: record per-kernel CUDA-event times (cvx_engine_get_profile) */
-  int32_t reserved[7];     /* zero */
+  int32_t reserved[7];     /* zero.  reserved[0]: debug kernel selection (tests); reserved[1] != 0: range check mode
+                            * for fp16 operands -- every layer's output is stored and inspected for values clipped
+                            * at +-65504 (cvx_engine_saturation_counts); slower, for validating a new model */
 } cvx_engine_options;
 
 void cvx_engine_options_default(cvx_engine_options* opts);
@@ -304,6 +306,11 @@ typedef struct cvx_kernel_profile {
 
 int cvx_engine_get_profile(cvx_engine* engine, cvx_kernel_profile* records, int32_t max_records,
                            int32_t* num_records);
+/* Range check mode (options.reserved[1]): counts[0] = staged input values, counts[1 + l] = outputs of frame
+ * layer l that were clipped at the fp16 range limit since the engine was created.  The conversions
+ * saturate (cvt.rn.satfinite), so without this check a model whose activations exceed 65504 -- un-normalised
+ * features, a missing BatchNorm -- would be clipped silently.  *num_counts = 0 when the mode is off. */
+int cvx_engine_saturation_counts(cvx_engine* engine, int64_t* counts, int32_t max_counts, int32_t* num_counts);
 void cvx_engine_reset_profile(cvx_engine* engine);
 /* Kernels launched by this engine since creation (all classes). */
 int64_t cvx_engine_launch_count(const cvx_engine* engine);

@@ -87,7 +87,7 @@ ABI_SYMBOLS = [
     "cvx_test_prestep", "cvx_host_alloc", "cvx_host_free", "cvx_device_alloc",
     "cvx_device_free", "cvx_memcpy_h2d", "cvx_device_count", "cvx_engine_get_profile",
     "cvx_engine_reset_profile", "cvx_engine_launch_count", "cvx_engine_last_extract_ms", "cvx_test_tdnn_layer", "cvx_test_tdnn_layer_bench", "cvx_test_stats_pool",
-    "cvx_acquire_device", "cvx_test_acquire_lock", "cvx_lpt_shards",
+    "cvx_acquire_device", "cvx_test_acquire_lock", "cvx_lpt_shards", "cvx_engine_saturation_counts",
 ]
 
 _lib = None
@@ -145,6 +145,7 @@ def load_library() -> C.CDLL:
     lib.cvx_device_count.argtypes = [C.POINTER(C.c_int32)]
     lib.cvx_engine_get_profile.argtypes = [C.c_void_p, C.POINTER(KernelProfile), C.c_int32, C.POINTER(C.c_int32)]
     lib.cvx_engine_reset_profile.argtypes = [C.c_void_p]
+    lib.cvx_engine_saturation_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]
     lib.cvx_engine_launch_count.argtypes = [C.c_void_p]
     lib.cvx_engine_launch_count.restype = C.c_int64
     lib.cvx_engine_last_extract_ms.argtypes = [C.c_void_p]
@@ -264,12 +265,13 @@ class Extractor:
     """One GPU engine (cvx_engine) for one model."""
 
     def __init__(self, model: Model, device: int = 0, precision: str = "fp16", max_batch_rows: int = 0,
-                 profile: bool = False):
+                 profile: bool = False, check_saturation: bool = False):
         self._lib = load_library()
         self.model = model
         o = EngineOptions()
         self._lib.cvx_engine_options_default(C.byref(o))
         o.device, o.precision, o.max_batch_rows, o.profile = device, PRECISION[precision], max_batch_rows, int(profile)
+        o.reserved[1] = int(check_saturation)
         h = C.c_void_p()
         _check(self._lib.cvx_engine_create(model._h, C.byref(o), C.byref(h)))
         self._h = h
@@ -406,6 +408,13 @@ class Extractor:
         _check(self._lib.cvx_engine_get_profile(self._h, recs, 64, C.byref(n)))
         return [dict(name=recs[i].name.decode(), launches=recs[i].launches, total_ms=recs[i].total_ms,
                      flops=recs[i].flops, bytes=recs[i].bytes) for i in range(n.value)]
+
+    def saturation_counts(self) -> List[int]:
+        """check_saturation=True engines: [staged inputs, frame layer 0, 1, ...] values clipped at the fp16 limit."""
+        buf = (C.c_int64 * 64)()
+        n = C.c_int32(0)
+        _check(self._lib.cvx_engine_saturation_counts(self._h, buf, 64, C.byref(n)))
+        return [int(buf[i]) for i in range(n.value)]
 
     def reset_profile(self) -> None:
         self._lib.cvx_engine_reset_profile(self._h)

@@ -223,7 +223,7 @@ int ExtractMain(int argc, const char* const* argv, bool multiple_input) {
     int32_t chunk_size = -1, min_chunk_size = 100, gpu_id = -1, cmn_window = 0, min_cmn_window = 100, num_gpus = 1;
     bool cmn_center = true, cmn_norm_vars = false;
     int64_t batch_rows = 1 << 20, max_batch_rows = 0;
-    bool pad_input = false, profile = false;
+    bool pad_input = false, profile = false, check_saturation = false;
     // accepted for command-line compatibility with nnet3 programs; no effect here
     int32_t ign_i[4] = {0, 0, 0, 0};
     float ign_f = 1.0f;
@@ -258,6 +258,9 @@ int ExtractMain(int argc, const char* const* argv, bool multiple_input) {
     po.Register("batch-rows", &batch_rows, "Frames read from the feature pipe(s) per cvx_extract call");
     po.Register("max-batch-rows", &max_batch_rows, "Frames per packed device batch (0 = engine default)");
     po.Register("profile", &profile, "Print per-kernel CUDA-event times at the end");
+    po.Register("check-saturation", &check_saturation,
+                "Validation mode for a new model (fp16 operands): store every layer and report activations that were clipped "
+                "at the fp16 range limit; slower (no fused pooling)");
     po.Register("vad-rspecifier", &vad_rspecifier,
                 "If set, the features are RAW: keep only frames whose VAD value is non-zero (what piping through "
                 "select-voiced-frames does), on the GPU");
@@ -363,9 +366,13 @@ int ExtractMain(int argc, const char* const* argv, bool multiple_input) {
     eo.precision = prec;
     eo.max_batch_rows = max_batch_rows;
     eo.profile = profile ? 1 : 0;
+    eo.reserved[1] = check_saturation ? 1 : 0;
     int32_t ndev = 0;
     if (cvx_device_count(&ndev) != CVX_OK) throw KaldiError(std::string("no usable CUDA device: ") + cvx_last_error());
-    if (gpu_id + num_gpus > ndev)
+    // test aid: CVX_WRAP_DEVICES=1 lets --num-gpus exceed the visible devices (engine g runs on device
+    // (gpu-id + g) mod ndev), so the multi-engine / multi-lane paths can be exercised on a one-GPU box
+    const bool wrap_devices = std::getenv("CVX_WRAP_DEVICES") != nullptr && ndev > 0;
+    if (gpu_id + num_gpus > ndev && !wrap_devices)
       throw KaldiError("--gpu-id=" + std::to_string(gpu_id) + " --num-gpus=" + std::to_string(num_gpus) + " but only " +
                        std::to_string(ndev) + " CUDA device(s) are visible");
 
@@ -400,7 +407,7 @@ int ExtractMain(int argc, const char* const* argv, bool multiple_input) {
       for (int g = 0; g < num_gpus; ++g)
         th.emplace_back([&, g] {
           cvx_engine_options o = eo;
-          o.device = gpu_id + g;
+          o.device = wrap_devices ? (gpu_id + g) % ndev : gpu_id + g;
           if (cvx_engine_create(model, &o, &engines[g]) != CVX_OK) errs[g] = cvx_last_error();
         });
       for (std::thread& t : th) t.join();
@@ -759,6 +766,32 @@ int ExtractMain(int argc, const char* const* argv, bool multiple_input) {
                               << " ms=" << recs[i].total_ms
                               << (recs[i].flops > 0 ? " TFLOP/s=" + std::to_string(recs[i].flops / recs[i].total_ms * 1e-9) : "")
                               << (recs[i].bytes > 0 ? " GB/s=" + std::to_string(recs[i].bytes / recs[i].total_ms * 1e-6) : ""));
+    }
+    if (check_saturation) {
+      // names of the inspected buffers: the staged inputs, then the frame layers in plan order
+      std::vector<std::string> names{"the staged input features"};
+      std::istringstream desc(cvx_model_describe(model));
+      for (std::string ln; std::getline(desc, ln);)
+        if (ln.rfind("frame[", 0) == 0) {
+          std::istringstream w(ln);
+          std::string idx, name;
+          w >> idx >> name;
+          names.push_back("layer " + name);
+        }
+      int64_t total = 0;
+      for (int g = 0; g < num_gpus; ++g) {
+        int64_t counts[80];
+        int32_t n = 0;
+        if (cvx_engine_saturation_counts(engines[g], counts, 80, &n) != CVX_OK) continue;
+        for (int32_t i = 0; i < n; ++i) {
+          if (counts[i] == 0) continue;
+          total += counts[i];
+          CVX_WARN(counts[i] << " values of " << (static_cast<size_t>(i) < names.size() ? names[i] : std::string("buffer ") + std::to_string(i))
+                             << " were clipped at the fp16 range limit (+-65504); the embeddings are not reliable -- use --precision=bf16 "
+                                "(fp32 exponent range) or --precision=fp32 for this model");
+        }
+      }
+      if (total == 0) CVX_LOG("range check: no activation reached the fp16 range limit");
     }
     for (cvx_engine* e : engines) cvx_engine_destroy(e);
     cvx_model_free(model);

@@ -289,6 +289,13 @@ int cvx_engine_get_profile(cvx_engine* engine, cvx_kernel_profile* records, int3
   *num_records = engine->impl->GetProfile(records, max_records);
   return CVX_OK;
 }
+int cvx_engine_saturation_counts(cvx_engine* engine, int64_t* counts, int32_t max_counts, int32_t* num_counts) {
+  return Guard([&] {
+    if (!engine || !counts || !num_counts) throw cvx::InvalidArgument("cvx_engine_saturation_counts: NULL argument");
+    *num_counts = engine->impl->SaturationCounts(counts, max_counts);
+  });
+}
+
 void cvx_engine_reset_profile(cvx_engine* engine) {
   if (engine) engine->impl->ResetProfile();
 }

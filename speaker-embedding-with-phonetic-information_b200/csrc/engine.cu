@@ -144,6 +144,7 @@ void Engine::Build() {
     if (env[0] == '1') debug_ |= kDebugSingleCtaGemm;  // A/B aid: same results, 1-CTA tiles
   }
   profile_ = opts.profile != 0;
+  check_sat_ = opts.reserved[1] != 0 && elem_ == kF16;
   max_batch_rows_ = opts.max_batch_rows > 0 ? opts.max_batch_rows : (int64_t{1} << 19);
   max_batch_rows_ = (max_batch_rows_ + kGemmBlockM - 1) / kGemmBlockM * kGemmBlockM;
 
@@ -306,6 +307,29 @@ void Engine::Build() {
   if (!plan_.FrameOutput())
     for (const Tap& t : plan_.frame[plan_.pool_src].taps) fused_pool_ = fused_pool_ && t.offset == 0;
   if (const char* env = std::getenv("CVX_FUSED_POOL")) fused_pool_ = fused_pool_ && env[0] != '0';
+  if (check_sat_) {
+    fused_pool_ = false;  // every layer's output must exist in memory to be inspected
+    d_sat_ = DevAlloc<unsigned long long>(1 + plan_.frame.size());
+    CVX_CUDA_CHECK(cudaMemset(d_sat_, 0, (1 + plan_.frame.size()) * sizeof(unsigned long long)));
+    sat_counts_.assign(1 + plan_.frame.size(), 0);
+  }
+}
+
+void Engine::CollectSaturation() {
+  if (!check_sat_) return;
+  std::vector<unsigned long long> h(sat_counts_.size());
+  CVX_CUDA_CHECK(cudaMemcpy(h.data(), d_sat_, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < h.size(); ++i) sat_counts_[i] = static_cast<int64_t>(h[i]);
+}
+
+int Engine::SaturationCounts(int64_t* counts, int32_t max_counts) {
+  if (!check_sat_) return 0;
+  CVX_CUDA_CHECK(cudaSetDevice(opts_.device));
+  CVX_CUDA_CHECK(cudaStreamSynchronize(compute_));
+  CollectSaturation();
+  const int n = std::min<int>(max_counts, static_cast<int>(sat_counts_.size()));
+  for (int i = 0; i < n; ++i) counts[i] = sat_counts_[i];
+  return n;
 }
 
 Engine::~Engine() { Release(); }
@@ -318,6 +342,7 @@ void Engine::Release() noexcept {
   cudaFree(d_chain_mean_);
   cudaFree(d_chain_tf_);
   cudaFree(d_chain_out_);
+  cudaFree(d_sat_);
   cudaFree(d_frame_out_[0]);
   cudaFree(d_frame_out_[1]);
   if (d2h_) {
@@ -665,6 +690,7 @@ void Engine::RunFrames(const float* const* dev_feats, int64_t rows, int64_t src_
     ProfBegin(kProfStage, 0, static_cast<double>(rows) * (buffers_[s.buffer].dim * 4.0 + a.ld_out * ElemSize(elem_)));
     CVX_CUDA_CHECK(LaunchStageInput(a, compute_));
     ProfEnd();
+    if (check_sat_) CVX_CUDA_CHECK(LaunchCountSaturated(a.out, rows, a.ld_out, buffers_[s.buffer].dim, d_sat_, compute_));
   }
   for (FrameOp& op : frame_ops_) {
     const Layer& L = plan_.frame[op.layer];
@@ -716,6 +742,9 @@ void Engine::RunFrames(const float* const* dev_feats, int64_t rows, int64_t src_
       }
     }
     ProfEnd();
+    if (check_sat_ && !(f32_out && &op == &frame_ops_.back()))
+      CVX_CUDA_CHECK(LaunchCountSaturated(buffers_[op.out_buffer].ptr, rows, buffers_[op.out_buffer].ld, L.out_dim,
+                                          d_sat_ + 1 + op.layer, compute_));
   }
 }
 

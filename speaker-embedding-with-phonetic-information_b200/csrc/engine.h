@@ -73,6 +73,9 @@ class Engine {
   void SetVectorChain(const cvx_vector_chain* chain);
   int32_t OutputDim() const { return chain_on_ ? chain_out_dim_ : plan_.EmbeddingDim(); }
 
+  // check mode (opts.reserved[1]): values clipped at the fp16 range limit since the engine was built, for
+  // the staged inputs (index 0) and every frame layer's output (index 1 + layer); names[] optional
+  int SaturationCounts(int64_t* counts, int32_t max_counts);
   int GetProfile(cvx_kernel_profile* recs, int32_t max_recs);
   void ResetProfile();
   int64_t launch_count() const { return launches_; }
@@ -196,6 +199,10 @@ class Engine {
   void* d_chain_out_ = nullptr;
   size_t chain_out_cap_ = 0;
 
+  bool check_sat_ = false;
+  unsigned long long* d_sat_ = nullptr;  // [1 + frame layers]
+  std::vector<int64_t> sat_counts_;
+  void CollectSaturation();               // after a synchronised call: device counters -> sat_counts_
   bool profile_ = false;
   std::vector<PendingEvent> pending_;
   std::vector<cudaEvent_t> event_pool_;

@@ -204,6 +204,54 @@ void Engine::Extract(const float* const* feats, int32_t num_streams, int64_t tot
   // the pageable host vectors above must stay alive until these copies ran
   CVX_CUDA_CHECK(cudaStreamSynchronize(compute_));
 
+  // Results leave flush by flush: once the segment layers ran on a group of chunks, the utterances
+  // whose chunks are all done are averaged (+ post-step) and copied out on their own stream while the
+  // next batches compute -- with 10^5 short segments per call the embeddings are hundreds of MB.
+  // Needs a destination an asynchronous copy can write: device memory or pinned host memory (a copy
+  // into pageable memory would stall the enqueueing thread); otherwise everything is delivered at the end.
+  bool stream_out = dev_out;
+  if (!dev_out) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, out) == cudaSuccess) stream_out = attr.type == cudaMemoryTypeHost;
+    else cudaGetLastError();
+  }
+  if (!d2h_) {
+    CVX_CUDA_CHECK(cudaStreamCreateWithFlags(&d2h_, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      CVX_CUDA_CHECK(cudaEventCreateWithFlags(&out_ready_[i], cudaEventDisableTiming));
+      CVX_CUDA_CHECK(cudaEventCreateWithFlags(&out_free_[i], cudaEventDisableTiming));
+    }
+  }
+  if (chain_on_) Grow(&d_chain_out_, &chain_out_cap_, static_cast<size_t>(num_utts) * chain_out_dim_ * 4);
+  const int32_t OD = OutputDim();
+  int32_t utt_done = 0;
+  // average (+ post-step) utterances [u0, u1) on the compute stream, then hand them to the caller
+  auto deliver = [&](int32_t u0, int32_t u1) {
+    if (u1 <= u0) return;
+    const int32_t n = u1 - u0;
+    float* avg_dst = (dev_out && !chain_on_) ? out + static_cast<size_t>(u0) * E : static_cast<float*>(d_out_) + static_cast<size_t>(u0) * E;
+    ProfBegin(kProfAverage, 0, static_cast<double>(n) * E * 4 * 2);
+    CVX_CUDA_CHECK(LaunchUttAverage(static_cast<const float*>(d_chunk_emb_), E, static_cast<const int64_t*>(d_utt_off_) + u0,
+                                    static_cast<const float*>(d_weights_), n, avg_dst, compute_));
+    ProfEnd();
+    const float* result = avg_dst;
+    if (chain_on_) {
+      // post-step on the device: the vectors leave as the back-end wants them
+      float* dst = dev_out ? out + static_cast<size_t>(u0) * OD : static_cast<float*>(d_chain_out_) + static_cast<size_t>(u0) * OD;
+      ProfBegin(kProfAverage, 0, static_cast<double>(n) * (E + OD) * 4);
+      CVX_CUDA_CHECK(LaunchVectorChain(avg_dst, n, E, d_chain_mean_, d_chain_tf_, chain_.transform_rows, chain_.transform_cols,
+                                       chain_.normalize_length, chain_.scaleup, /*keep_zero=*/1, dst, nullptr, compute_));
+      ProfEnd();
+      result = dst;
+    }
+    if (!dev_out) {
+      CVX_CUDA_CHECK(cudaEventRecord(out_ready_[0], compute_));
+      CVX_CUDA_CHECK(cudaStreamWaitEvent(d2h_, out_ready_[0], 0));
+      CVX_CUDA_CHECK(cudaMemcpyAsync(out + static_cast<size_t>(u0) * OD, result, static_cast<size_t>(n) * OD * 4,
+                                     cudaMemcpyDeviceToHost, d2h_));
+    }
+  };
+
   // ---- batches ----
   CVX_CUDA_CHECK(cudaEventRecord(call_begin_, compute_));
   int64_t pending = 0, pending_c0 = 0;  // chunks whose statistics wait for the segment layers
@@ -326,27 +374,19 @@ void Engine::Extract(const float* const* feats, int32_t num_streams, int64_t tot
       }
       pending_c0 += pending;
       pending = 0;
+      if (stream_out && !last_batch) {
+        int32_t u1 = utt_done;
+        while (u1 < num_utts && utt_off[u1 + 1] <= pending_c0) ++u1;
+        deliver(utt_done, u1);
+        utt_done = u1;
+      }
     }
   }
-  ProfBegin(kProfAverage, 0, static_cast<double>(num_chunks + num_utts) * E * 4);
-  CVX_CUDA_CHECK(LaunchUttAverage(static_cast<const float*>(d_chunk_emb_), E, static_cast<const int64_t*>(d_utt_off_),
-                                  static_cast<const float*>(d_weights_), num_utts,
-                                  dev_out && !chain_on_ ? out : static_cast<float*>(d_out_), compute_));
-  ProfEnd();
-  const void* result = d_out_;
-  if (chain_on_) {
-    // post-step on the device: the vectors leave as the back-end wants them
-    Grow(&d_chain_out_, &chain_out_cap_, static_cast<size_t>(num_utts) * chain_out_dim_ * 4);
-    float* dst = dev_out ? out : static_cast<float*>(d_chain_out_);
-    ProfBegin(kProfAverage, 0, static_cast<double>(num_utts) * (E + chain_out_dim_) * 4);
-    CVX_CUDA_CHECK(LaunchVectorChain(static_cast<const float*>(d_out_), num_utts, E, d_chain_mean_, d_chain_tf_,
-                                     chain_.transform_rows, chain_.transform_cols, chain_.normalize_length,
-                                     chain_.scaleup, /*keep_zero=*/1, dst, nullptr, compute_));
-    ProfEnd();
-    result = d_chain_out_;
+  deliver(utt_done, num_utts);
+  if (!dev_out) {  // the caller's buffer is complete when the call returns; the copy tail is inside the timed bracket
+    CVX_CUDA_CHECK(cudaEventRecord(out_free_[0], d2h_));
+    CVX_CUDA_CHECK(cudaStreamWaitEvent(compute_, out_free_[0], 0));
   }
-  if (!dev_out)
-    CVX_CUDA_CHECK(cudaMemcpyAsync(out, result, static_cast<size_t>(num_utts) * OutputDim() * 4, cudaMemcpyDeviceToHost, compute_));
   CVX_CUDA_CHECK(cudaEventRecord(call_end_, compute_));
   CVX_CUDA_CHECK(cudaStreamSynchronize(compute_));
   CVX_CUDA_CHECK(cudaEventElapsedTime(&last_call_ms_, call_begin_, call_end_));

@@ -146,6 +146,10 @@ struct StageArgs {
 };
 cudaError_t LaunchStageInput(const StageArgs& args, cudaStream_t stream);
 
+// counts the fp16 values of buf [rows, dim] (row pitch ld) that sit at the range limit (saturation.cu)
+cudaError_t LaunchCountSaturated(const void* buf, int64_t rows, int32_t ld, int32_t dim, unsigned long long* counter,
+                                 cudaStream_t stream);
+
 // ---- K2: ragged mean + stddev pooling -------------------------------------
 struct PoolSlab {
   int64_t row_begin;  // first row (in the activation buffer) of this slab

@@ -38,9 +38,19 @@ constexpr int kNumBars = 2 * kStages + 5;
 constexpr int kSmemTmemPtr = kSmemBars + kNumBars * 8;  // 231552
 constexpr int kSmemTotal = kSmemTmemPtr + 32;           // 231584 <= 232448
 constexpr int kTmemCols = 512;
-constexpr int kThreads = 320;
-constexpr int kEpilogueThreads = 256;
-constexpr int kEpilogueWarps = 8;
+// Epilogue warps: 8 (two per TMEM lane quarter, 64-column chunks) for the storing variants.  The
+// fused-pooling epilogue is latency-bound (tcgen05.ld -> convert -> smem transpose -> dependent
+// FHADD/FHFMA chains; ncu r2: ~5 600 cycles per 128 x 256 tile with two warps per scheduler, issue
+// slots 40 % used), so it runs 16 warps (four per quarter) on 32-column units with half the
+// per-warp staging buffer each.
+template <bool kPool>
+struct PairCfg {
+  static constexpr int kEpiWarps = kPool ? 16 : 8;
+  static constexpr int kEpiThreads = 32 * kEpiWarps;
+  static constexpr int kThreads = 64 + kEpiThreads;
+  static constexpr int kParts = kEpiWarps / 4;       // warps sharing one TMEM lane quarter
+  static constexpr int kWarpBuf = 8 * kCWarpBytes / kEpiWarps;  // bytes of smem_c per warp
+};
 
 template <bool kBF16>
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
@@ -71,8 +81,11 @@ __device__ __forceinline__ void accum16(uint16_t x, float& sx, float& sxx) {
 // group (PoolGroupMeta) into per-slot partials through a swizzled smem transpose; the
 // [rows, 1500] activation is never written.
 template <bool kBF16, bool kOutF32, bool kPool>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairCfg<kPool>::kThreads, 1)
     tdnn_gemm_pair_kernel(const __grid_constant__ TdnnGemmArgs args) {
+  using Cfg = PairCfg<kPool>;
+  constexpr int kEpilogueThreads = Cfg::kEpiThreads;
+  constexpr int kEpilogueWarps = Cfg::kEpiWarps;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* smem_a = smem + kSmemA;
   uint8_t* smem_b = smem + kSmemB;
@@ -209,11 +222,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   } else {
     // ---------------------------------------------------------- epilogue --
     const int q = warp & 3;            // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;  // which of the quarter's two warps: takes chunks c % 2 == half
+    const int half = (warp - 2) >> 2;  // which of the quarter's warps: takes chunks / units c % kParts == half
     const int et = threadIdx.x - 64;
-    uint8_t* buf = smem_c + (warp - 2) * kCWarpBytes;
+    uint8_t* buf = smem_c + (warp - 2) * Cfg::kWarpBuf;
     int it = 0;
-    static_assert(kEpilogueThreads == kGemmBlockN, "one parameter column per epilogue thread");
+    static_assert(kEpilogueThreads >= kGemmBlockN, "one parameter column per epilogue thread");
     int staged_n0 = -1, pre_n0 = -1;
     float2 pre = make_float2(0.f, 0.f);
     for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
@@ -229,15 +242,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       // from registers loaded during the previous tile (the L2 latency is off the critical path).
       if (n0 != staged_n0) {
         asm volatile("bar.sync 1, %0;" ::"n"(kEpilogueThreads) : "memory");  // previous tile's params no longer read
-        const float2 p = (pre_n0 == n0) ? pre : epi::load_post(args.post, n0 + et, args.n_pad);
-        epi::store_post<kBF16, kOutF32>(smem + kSmemPost, et, p);
+        if (et < kGemmBlockN) {
+          const float2 p = (pre_n0 == n0) ? pre : epi::load_post(args.post, n0 + et, args.n_pad);
+          epi::store_post<kBF16, kOutF32>(smem + kSmemPost, et, p);
+        }
         asm volatile("bar.sync 1, %0;" ::"n"(kEpilogueThreads) : "memory");
         staged_n0 = n0;
       }
       if (tile + tile_step < num_tiles) {
         const int nn0 = ((tile + tile_step) % num_n_tiles) * args.tile_n;
         if (nn0 != n0) {
-          pre = epi::load_post(args.post, nn0 + et, args.n_pad);
+          if (et < kGemmBlockN) pre = epi::load_post(args.post, nn0 + et, args.n_pad);
           pre_n0 = nn0;
         }
       }
@@ -246,84 +261,69 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       ptx::tcgen05_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kGemmBlockN;
 
-      PoolGroupMeta meta{};
-      if constexpr (kPool) meta = args.pool_meta[(m0 + q * 32) >> 5];
-      for (int c = half; c < n_chunks; c += 2) {
-        if constexpr (kPool) {
-          const bool has_a = meta.a1 > meta.a0, has_b = meta.b1 > meta.b0;
-          if (!has_a && !has_b) break;  // no valid row in this 32-row group (edge / gap rows)
-          const bool half_chunk = (n_cols - c * 64) < 64;
-          // both 32-column halves of the chunk: loaded, rounded to the operand type (the values a
-          // consumer would read) and transposed together, so that each lane then sums TWO columns
-          // (one per half) with independent dependency chains.
-          uint32_t r0[32], r1[32];
-          ptx::tmem_ld_32x32b_x32(t_row + c * 64, r0);
-          if (!half_chunk) ptx::tmem_ld_32x32b_x32(t_row + c * 64 + 32, r1);
-          ptx::tmem_ld_wait();
-          uint32_t pk0[16], pk1[16];
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            uint32_t p4[4];
-            epi::pack8<kBF16>(&r0[j], smem + kSmemPost, c * 64 + j, args.relu != 0, p4);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) pk0[(j >> 1) + e] = p4[e];
-            if (!half_chunk) {
-              epi::pack8<kBF16>(&r1[j], smem + kSmemPost, c * 64 + 32 + j, args.relu != 0, p4);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) pk1[(j >> 1) + e] = p4[e];
-            }
-          }
-          // transpose through this warp's (otherwise unused) staging buffer as 16-bit values, one
-          // 2 KB tile per half: lane = row writes its 16 words, word index ^ (row >> 1); then lane =
-          // column reads one 16-bit value per row and accumulates it with the mixed-precision
-          // FHADD / FHFMA (fp32 += fp16, no unpacking).  Both phases are bank-conflict free.
+      if constexpr (kPool) {
+        // 32-column units: this warp's 32 rows x 32 columns are loaded, rounded to the operand type (the
+        // values a consumer would read), transposed through the warp's 2 KB buffer as 16-bit values
+        // (lane = row writes its 16 words at word index ^ (row >> 1); lane = column then reads one
+        // 16-bit value per row: both phases bank-conflict free) and summed with the mixed-precision
+        // FHADD / FHFMA (fp32 += fp16, no unpacking), even and odd rows in separate chains.
+        const PoolGroupMeta meta = args.pool_meta[(m0 + q * 32) >> 5];
+        const bool has_a = meta.a1 > meta.a0, has_b = meta.b1 > meta.b0;
+        const int n_units = n_cols >> 5;
+        if (has_a || has_b) {  // else: no valid row in this 32-row group (edge / gap rows)
           uint32_t* tile = reinterpret_cast<uint32_t*>(buf);
-          __syncwarp();
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            tile[lane * 16 + (j ^ (lane >> 1))] = pk0[j];
-            if (!half_chunk) tile[512 + lane * 16 + (j ^ (lane >> 1))] = pk1[j];
-          }
-          __syncwarp();
           const uint32_t lp = static_cast<uint32_t>(lane) << 1;  // byte offset of column `lane` in an un-swizzled row
-          auto row_value = [&](int h, int r) -> uint16_t {
-            return *reinterpret_cast<const uint16_t*>(buf + h * 2048 + r * 64 + (lp ^ (static_cast<uint32_t>(r >> 1) << 2)));
+          auto row_value = [&](int r) -> uint16_t {
+            return *reinterpret_cast<const uint16_t*>(buf + r * 64 + (lp ^ (static_cast<uint32_t>(r >> 1) << 2)));
           };
-#pragma unroll 1
-          for (int seg = 0; seg < 2; ++seg) {
-            const int lo = seg ? meta.b0 : meta.a0, hi = seg ? meta.b1 : meta.a1;
-            if (hi <= lo) continue;
-            float sx0 = 0.f, sxx0 = 0.f, sx1 = 0.f, sxx1 = 0.f;  // column `lane` of half 0 / half 1
-            if (lo == 0 && hi == 32 && !half_chunk) {  // interior group: every row is valid
+          for (int u = half; u < n_units; u += Cfg::kParts) {
+            uint32_t r[32];
+            ptx::tmem_ld_32x32b_x32(t_row + u * 32, r);
+            ptx::tmem_ld_wait();
+            uint32_t pk[16];
 #pragma unroll
-              for (int r = 0; r < 32; ++r) {
-                accum16<kBF16>(row_value(0, r), sx0, sxx0);
-                accum16<kBF16>(row_value(1, r), sx1, sxx1);
-              }
-            } else {
-#pragma unroll 2
-              for (int r = lo; r < hi; ++r) {
-                accum16<kBF16>(row_value(0, r), sx0, sxx0);
-                if (!half_chunk) accum16<kBF16>(row_value(1, r), sx1, sxx1);
-              }
+            for (int j = 0; j < 32; j += 8) {
+              uint32_t p4[4];
+              epi::pack8<kBF16>(&r[j], smem + kSmemPost, u * 32 + j, args.relu != 0, p4);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) pk[(j >> 1) + e] = p4[e];
             }
-            const int slot = meta.slot + ((seg && has_a) ? 1 : 0);
-            // blocked layout [column block of 64][slot][sum | sum of squares][64] (the tile column base is a
-            // multiple of 32, so a half's 32 columns stay inside one block)
-            const int col = n0 + c * 64;
-            float* out = args.pool_partials +
-                         ((static_cast<int64_t>(col >> 6) * args.pool_slots + slot) * 2) * 64 + (col & 63) + lane;
-            out[0] = sx0;
-            out[64] = sxx0;
-            if (!half_chunk) {
-              float* out1 = args.pool_partials +
-                            ((static_cast<int64_t>((col + 32) >> 6) * args.pool_slots + slot) * 2) * 64 + ((col + 32) & 63) + lane;
-              out1[0] = sx1;
-              out1[64] = sxx1;
+            __syncwarp();  // the previous unit's reads of `tile` are done
+#pragma unroll
+            for (int j = 0; j < 16; ++j) tile[lane * 16 + (j ^ (lane >> 1))] = pk[j];
+            __syncwarp();
+#pragma unroll 1
+            for (int seg = 0; seg < 2; ++seg) {
+              const int lo = seg ? meta.b0 : meta.a0, hi = seg ? meta.b1 : meta.a1;
+              if (hi <= lo) continue;
+              float sx0 = 0.f, sxx0 = 0.f, sx1 = 0.f, sxx1 = 0.f;  // even / odd rows of column `lane`
+              if (lo == 0 && hi == 32) {  // interior group: every row is valid
+#pragma unroll
+                for (int rr = 0; rr < 32; rr += 2) {
+                  accum16<kBF16>(row_value(rr), sx0, sxx0);
+                  accum16<kBF16>(row_value(rr + 1), sx1, sxx1);
+                }
+              } else {
+                int rr = lo;
+                for (; rr + 1 < hi; rr += 2) {
+                  accum16<kBF16>(row_value(rr), sx0, sxx0);
+                  accum16<kBF16>(row_value(rr + 1), sx1, sxx1);
+                }
+                if (rr < hi) accum16<kBF16>(row_value(rr), sx0, sxx0);
+              }
+              const int slot = meta.slot + ((seg && has_a) ? 1 : 0);
+              // blocked layout [column block of 64][slot][sum | sum of squares][64] (the tile column base is a
+              // multiple of 32, so a unit's 32 columns stay inside one block)
+              const int col = n0 + u * 32;
+              float* out = args.pool_partials +
+                           ((static_cast<int64_t>(col >> 6) * args.pool_slots + slot) * 2) * 64 + (col & 63) + lane;
+              out[0] = sx0 + sx1;
+              out[64] = sxx0 + sxx1;
             }
           }
-          continue;
         }
+      }
+      for (int c = half; !kPool && c < n_chunks; c += Cfg::kParts) {
         if (ptx::elect_one_sync()) ptx::tma_store_wait_read<0>();  // this warp's previous store is done with `buf`
         __syncwarp();
         if constexpr (kOutF32) {
@@ -421,7 +421,8 @@ cudaError_t LaunchTdnnGemmPair(const TdnnGemmArgs& args, int num_sms, cudaStream
     clusters = clusters / args.num_n_tiles * args.num_n_tiles;
     if (clusters == 0) clusters = args.num_n_tiles;
   }
-  kern<<<2 * clusters, kThreads, kSmemTotal, stream>>>(args);
+  const int threads = args.pool_meta ? PairCfg<true>::kThreads : PairCfg<false>::kThreads;
+  kern<<<2 * clusters, threads, kSmemTotal, stream>>>(args);
   return cudaGetLastError();
 }
 

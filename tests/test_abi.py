@@ -66,9 +66,13 @@ def test_product_code_does_not_touch_the_oracle():
             if f.endswith((".py", ".cc", ".cu", ".h", ".cuh")) or f == "Makefile":
                 txt = open(os.path.join(dp, f), errors="ignore").read()
                 assert not pat.search(txt), f"{f} uses the oracle"
-    # bench.py: only inside run_reference() and the cpu_baseline leg
+    # bench.py: only inside run_reference(), the cpu_baseline leg, and parity_check() -- the oracle as the
+    # CHECKER of the timed output (outside the timed region), never as the thing measured
     b = open(os.path.join(ROOT, "bench.py")).read()
-    assert len(re.findall(r"from oracle import cpu_baseline", b)) == 2 and "nnet3_oracle" not in b
+    assert len(re.findall(r"from oracle import cpu_baseline", b)) == 2
+    assert len(re.findall(r"(?:from|import) oracle", b)) == 3
+    body = b[b.index("def parity_check("):b.index("def cli_leg(")]
+    assert "from oracle.nnet3_oracle import" in body and b.count("nnet3_oracle import") == 1
 
 
 def test_model_from_plan_and_invalid_arguments(cvx):

@@ -299,6 +299,64 @@ def test_cli_reads_compressed_feature_archives(cvx, kf, synth, model_dir, requir
     assert rr <= TOL_REL and cc >= TOL_COS, (rr, cc)
 
 
+@pytest.mark.parametrize("fmt", ["CM", "CM3"])
+def test_cli_reads_cm_and_cm3_archives(cvx, kf, synth, model_dir, require_gpu, tmp_path, fmt):
+    """the other two CompressedMatrix layouts through the C++ reader: CM = per-column uint16 percentile
+    header + one byte per value, column-major (what steps/make_mfcc.sh --compress=true writes); CM3 = one
+    byte per value with a global min/range.  Expected values = the decoded matrices (decode formulas
+    restated here, [UPSTREAM-RECALL matrix/compressed-matrix.cc])."""
+    import os
+    import struct
+    import subprocess
+    from oracle.nnet3_oracle import Oracle, extract_all, parity_metrics
+    path, model = model_dir("v2_xvector")
+    lengths = [150, 260]
+    x = synth.make_features(lengths, 23, 19)
+    lo, rng = float(x.min()), float(x.max() - x.min())
+    deq = np.zeros_like(x)
+    with open(tmp_path / "c.ark", "wb") as f, open(tmp_path / "c.scp", "w") as scp:
+        r = 0
+        for k, T in zip(synth.utt_keys(2), lengths):
+            m = x[r:r + T]
+            f.write(k.encode() + b" ")
+            scp.write(f"{k} {tmp_path}/c.ark:{f.tell()}\n")
+            if fmt == "CM3":
+                q = np.clip(np.round((m - lo) / rng * 255.0), 0, 255).astype(np.uint8)
+                deq[r:r + T] = np.float32(lo) + np.float32(rng) * np.float32(1.0 / 255.0) * q.astype(np.float32)
+                f.write(b"\0BCM3 " + struct.pack("<ffii", lo, rng, T, 23) + q.tobytes())
+            else:
+                inc = np.float32(rng) * np.float32(1.0 / 65535.0)
+                to16 = lambda v: np.clip(np.round((v - lo) / rng * 65535.0), 0, 65535).astype(np.uint16)
+                srt = np.sort(m, axis=0)
+                h = np.stack([to16(srt[0]), to16(srt[T // 4]), to16(srt[3 * T // 4]), to16(srt[-1])], axis=1)   # [cols, 4]
+                h[:, 1] = np.maximum(h[:, 1], h[:, 0] + 1); h[:, 2] = np.maximum(h[:, 2], h[:, 1] + 1); h[:, 3] = np.maximum(h[:, 3], h[:, 2] + 1)
+                p = np.float32(lo) + inc * h.astype(np.float32)                                                  # percentile values
+                body = np.zeros((23, T), np.uint8)
+                for c in range(23):
+                    v = m[:, c]
+                    b = np.where(v < p[c, 1], np.round((v - p[c, 0]) / (p[c, 1] - p[c, 0]) * 64.0),
+                                 np.where(v < p[c, 2], 64 + np.round((v - p[c, 1]) / (p[c, 2] - p[c, 1]) * 128.0),
+                                          192 + np.round((v - p[c, 2]) / (p[c, 3] - p[c, 2]) * 63.0)))
+                    b = np.clip(b, 0, 255).astype(np.uint8)
+                    body[c] = b
+                    bf = b.astype(np.float32)
+                    deq[r:r + T, c] = np.where(b <= 64, p[c, 0] + (p[c, 1] - p[c, 0]) * bf * np.float32(1 / 64.0),
+                                               np.where(b <= 192, p[c, 1] + (p[c, 2] - p[c, 1]) * (bf - 64) * np.float32(1 / 128.0),
+                                                        p[c, 2] + (p[c, 3] - p[c, 2]) * (bf - 192) * np.float32(1 / 63.0)))
+                f.write(b"\0BCM " + struct.pack("<ffii", lo, rng, T, 23) + h.astype("<u2").tobytes() + body.tobytes())
+            r += T
+    assert np.max(np.abs(deq - x)) < 0.1          # the compression is lossy but sane
+    exe = os.path.join(cvx.BIN_DIR, "nnet3-xvector-compute")
+    res = subprocess.run([exe, "--min-chunk-size=25", "--chunk-size=200", "--output-node=tdnn6.affine", path,
+                          f"scp:{tmp_path}/c.scp", f"ark:{tmp_path}/o.ark"], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr
+    got = np.stack([v for _, v in kf.read_ark(str(tmp_path / "o.ark"))])
+    ref, ok = extract_all(Oracle(model, "tdnn6.affine", np.float64), {"input": deq.astype(np.float32)}, lengths,
+                          chunk_size=200, min_chunk_size=25)
+    rr, cc = parity_metrics(got, ref[ok])
+    assert rr <= TOL_REL and cc >= TOL_COS, (fmt, rr, cc)
+
+
 def test_cli_num_gpus_is_checked_against_visible_devices(cvx, require_gpu, tmp_path):
     """--num-gpus beyond the visible devices is refused before any work (SURVEY 8e mode ii)."""
     import os
@@ -354,3 +412,35 @@ def test_bf16_operands_end_to_end(cvx, synth, model_dir, require_gpu, topology):
     ref, _ = extract_all(_oracle(model, node), feats, lengths, chunk_size=500, min_chunk_size=25)
     r, c = parity_metrics(got[ok], ref[ok])
     assert r <= 8e-3 and c >= 0.9999, (r, c)
+
+
+def test_fp16_range_check_mode_counts_clipped_values(cvx, kf, synth, require_gpu, tmp_path):
+    """check_saturation engines store every layer and count the values the saturating fp16 converts
+    clipped at +-65504: zero for the recipes' BatchNorm-ed nets, non-zero -- with the
+    layer identified -- for a net whose second layer explodes; the drop-in program warns about it."""
+    import os
+    import subprocess
+    m = synth.make_tiny_model()
+    lengths = [60, 200]
+    feats = {"input": synth.make_features(lengths, 5, 3)}
+    kf.write_nnet3(str(tmp_path / "ok.raw"), m, True)
+    ex = cvx.Extractor(cvx.Model(str(tmp_path / "ok.raw"), "tdnn6.affine"), precision="fp16", check_saturation=True)
+    a, ok = ex.extract(feats, lengths, chunk_size=100, min_chunk_size=25)
+    assert ok.all() and ex.saturation_counts() == [0, 0, 0, 0]
+    plain, _ = cvx.Extractor(cvx.Model(str(tmp_path / "ok.raw"), "tdnn6.affine"), precision="fp16").extract(
+        feats, lengths, chunk_size=100, min_chunk_size=25)
+    assert np.allclose(a, plain, rtol=2e-5, atol=2e-5)          # check mode = stand-alone pooling kernels, same numbers
+    # BatchNorm of tdnn2 with a tiny variance: scale ~ 3e4, outputs far beyond the fp16 range
+    m.components["tdnn2.batchnorm"].fields["StatsVar"] = np.full_like(m.components["tdnn2.batchnorm"].fields["StatsVar"], 1e-12)
+    m.components["tdnn2.batchnorm"].fields["Epsilon"] = 1e-9
+    kf.write_nnet3(str(tmp_path / "hot.raw"), m, True)
+    ex = cvx.Extractor(cvx.Model(str(tmp_path / "hot.raw"), "tdnn6.affine"), precision="fp16", check_saturation=True)
+    ex.extract(feats, lengths, chunk_size=100, min_chunk_size=25)
+    c = ex.saturation_counts()
+    assert c[0] == 0 and c[1] == 0 and c[2] > 0, c
+    assert cvx.Extractor(cvx.Model(str(tmp_path / "hot.raw"), "tdnn6.affine"), precision="fp16").saturation_counts() == []
+    kf.write_ark(str(tmp_path / "f.ark"), [("a", feats["input"][:60]), ("b", feats["input"][60:])])
+    exe = os.path.join(cvx.BIN_DIR, "nnet3-xvector-compute")
+    r = subprocess.run([exe, "--check-saturation=true", "--min-chunk-size=25", "--chunk-size=100", "--output-node=tdnn6.affine",
+                        str(tmp_path / "hot.raw"), f"ark:{tmp_path}/f.ark", f"ark:{tmp_path}/o.ark"], capture_output=True, text=True)
+    assert r.returncode == 0 and "clipped at the fp16 range limit" in r.stderr and "tdnn2" in r.stderr, r.stderr
