@@ -338,6 +338,14 @@ int cvx_test_tdnn_layer_bench(int32_t device, int32_t precision, int64_t rows, i
                               const int32_t* offsets, int32_t num_offsets, int32_t out_dim,
                               int32_t iters, double* avg_ms);
 
+/* One segment-level layer (tdnn6: [chunks, 3000] x [3000, 512]) on fp32 host data through the production path:
+ * out[m, n] = post(in[m, k] w[n, k]^T), post = (+bias, optional ReLU, optional scale/offset).  With 16-bit
+ * `precision` that is the hi/lo-split tensor-core GEMM (fp32-accurate, ~2^-22); with CVX_PRECISION_FP32 the
+ * CUDA-core kernel. */
+int cvx_test_segment_affine(int32_t device, int32_t precision, const float* in, int64_t m, int32_t k,
+                            const float* w, const float* bias, int32_t relu, const float* scale,
+                            const float* offset, int32_t n, float* out);
+
 /* mean|stddev over row ranges [begin[c], end[c]) of an fp32 host matrix [rows, dim]. */
 int cvx_test_stats_pool(int32_t device, int32_t precision, const float* in, int64_t rows,
                         int32_t dim, const int64_t* begin, const int64_t* end, int64_t num_chunks,

@@ -88,6 +88,7 @@ ABI_SYMBOLS = [
     "cvx_device_free", "cvx_memcpy_h2d", "cvx_device_count", "cvx_engine_get_profile",
     "cvx_engine_reset_profile", "cvx_engine_launch_count", "cvx_engine_last_extract_ms", "cvx_test_tdnn_layer", "cvx_test_tdnn_layer_bench", "cvx_test_stats_pool",
     "cvx_acquire_device", "cvx_test_acquire_lock", "cvx_lpt_shards", "cvx_engine_saturation_counts",
+    "cvx_test_segment_affine",
 ]
 
 _lib = None
@@ -489,6 +490,22 @@ def plda_score(mean, transform, psi, train, test, trial_train, trial_test, train
     _check(lib.cvx_plda_score(device, C.byref(m), _ptr(tr), _ptr(nu), tr.shape[0], _ptr(te), te.shape[0], _ptr(ti), _ptr(tj),
                               len(ti), _ptr(scores)))
     return scores
+
+
+def test_segment_affine(x: np.ndarray, weight: np.ndarray, bias=None, relu=False, scale=None, offset=None,
+                        precision: str = "fp16", device: int = 0) -> np.ndarray:
+    """One segment-level layer through the production path (cvx_test_segment_affine)."""
+    lib = load_library()
+    x = np.ascontiguousarray(x, np.float32)
+    w = np.ascontiguousarray(weight, np.float32)
+    f = lambda a: None if a is None else np.ascontiguousarray(a, np.float32)
+    b, s, o = f(bias), f(scale), f(offset)
+    out = np.zeros((x.shape[0], w.shape[0]), np.float32)
+    lib.cvx_test_segment_affine.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
+                                            C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+    _check(lib.cvx_test_segment_affine(device, PRECISION[precision], _ptr(x), x.shape[0], x.shape[1], _ptr(w), _ptr(b),
+                                       int(relu), _ptr(s), _ptr(o), w.shape[0], _ptr(out)))
+    return out
 
 
 def test_stats_pool(x: np.ndarray, begin: Sequence[int], end: Sequence[int], precision: str = "fp16",

@@ -296,6 +296,11 @@ int cvx_engine_saturation_counts(cvx_engine* engine, int64_t* counts, int32_t ma
   });
 }
 
+int cvx_test_segment_affine(int32_t device, int32_t precision, const float* in, int64_t m, int32_t k, const float* w,
+                            const float* bias, int32_t relu, const float* scale, const float* offset, int32_t n, float* out) {
+  return Guard([&] { cvx::TestSegmentAffine(device, precision, in, m, k, w, bias, relu, scale, offset, n, out); });
+}
+
 void cvx_engine_reset_profile(cvx_engine* engine) {
   if (engine) engine->impl->ResetProfile();
 }

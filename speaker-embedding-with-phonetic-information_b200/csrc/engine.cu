@@ -238,63 +238,10 @@ void Engine::Build() {
     frame_ops_.push_back(std::move(op));
   }
 
-  // ---- segment layers (fp32) ----
+  // ---- segment layers (fp32 in / out; hi-lo split on the tensor path) ----
   for (const Layer& L : plan_.segment) {
-    SegOp s;
-    s.in_dim = L.in_dim;
-    s.out_dim = L.out_dim;
-    s.relu = L.relu;
-    s.d_w = DevAlloc<float>(L.weight.size());
-    CVX_CUDA_CHECK(cudaMemcpy(s.d_w, L.weight.data(), L.weight.size() * 4, cudaMemcpyHostToDevice));
-    if (!L.bias.empty()) {
-      s.d_b = DevAlloc<float>(L.bias.size());
-      CVX_CUDA_CHECK(cudaMemcpy(s.d_b, L.bias.data(), L.bias.size() * 4, cudaMemcpyHostToDevice));
-    }
-    if (!L.scale.empty()) {
-      s.d_scale = DevAlloc<float>(L.scale.size());
-      s.d_offset = DevAlloc<float>(L.offset.size());
-      CVX_CUDA_CHECK(cudaMemcpy(s.d_scale, L.scale.data(), L.scale.size() * 4, cudaMemcpyHostToDevice));
-      CVX_CUDA_CHECK(cudaMemcpy(s.d_offset, L.offset.data(), L.offset.size() * 4, cudaMemcpyHostToDevice));
-    }
-    bool scale_ok = true;
-    for (float v : L.scale) scale_ok = scale_ok && (!L.relu || v > 0.f);
-    s.kp = RoundUp(L.in_dim, kGemmBlockK);
-    if (elem_ != kF32 && L.out_dim % 4 == 0 && scale_ok && 3 * (s.kp / kGemmBlockK) <= kMaxKBlocks) {
-      s.tensor = true;
-      s.n_pad = RoundUp(L.out_dim, 64);
-      const size_t kc = static_cast<size_t>(3) * s.kp;
-      std::vector<float> whi(static_cast<size_t>(s.n_pad) * kc, 0.f), wlo_src(static_cast<size_t>(s.n_pad) * s.kp, 0.f);
-      std::vector<float2> post(s.n_pad, make_float2(0.f, 0.f));
-      for (int32_t n = 0; n < L.out_dim; ++n) {
-        const float sc = L.scale.empty() ? 1.f : L.scale[n];
-        for (int32_t k = 0; k < L.in_dim; ++k) wlo_src[static_cast<size_t>(n) * s.kp + k] = L.weight[static_cast<size_t>(n) * L.in_dim + k] * sc;
-        post[n] = make_float2((L.bias.empty() ? 0.f : L.bias[n]) * sc, L.offset.empty() ? 0.f : L.offset[n]);
-      }
-      // Wh = round16(W), Wl = round16(W - Wh)
-      std::vector<uint8_t> h16(wlo_src.size() * 2), l16(wlo_src.size() * 2);
-      ConvertToElem(wlo_src.data(), wlo_src.size(), elem_, h16.data());
-      std::vector<float> resid(wlo_src.size());
-      for (size_t i = 0; i < resid.size(); ++i) resid[i] = wlo_src[i] - ElemToFloat(h16.data(), i, elem_);
-      ConvertToElem(resid.data(), resid.size(), elem_, l16.data());
-      std::vector<uint8_t> wcat(static_cast<size_t>(s.n_pad) * kc * 2);
-      for (int32_t n = 0; n < s.n_pad; ++n) {
-        uint8_t* row = wcat.data() + static_cast<size_t>(n) * kc * 2;
-        std::memcpy(row, h16.data() + static_cast<size_t>(n) * s.kp * 2, static_cast<size_t>(s.kp) * 2);
-        std::memcpy(row + static_cast<size_t>(s.kp) * 2, h16.data() + static_cast<size_t>(n) * s.kp * 2, static_cast<size_t>(s.kp) * 2);
-        std::memcpy(row + static_cast<size_t>(s.kp) * 4, l16.data() + static_cast<size_t>(n) * s.kp * 2, static_cast<size_t>(s.kp) * 2);
-      }
-      CVX_CUDA_CHECK(cudaMalloc(&s.d_wcat, wcat.size()));
-      CVX_CUDA_CHECK(cudaMemcpy(s.d_wcat, wcat.data(), wcat.size(), cudaMemcpyHostToDevice));
-      s.d_post = DevAlloc<float2>(post.size());
-      CVX_CUDA_CHECK(cudaMemcpy(s.d_post, post.data(), post.size() * sizeof(float2), cudaMemcpyHostToDevice));
-      const int32_t k_real = RoundUp(L.in_dim, 16);
-      for (int pass = 0; pass < 3; ++pass)
-        for (int32_t j = 0; j * kGemmBlockK < k_real; ++j)
-          s.kb.push_back({pass == 1 ? 1 : 0, j * kGemmBlockK, 0, std::min(kGemmBlockK, k_real - j * kGemmBlockK) / 16});
-      // every pass must cover the same kp/64 blocks so that W's column offset is kb*64
-      if (static_cast<int32_t>(s.kb.size()) != 3 * (s.kp / kGemmBlockK)) s.tensor = false;
-    }
-    seg_ops_.push_back(s);
+    seg_ops_.emplace_back();
+    BuildSegmentOp(L, elem_, &seg_ops_.back());
   }
 
   // Fused pooling: possible when the pooled layer feeds nothing but the pooling, runs on the plain
@@ -371,14 +318,7 @@ void Engine::Release() noexcept {
   piece_events_.clear();
   cudaFree(d_seg_hi_);
   cudaFree(d_seg_lo_);
-  for (SegOp& s : seg_ops_) {
-    cudaFree(s.d_wcat);
-    cudaFree(s.d_post);
-    cudaFree(s.d_w);
-    cudaFree(s.d_b);
-    cudaFree(s.d_scale);
-    cudaFree(s.d_offset);
-  }
+  for (SegmentOp& s : seg_ops_) FreeSegmentOp(&s);
   for (int i = 0; i < 2; ++i)
     for (int s = 0; s < kMaxASources; ++s) cudaFree(d_feat_[i][s]);
   void* scratch[] = {d_slabs_, d_chunk_slab_off_, d_weights_, d_utt_off_, d_partials_, d_stats_,

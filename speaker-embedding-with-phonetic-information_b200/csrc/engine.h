@@ -38,6 +38,31 @@ constexpr uint32_t kDebugForceTapPath = 1u;   // cvx_engine_options.reserved[0] 
 constexpr uint32_t kDebugSingleCtaGemm = 2u;  // use the 1-CTA tcgen05 kernel instead of the CTA-pair one
 constexpr uint32_t kDebugNoHaloGemm = 4u;     // use the plain CTA-pair kernel instead of the tap-halo one
 
+// Segment-level affine layer (tdnn6 and later): fp32 in, fp32 out.  On the tensor path the fp32
+// input and weights are split into 16-bit hi/lo parts -- x = hi + lo, W = Wh + Wl,
+// y = hi*Wh + lo*Wh + hi*Wl (~2^-22 relative) -- and run through the CTA-pair GEMM with its fp32
+// epilogue (engine_segment.cu).
+struct SegmentOp {
+  int32_t in_dim = 0, out_dim = 0;
+  float *d_w = nullptr, *d_b = nullptr, *d_scale = nullptr, *d_offset = nullptr;
+  bool relu = false;
+  bool tensor = false;
+  int32_t kp = 0, n_pad = 0;
+  void* d_wcat = nullptr;      // [n_pad, 3*kp] = [Wh | Wh | Wl]
+  float2* d_post = nullptr;    // [n_pad]
+  std::vector<KBlockDesc> kb;  // hi blocks, lo blocks, hi blocks
+};
+// Uploads (and, for 16-bit `elem`, splits) the layer's parameters on the current device.
+void BuildSegmentOp(const Layer& L, int32_t elem, SegmentOp* op);
+void FreeSegmentOp(SegmentOp* op) noexcept;
+// out[m, out_dim] = post(in[m, in_dim] W^T); hi / lo: scratch of split_rows x kp 16-bit values each
+// (split_rows = m rounded up to 256), only used when op.tensor.
+void RunSegmentOp(const SegmentOp& op, int32_t elem, int num_sms, const float* in, int32_t ld_in, int64_t m, float* out,
+                  int32_t ld_out, void* hi, void* lo, int64_t split_rows, cudaStream_t stream);
+// Test entry (cvx_test_segment_affine): one segment layer on host data through the production path.
+void TestSegmentAffine(int32_t device, int32_t precision, const float* in, int64_t m, int32_t k, const float* w,
+                       const float* bias, int32_t relu, const float* scale, const float* offset, int32_t n, float* out);
+
 class Engine {
  public:
   Engine(const Plan& plan, const cvx_engine_options& opts);
@@ -105,17 +130,6 @@ class Engine {
     TdnnGemmHaloArgs hargs;
     bool halo_ok = false;  // the layer fits the tap-halo kernel's limits
   };
-  struct SegOp {
-    int32_t in_dim = 0, out_dim = 0;
-    float *d_w = nullptr, *d_b = nullptr, *d_scale = nullptr, *d_offset = nullptr;
-    bool relu = false;
-    // tensor-core path: x = hi + lo, W = Wh + Wl (16-bit splits), y = hi*Wh + lo*Wh + hi*Wl
-    bool tensor = false;
-    int32_t kp = 0, n_pad = 0;
-    void* d_wcat = nullptr;      // [n_pad, 3*kp] = [Wh | Wh | Wl]
-    float2* d_post = nullptr;    // [n_pad]
-    std::vector<KBlockDesc> kb;  // hi blocks, lo blocks, hi blocks
-  };
   enum ProfClass { kProfStage = 0, kProfGemm, kProfPool, kProfPoolFin, kProfSegment, kProfAverage, kNumProf };
   struct PendingEvent {
     int cls;
@@ -152,7 +166,7 @@ class Engine {
   std::vector<Buffer> buffers_;
   std::vector<Staging> stagings_;
   std::vector<FrameOp> frame_ops_;
-  std::vector<SegOp> seg_ops_;
+  std::vector<SegmentOp> seg_ops_;
   std::vector<int32_t> layer_buffer_;
   int64_t rows_cap_ = 0;
   int64_t max_batch_rows_ = 0;

@@ -174,7 +174,7 @@ void Engine::Extract(const float* const* feats, int32_t num_streams, int64_t tot
   for (size_t i = 0; i + 1 < seg_ops_.size(); ++i) max_seg = std::max(max_seg, seg_ops_[i].out_dim);
   for (int i = 0; i < 2; ++i) Grow(&d_seg_[i], &seg_cap_[i], static_cast<size_t>(seg_cap_chunks) * std::max(max_seg, 1) * 4);
   int32_t max_kp = 0;
-  for (const SegOp& so : seg_ops_)
+  for (const SegmentOp& so : seg_ops_)
     if (so.tensor) max_kp = std::max(max_kp, so.kp);
   if (max_kp > 0) {
     const int64_t split_rows = (seg_cap_chunks + 2 * kGemmBlockM - 1) / (2 * kGemmBlockM) * (2 * kGemmBlockM);
@@ -332,42 +332,12 @@ void Engine::Extract(const float* const* feats, int32_t num_streams, int64_t tot
       if (seg_ops_.empty())
         CVX_CUDA_CHECK(cudaMemcpyAsync(emb, cur, static_cast<size_t>(pending) * E * 4, cudaMemcpyDeviceToDevice, compute_));
       for (size_t si = 0; si < seg_ops_.size(); ++si) {
-        const SegOp& s = seg_ops_[si];
+        const SegmentOp& s = seg_ops_[si];
         const bool last = si + 1 == seg_ops_.size();
         float* dst = last ? emb : static_cast<float*>(d_seg_[si & 1]);
         const int32_t dst_ld = s.out_dim;
         ProfBegin(kProfSegment, 2.0 * pending * s.in_dim * s.out_dim, 0);
-        if (s.tensor) {
-          CVX_CUDA_CHECK(LaunchSplitF32(cur, cur_ld, pending, s.in_dim, d_seg_hi_, d_seg_lo_, s.kp, elem_, compute_));
-          TdnnGemmArgs a;
-          std::memset(&a, 0, sizeof(a));
-          Encode2D(&a.a_maps[0], elem_, d_seg_hi_, seg_split_rows_, s.kp, kGemmBlockK, kGemmBlockM);
-          Encode2D(&a.a_maps[1], elem_, d_seg_lo_, seg_split_rows_, s.kp, kGemmBlockK, kGemmBlockM);
-          a.a_maps[2] = a.a_maps[3] = a.a_maps[0];
-          a.b_box_rows = std::min(kGemmBlockN, s.n_pad);
-          a.b_box_rows_pair = std::min(kGemmBlockN / 2, s.n_pad);
-          Encode2D(&a.b_map, elem_, s.d_wcat, s.n_pad, 3 * s.kp, kGemmBlockK, a.b_box_rows);
-          Encode2D(&a.b_map_pair, elem_, s.d_wcat, s.n_pad, 3 * s.kp, kGemmBlockK, a.b_box_rows_pair);
-          // fp32 output; rows beyond `pending` and columns beyond out_dim are clipped by the map
-          Encode2D(&a.c_map, kF32, dst, pending, dst_ld, 32, 32, s.out_dim);
-          a.num_kb = static_cast<int32_t>(s.kb.size());
-          for (size_t i = 0; i < s.kb.size(); ++i) a.kb[i] = s.kb[i];
-          a.n_pad = s.n_pad;
-          a.n_mma = RoundUp(s.out_dim, 32);
-          a.tile_n = kGemmBlockN;
-          a.c_map_half = a.c_map;
-          a.num_m_tiles = static_cast<int32_t>((pending + kGemmBlockM - 1) / kGemmBlockM);
-          a.num_n_tiles = (a.n_mma + kGemmBlockN - 1) / kGemmBlockN;
-          a.post = s.d_post;
-          a.relu = s.relu ? 1 : 0;
-          a.ab_format = elem_ == kBF16 ? 1 : 0;
-          a.out_f32 = 1;
-          a.num_stages = 64;
-          CVX_CUDA_CHECK(LaunchTdnnGemmPair(a, num_sms_, compute_));
-        } else {
-          CVX_CUDA_CHECK(LaunchSegmentAffine(cur, cur_ld, pending, s.in_dim, s.d_w, s.d_b, s.relu ? 1 : 0, s.d_scale,
-                                             s.d_offset, s.out_dim, dst, dst_ld, compute_));
-        }
+        RunSegmentOp(s, elem_, num_sms_, cur, cur_ld, pending, dst, dst_ld, d_seg_hi_, d_seg_lo_, seg_split_rows_, compute_);
         ProfEnd();
         cur = dst;
         cur_ld = dst_ld;

@@ -44,7 +44,7 @@ void Input::Open(const std::string& rx_in) {
   Close();
   std::string rx = Trim(rx_in);
   name_ = rx;
-  buf_.resize(1 << 20);
+  buf_.resize(1 << 16);  // headers and text go through this buffer; large binary bodies are read straight into their destination
   pos_ = end_ = 0;
   if (rx.empty()) throw KaldiError("empty rxfilename");
   if (rx == "-") {

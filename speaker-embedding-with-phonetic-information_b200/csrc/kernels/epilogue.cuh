@@ -22,6 +22,7 @@
 #include <cstdint>
 
 #include "kernels.h"
+#include "ptx.cuh"
 
 namespace cvx {
 namespace epi {
@@ -81,6 +82,82 @@ __device__ __forceinline__ void pack8(const uint32_t* r, const uint8_t* smem_pos
     asm("mov.b64 {%0, %1}, %2;" : "=f"(t0), "=f"(t1) : "l"(sum));
     const uint32_t h = pack2<kBF16>(t0, t1);
     pk[e] = relu ? max16x2<kBF16>(h, oo[e]) : h;
+  }
+}
+
+
+// One 128-byte-wide output chunk (64 16-bit or 32 fp32 columns) of this warp's 32 accumulator rows:
+// TMEM -> bias / ReLU / BatchNorm offset -> this warp's 4 KB staging buffer (128B-swizzled like the
+// tensor map) -> TMA store at (n0 + chunk columns, row0).  Shared by the CTA-pair and tap-halo
+// kernels.  `t_row`: TMEM address of the warp's lane quarter and accumulator stage; `smem_post`: the
+// tile's staged column parameters (store_post); n_cols: width of the N tile (multiple of 32 -- a
+// tile of odd width in 32-column units ends in a half chunk that goes through the un-swizzled
+// 32-column map).
+template <bool kBF16, bool kOutF32>
+__device__ __forceinline__ void store_chunk(uint32_t t_row, int c, int n_cols, int n0, int row0, int lane, uint8_t* buf,
+                                            const uint8_t* smem_post, bool relu, const CUtensorMap* c_map,
+                                            const CUtensorMap* c_map_half) {
+  constexpr int kChunkCols = kOutF32 ? 32 : 64;
+  if (ptx::elect_one_sync()) ptx::tma_store_wait_read<0>();  // this warp's previous store is done with `buf`
+  __syncwarp();
+  if constexpr (kOutF32) {
+    const float2* post = reinterpret_cast<const float2*>(smem_post);
+    uint32_t r[32];
+    ptx::tmem_ld_32x32b_x32(t_row + c * 32, r);
+    ptx::tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      float v[4];
+#pragma unroll
+      for (int e = 0; e < 4; e += 2) {
+        const float4 p = *reinterpret_cast<const float4*>(&post[c * 32 + j + e]);
+        v[e] = __uint_as_float(r[j + e]) + p.x;
+        v[e + 1] = __uint_as_float(r[j + e + 1]) + p.z;
+        if (relu) {
+          v[e] = fmaxf(v[e], 0.f);
+          v[e + 1] = fmaxf(v[e + 1], 0.f);
+        }
+        v[e] += p.y;
+        v[e + 1] += p.w;
+      }
+      const int unit = j >> 2;  // 16-byte unit (4 floats) inside the 128-byte row
+      *reinterpret_cast<float4*>(buf + lane * 128 + ((unit ^ (lane & 7)) << 4)) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+  } else {
+    const bool half_chunk = (n_cols - c * 64) < 64;
+    // both 32-column halves of the chunk are requested before the single wait
+    uint32_t r0[32], r1[32];
+    ptx::tmem_ld_32x32b_x32(t_row + c * 64, r0);
+    if (!half_chunk) ptx::tmem_ld_32x32b_x32(t_row + c * 64 + 32, r1);
+    ptx::tmem_ld_wait();
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (h == 1 && half_chunk) break;
+      const uint32_t* r = h ? r1 : r0;
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        uint32_t pk[4];
+        pack8<kBF16>(&r[j], smem_post, c * 64 + h * 32 + j, relu, pk);
+        const int unit = h * 4 + (j >> 3);  // 16-byte unit inside the 128-byte row
+        uint8_t* dst = half_chunk ? buf + lane * 64 + (unit << 4) : buf + lane * 128 + ((unit ^ (lane & 7)) << 4);
+        *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+    }
+    if (half_chunk) {
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (ptx::elect_one_sync()) {
+        ptx::tma_store_2d(c_map_half, buf, n0 + c * 64, row0);
+        ptx::tma_store_commit();
+      }
+      return;
+    }
+  }
+  ptx::fence_proxy_async_smem();
+  __syncwarp();
+  if (ptx::elect_one_sync()) {
+    ptx::tma_store_2d(c_map, buf, n0 + c * kChunkCols, row0);
+    ptx::tma_store_commit();
   }
 }
 

@@ -90,7 +90,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairCfg<kPool>::kThr
   uint8_t* smem_a = smem + kSmemA;
   uint8_t* smem_b = smem + kSmemB;
   uint8_t* smem_c = smem + kSmemC;
-  float2* smem_post = reinterpret_cast<float2*>(smem + kSmemPost);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kSmemBars);  // used in the leader
   uint64_t* empty_bar = full_bar + kStages;                            // per CTA
   uint64_t* tmem_full_bar = empty_bar + kStages;                       // per CTA
@@ -324,68 +323,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairCfg<kPool>::kThr
         }
       }
       for (int c = half; !kPool && c < n_chunks; c += Cfg::kParts) {
-        if (ptx::elect_one_sync()) ptx::tma_store_wait_read<0>();  // this warp's previous store is done with `buf`
-        __syncwarp();
-        if constexpr (kOutF32) {
-          uint32_t r[32];
-          ptx::tmem_ld_32x32b_x32(t_row + c * 32, r);
-          ptx::tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float v[4];
-#pragma unroll
-            for (int e = 0; e < 4; e += 2) {
-              const float4 p = *reinterpret_cast<const float4*>(&smem_post[c * 32 + j + e]);
-              v[e] = __uint_as_float(r[j + e]) + p.x;
-              v[e + 1] = __uint_as_float(r[j + e + 1]) + p.z;
-              if (args.relu) {
-                v[e] = fmaxf(v[e], 0.f);
-                v[e + 1] = fmaxf(v[e + 1], 0.f);
-              }
-              v[e] += p.y;
-              v[e + 1] += p.w;
-            }
-            const int unit = j >> 2;  // 16-byte unit (4 floats) inside the 128-byte row
-            *reinterpret_cast<float4*>(buf + lane * 128 + ((unit ^ (lane & 7)) << 4)) = make_float4(v[0], v[1], v[2], v[3]);
-          }
-        } else {
-          // a tile whose width is an odd multiple of 32 ends in a half chunk: 32 columns, stored
-          // through the un-swizzled 32-column map (rows 64 bytes apart in `buf`)
-          const bool half_chunk = (n_cols - c * 64) < 64;
-          // both 32-column halves of the chunk are requested before the single wait
-          uint32_t r0[32], r1[32];
-          ptx::tmem_ld_32x32b_x32(t_row + c * 64, r0);
-          if (!half_chunk) ptx::tmem_ld_32x32b_x32(t_row + c * 64 + 32, r1);
-          ptx::tmem_ld_wait();
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            if (h == 1 && half_chunk) break;
-            const uint32_t* r = h ? r1 : r0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint32_t pk[4];
-              epi::pack8<kBF16>(&r[j], smem + kSmemPost, c * 64 + h * 32 + j, args.relu != 0, pk);
-              const int unit = h * 4 + (j >> 3);  // 16-byte unit inside the 128-byte row
-              uint8_t* dst = half_chunk ? buf + lane * 64 + (unit << 4) : buf + lane * 128 + ((unit ^ (lane & 7)) << 4);
-              *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            }
-          }
-          if (half_chunk) {
-            ptx::fence_proxy_async_smem();
-            __syncwarp();
-            if (ptx::elect_one_sync()) {
-              ptx::tma_store_2d(&args.c_map_half, buf, n0 + c * 64, args.c_row0 + m0 + q * 32);
-              ptx::tma_store_commit();
-            }
-            continue;
-          }
-        }
-        ptx::fence_proxy_async_smem();
-        __syncwarp();
-        if (ptx::elect_one_sync()) {
-          ptx::tma_store_2d(&args.c_map, buf, n0 + c * kChunkCols, args.c_row0 + m0 + q * 32);
-          ptx::tma_store_commit();
-        }
+        epi::store_chunk<kBF16, kOutF32>(t_row, c, n_cols, n0, args.c_row0 + m0 + q * 32, lane, buf, smem + kSmemPost, args.relu != 0,
+                                         &args.c_map, &args.c_map_half);
       }
       ptx::tcgen05_fence_before();
       __syncwarp();

@@ -114,3 +114,24 @@ def test_stats_pool_constant_column_hits_floor(cvx, require_gpu):
     got = cvx.test_stats_pool(x, [0], [100], precision="fp32")
     assert np.allclose(got[0, :64], 3.0)
     assert np.allclose(got[0, 64:], np.sqrt(1e-10), rtol=1e-3)
+
+
+@pytest.mark.parametrize("m,k,n", [(1, 3000, 512), (37, 3000, 512), (700, 1024, 512), (5000, 3000, 512), (300, 200, 96)])
+@pytest.mark.parametrize("precision,tol", [("fp16", 2e-6), ("bf16", 3e-5), ("fp32", 2e-6)])
+def test_segment_affine_hi_lo_split_is_fp32_accurate(cvx, require_gpu, m, k, n, precision, tol):
+    """tdnn6 in isolation: the 16-bit hi/lo split GEMM (x = hi + lo, W = Wh + Wl,
+    y = hi Wh + lo Wh + hi Wl on tcgen05, fp32 epilogue) against fp64 numpy -- fp32-class accuracy
+    (fp16 split: ~2^-22; bf16 split keeps 16 mantissa bits: ~2^-16), with and without ReLU + BatchNorm."""
+    rng = np.random.default_rng(m + k)
+    x = rng.standard_normal((m, k)).astype(np.float32) * np.float32(3.0)
+    x[:, : k // 2] = np.abs(x[:, : k // 2])                       # pooled vectors: means of post-ReLU values, stddevs > 0
+    w = (rng.standard_normal((n, k)) / np.sqrt(k)).astype(np.float32)
+    b = (0.1 * rng.standard_normal(n)).astype(np.float32)
+    ref = x.astype(np.float64) @ w.astype(np.float64).T + b
+    got = cvx.test_segment_affine(x, w, b, precision=precision)
+    assert np.max(np.abs(got - ref)) <= tol * np.max(np.abs(ref)), np.max(np.abs(got - ref)) / np.max(np.abs(ref))
+    s = rng.uniform(0.5, 2.0, n).astype(np.float32)
+    o = (0.2 * rng.standard_normal(n)).astype(np.float32)
+    ref2 = np.maximum(ref, 0) * s + o
+    got2 = cvx.test_segment_affine(x, w, b, relu=True, scale=s, offset=o, precision=precision)
+    assert np.max(np.abs(got2 - ref2)) <= 2 * tol * np.max(np.abs(ref2))
