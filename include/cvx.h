@@ -284,6 +284,11 @@ int cvx_device_count(int32_t* count);
  * (may be NULL) is the number of jobs already on the chosen device.  wait != 0 (--use-gpu=wait):
  * block until a device is free instead of sharing. */
 int cvx_acquire_device(int32_t wait, int32_t* device, int32_t* sharers);
+/* The same protocol for a host that wants its device BEFORE it initialises CUDA (so that it can restrict
+ * CUDA_VISIBLE_DEVICES to it and not pay context set-up on every GPU of the box): ids[] are stable
+ * device names, e.g. the PCI bus ids under /proc/driver/nvidia/gpus; *index = the one acquired.  Names
+ * are matched case-insensitively with cvx_acquire_device's, so both kinds of job share one set of locks. */
+int cvx_acquire_device_by_id(const char* const* ids, int32_t num_ids, int32_t wait, int32_t* index, int32_t* sharers);
 /* Test entry: the same lock protocol over `num_devices` made-up devices in directory `dir`. */
 int cvx_test_acquire_lock(const char* dir, int32_t num_devices, int32_t wait, int32_t* device, int32_t* sharers);
 

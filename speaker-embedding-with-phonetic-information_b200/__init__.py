@@ -87,7 +87,7 @@ ABI_SYMBOLS = [
     "cvx_test_prestep", "cvx_host_alloc", "cvx_host_free", "cvx_device_alloc",
     "cvx_device_free", "cvx_memcpy_h2d", "cvx_device_count", "cvx_engine_get_profile",
     "cvx_engine_reset_profile", "cvx_engine_launch_count", "cvx_engine_last_extract_ms", "cvx_test_tdnn_layer", "cvx_test_tdnn_layer_bench", "cvx_test_stats_pool",
-    "cvx_acquire_device", "cvx_test_acquire_lock", "cvx_lpt_shards", "cvx_engine_saturation_counts",
+    "cvx_acquire_device", "cvx_acquire_device_by_id", "cvx_test_acquire_lock", "cvx_lpt_shards", "cvx_engine_saturation_counts",
     "cvx_test_segment_affine",
 ]
 

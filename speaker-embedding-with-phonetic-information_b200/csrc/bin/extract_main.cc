@@ -160,6 +160,9 @@ struct ResultQueue {
 struct LaneResult {
   int64_t num_success = 0, num_fail = 0, frame_count = 0;
   std::string error;
+  // where the lane's wall time went (logged with --verbose=1)
+  double setup_s = 0, gpu_wait_s = 0, extract_s = 0, total_s = 0;
+  int64_t calls = 0;
 };
 
 uint32_t KeyHash(const std::string& s) {  // FNV-1a: the same in every job of a stage
@@ -221,6 +224,7 @@ int ExtractMain(int argc, const char* const* argv, bool multiple_input) {
     std::string mean_vec, transform_mat;
     bool normalize_length = false, scaleup = true;
     int32_t chunk_size = -1, min_chunk_size = 100, gpu_id = -1, cmn_window = 0, min_cmn_window = 100, num_gpus = 1;
+    int32_t readers_per_gpu = 1;
     bool cmn_center = true, cmn_norm_vars = false;
     int64_t batch_rows = 1 << 20, max_batch_rows = 0;
     bool pad_input = false, profile = false, check_saturation = false;
@@ -249,6 +253,10 @@ int ExtractMain(int argc, const char* const* argv, bool multiple_input) {
                 "Use this many GPUs (devices gpu-id .. gpu-id + num-gpus - 1) from ONE process, one engine per GPU. "
                 "scp inputs: one reader thread per GPU over a length-balanced share of the table; archive / pipe "
                 "inputs: row batches go to the GPUs in turn.  Output order is the table's either way");
+    po.Register("readers-per-gpu", &readers_per_gpu,
+                "scp inputs: reader lanes (reader thread + pinned batches + engine) per GPU.  One reader copies ~4-6 GB/s "
+                "out of the page cache, about what ONE B200 consumes on the c-vector net; 2 keeps the GPU busy on the "
+                "x-vector nets and on compressed archives");
     po.Register("shard", &shard_spec,
                 "J/N: process only the J-th (1-based, like JOB) of N length-balanced shards of the feature table "
                 "(greedy LPT over frame counts; replaces utils/split_data.sh)");
@@ -326,6 +334,7 @@ int ExtractMain(int argc, const char* const* argv, bool multiple_input) {
       CVX_WARN("--chunk-size=" << chunk_size << " is below --min-chunk-size=" << min_chunk_size
                                << ": with --pad-input=true every chunk is padded to the minimum size");
     if (num_gpus < 1) throw KaldiError("--num-gpus must be >= 1");
+    if (readers_per_gpu < 1 || readers_per_gpu > 8) throw KaldiError("--readers-per-gpu must be in 1..8");
     const std::pair<int32_t, int32_t> shard = ParseShard(shard_spec);
     gpu_id = ChooseDevice(gpu_id, use_gpu, num_gpus);
 
@@ -384,7 +393,9 @@ int ExtractMain(int argc, const char* const* argv, bool multiple_input) {
       scp_input = scp_input && feat_specs.back().is_scp;
     }
     if (!vad_rspecifier.empty()) scp_input = scp_input && ParseRspecifier(vad_rspecifier).is_scp;
-    const int num_lanes = (num_gpus > 1 && scp_input) ? num_gpus : 1;
+    const int num_lanes = (scp_input && num_gpus * readers_per_gpu > 1) ? num_gpus * readers_per_gpu : 1;
+    const int lanes_per_gpu = num_lanes > 1 ? readers_per_gpu : 1;
+    const int num_engines = num_lanes > 1 ? num_lanes : num_gpus;
     const int32_t num_bins = shard.second * num_lanes;
     std::unordered_map<std::string, int32_t> bin_of;
     if (num_bins > 1) {
@@ -400,14 +411,15 @@ int ExtractMain(int argc, const char* const* argv, bool multiple_input) {
 
     // one engine per GPU (SURVEY 8e mode ii); engines share nothing, there is no collective.  Built
     // concurrently: each is ~0.3 s of weight re-packing and uploads.
-    std::vector<cvx_engine*> engines(num_gpus, nullptr);
+    std::vector<cvx_engine*> engines(num_engines, nullptr);
     {
-      std::vector<std::string> errs(num_gpus);
+      std::vector<std::string> errs(num_engines);
       std::vector<std::thread> th;
-      for (int g = 0; g < num_gpus; ++g)
+      for (int g = 0; g < num_engines; ++g)
         th.emplace_back([&, g] {
           cvx_engine_options o = eo;
-          o.device = wrap_devices ? (gpu_id + g) % ndev : gpu_id + g;
+          const int dev = gpu_id + g / lanes_per_gpu;  // lanes of one GPU are neighbours
+          o.device = wrap_devices ? dev % ndev : dev;
           if (cvx_engine_create(model, &o, &engines[g]) != CVX_OK) errs[g] = cvx_last_error();
         });
       for (std::thread& t : th) t.join();
@@ -452,6 +464,10 @@ int ExtractMain(int argc, const char* const* argv, bool multiple_input) {
     auto run_lane = [&](const std::vector<cvx_engine*>& engs, const std::function<bool(const std::string&)>& keep,
                         const std::function<void(const std::string&, const float*)>& emit, LaneResult* res) {
       const int ngpu = static_cast<int>(engs.size());
+      const auto lane_t0 = std::chrono::steady_clock::now();
+      auto since = [](std::chrono::steady_clock::time_point t) {
+        return std::chrono::duration<double>(std::chrono::steady_clock::now() - t).count();
+      };
       // pinned host batches: one being filled + one in flight per GPU of this lane
       std::vector<HostBatch> hb(ngpu + 1);
       for (HostBatch& b : hb) {
@@ -466,6 +482,7 @@ int ExtractMain(int argc, const char* const* argv, bool multiple_input) {
       std::unique_ptr<SequentialMatrixReader> vad_reader;
       if (!vad_rspecifier.empty()) vad_reader.reset(new SequentialMatrixReader(vad_rspecifier, /*allow_vectors=*/true, keep));
       batch_pool.WaitFor(0);
+      res->setup_s = since(lane_t0);
       int64_t& num_success = res->num_success;
       int64_t& num_fail = res->num_fail;
       int64_t& frame_count = res->frame_count;
@@ -476,6 +493,7 @@ int ExtractMain(int argc, const char* const* argv, bool multiple_input) {
         std::thread th;
         int status = CVX_OK;
         std::string error;
+        double seconds = 0;  // inside cvx_extract
       };
       std::deque<std::unique_ptr<Job>> inflight;
       struct Joiner {
@@ -492,7 +510,11 @@ int ExtractMain(int argc, const char* const* argv, bool multiple_input) {
         if (inflight.empty()) return;
         std::unique_ptr<Job> job = std::move(inflight.front());
         inflight.pop_front();
+        const auto tw = std::chrono::steady_clock::now();
         job->th.join();
+        res->gpu_wait_s += since(tw);
+        res->extract_s += job->seconds;
+        res->calls += 1;
         if (job->status != CVX_OK) throw KaldiError("cvx_extract failed: " + job->error);
         HostBatch& b = hb[job->batch];
         for (size_t u = 0; u < b.keys.size(); ++u) emit(b.keys[u], b.out + u * E);
@@ -513,6 +535,7 @@ int ExtractMain(int argc, const char* const* argv, bool multiple_input) {
         job->batch = which;
         Job* jp = job.get();
         job->th = std::thread([&, which, eng, jp]() {
+          const auto tj = std::chrono::steady_clock::now();
           HostBatch& w = hb[which];
           std::vector<const float*> f(w.feats.begin(), w.feats.end());
           if (raw_mode)
@@ -526,6 +549,7 @@ int ExtractMain(int argc, const char* const* argv, bool multiple_input) {
                                      w.chunk_utt.data(), w.chunk_weight.data(), static_cast<int64_t>(w.chunk_start.size()),
                                      static_cast<int32_t>(w.keys.size()), w.out, 0);
           if (jp->status != CVX_OK) jp->error = cvx_last_error();
+          jp->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - tj).count();
         });
         inflight.push_back(std::move(job));
         const int next = free_batches.back();
@@ -693,6 +717,11 @@ int ExtractMain(int argc, const char* const* argv, bool multiple_input) {
         int st = r->Close();
         if (st != 0) CVX_WARN("a feature input pipe exited with status " << st);
       }
+      res->total_s = since(lane_t0);
+      if (po.verbose >= 1)
+        CVX_LOG("lane timing: " << res->total_s << " s = " << res->setup_s << " s waiting for pinned buffers + readers, "
+                                << res->gpu_wait_s << " s blocked on the GPU, the rest reading / packing; " << res->calls
+                                << " cvx_extract calls took " << res->extract_s << " s");
     };
 
     VectorWriter writer(vector_wspecifier);
@@ -757,12 +786,12 @@ int ExtractMain(int argc, const char* const* argv, bool multiple_input) {
     CVX_LOG("Time taken " << elapsed << "s: real-time factor assuming 100 frames/sec is "
                           << (frame_count > 0 ? elapsed * 100.0 / static_cast<double>(frame_count) : 0.0));
     CVX_LOG("Done " << num_success << " utterances, failed for " << num_fail);
-    for (int g = 0; profile && g < num_gpus; ++g) {
+    for (int g = 0; profile && g < num_engines; ++g) {
       cvx_kernel_profile recs[16];
       int32_t n = 0;
       cvx_engine_get_profile(engines[g], recs, 16, &n);
       for (int32_t i = 0; i < n; ++i)
-        CVX_LOG("profile gpu" << (gpu_id + g) << " " << recs[i].name << ": launches=" << recs[i].launches
+        CVX_LOG("profile engine" << g << " (gpu " << (gpu_id + g / lanes_per_gpu) << ") " << recs[i].name << ": launches=" << recs[i].launches
                               << " ms=" << recs[i].total_ms
                               << (recs[i].flops > 0 ? " TFLOP/s=" + std::to_string(recs[i].flops / recs[i].total_ms * 1e-9) : "")
                               << (recs[i].bytes > 0 ? " GB/s=" + std::to_string(recs[i].bytes / recs[i].total_ms * 1e-6) : ""));
@@ -779,7 +808,7 @@ int ExtractMain(int argc, const char* const* argv, bool multiple_input) {
           names.push_back("layer " + name);
         }
       int64_t total = 0;
-      for (int g = 0; g < num_gpus; ++g) {
+      for (int g = 0; g < num_engines; ++g) {
         int64_t counts[80];
         int32_t n = 0;
         if (cvx_engine_saturation_counts(engines[g], counts, 80, &n) != CVX_OK) continue;

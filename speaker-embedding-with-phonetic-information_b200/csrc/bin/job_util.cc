@@ -1,6 +1,11 @@
 #include "job_util.h"
 
+#include <dirent.h>
+#include <unistd.h>
+
+#include <algorithm>
 #include <cstdlib>
+#include <fstream>
 #include <sstream>
 
 #include "../../../include/cvx.h"
@@ -8,11 +13,57 @@
 
 namespace cvx {
 
+namespace {
+// PCI bus ids of the GPUs this process can open, in PCI order, WITHOUT touching CUDA:
+// /proc/driver/nvidia/gpus/<bus id>/information holds "Device Minor: N"; kept if /dev/nvidiaN is accessible.
+std::vector<std::string> ListGpusFromProc() {
+  std::vector<std::string> ids;
+  const std::string root = "/proc/driver/nvidia/gpus";
+  DIR* d = opendir(root.c_str());
+  if (!d) return ids;
+  while (dirent* e = readdir(d)) {
+    const std::string name = e->d_name;
+    if (name == "." || name == "..") continue;
+    std::ifstream info(root + "/" + name + "/information");
+    std::string line;
+    int minor = -1;
+    while (std::getline(info, line)) {
+      const size_t p = line.find("Device Minor:");
+      if (p != std::string::npos) minor = std::atoi(line.c_str() + p + 13);
+    }
+    if (minor < 0) continue;
+    if (access(("/dev/nvidia" + std::to_string(minor)).c_str(), R_OK | W_OK) != 0) continue;
+    ids.push_back(name);
+  }
+  closedir(d);
+  std::sort(ids.begin(), ids.end());
+  return ids;
+}
+}  // namespace
+
 int32_t ChooseDevice(int32_t gpu_id, const std::string& use_gpu, int32_t num_gpus) {
   if (gpu_id >= 0) return gpu_id;
   if (const char* e = std::getenv("CVX_DEVICE")) return std::atoi(e);
   if (num_gpus > 1) return 0;  // --num-gpus=G takes devices 0 .. G-1
   int32_t dev = 0, sharers = 0;
+  // Preferred: pick the GPU before CUDA is initialised and make it the only visible one, so that this job
+  // does not pay (and hold) driver state on every GPU of the box -- with nj jobs starting together
+  // that is most of their start-up time.
+  if (!std::getenv("CUDA_VISIBLE_DEVICES") && !std::getenv("CVX_SELECT_WITH_CUDA")) {
+    const std::vector<std::string> ids = ListGpusFromProc();
+    if (!ids.empty()) {
+      std::vector<const char*> c;
+      for (const std::string& s : ids) c.push_back(s.c_str());
+      if (cvx_acquire_device_by_id(c.data(), static_cast<int32_t>(c.size()), use_gpu == "wait" ? 1 : 0, &dev, &sharers) == CVX_OK) {
+        setenv("CUDA_DEVICE_ORDER", "PCI_BUS_ID", 1);
+        setenv("CUDA_VISIBLE_DEVICES", std::to_string(dev).c_str(), 1);
+        if (sharers == 0) CVX_LOG("Selected GPU " << dev << " (" << ids[dev] << ": free; held for this job)");
+        else CVX_LOG("All " << ids.size() << " GPUs are in use by other jobs; sharing GPU " << dev << " (" << ids[dev] << ") with "
+                            << sharers << " other job(s)");
+        return 0;  // the only device CUDA will see
+      }
+    }
+  }
   if (cvx_acquire_device(use_gpu == "wait" ? 1 : 0, &dev, &sharers) != CVX_OK)
     throw KaldiError(std::string("selecting a GPU: ") + cvx_last_error());
   if (sharers == 0) CVX_LOG("Selected GPU " << dev << " (free; held for this job)");

@@ -14,6 +14,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <cctype>
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
@@ -27,10 +28,25 @@
 #include "api_error.h"
 
 namespace cvx {
+std::string NormalizeDeviceId(const std::string& id);
 namespace {
 
 constexpr int kMaxSharers = 64;
 int g_lock_fd = -1;  // held until the process exits (the kernel drops the lock with the descriptor)
+
+}  // namespace
+
+// "0000:1B:00.0" (CUDA) and "0000:1b:00.0" (/proc) name the same lock file
+std::string NormalizeDeviceId(const std::string& id_in) {
+  std::string id = id_in;
+  for (char& c : id) {
+    if (c == ':' || c == '/') c = '_';
+    else c = static_cast<char>(std::tolower(static_cast<unsigned char>(c)));
+  }
+  return id;
+}
+
+namespace {
 
 std::string LockDir() {
   const char* e = std::getenv("CVX_LOCK_DIR");
@@ -92,15 +108,27 @@ int cvx_acquire_device(int32_t wait, int32_t* device, int32_t* sharers) {
   for (int d = 0; d < n; ++d) {
     char buf[32] = {0};
     if (cudaDeviceGetPCIBusId(buf, sizeof(buf), d) != cudaSuccess) std::snprintf(buf, sizeof(buf), "ordinal%d", d);
-    std::string id(buf);
-    for (char& c : id)
-      if (c == ':' || c == '/') c = '_';
-    ids.push_back(id);
+    ids.push_back(cvx::NormalizeDeviceId(buf));
   }
   int32_t dev = 0, sh = 0;
   int rc = cvx::AcquireLock(cvx::LockDir(), ids, wait != 0, &dev, &sh);
   if (rc != CVX_OK) return cvx::SetApiError(rc, "cvx_acquire_device: could not take a device lock");
   *device = dev;
+  if (sharers) *sharers = sh;
+  return CVX_OK;
+}
+
+int cvx_acquire_device_by_id(const char* const* ids, int32_t num_ids, int32_t wait, int32_t* index, int32_t* sharers) {
+  if (!ids || num_ids <= 0 || !index) return cvx::SetApiError(CVX_ERR_INVALID, "cvx_acquire_device_by_id: bad argument");
+  std::vector<std::string> names;
+  for (int32_t i = 0; i < num_ids; ++i) {
+    if (!ids[i]) return cvx::SetApiError(CVX_ERR_INVALID, "cvx_acquire_device_by_id: NULL id");
+    names.push_back(cvx::NormalizeDeviceId(ids[i]));
+  }
+  int32_t dev = 0, sh = 0;
+  int rc = cvx::AcquireLock(cvx::LockDir(), names, wait != 0, &dev, &sh);
+  if (rc != CVX_OK) return cvx::SetApiError(rc, "cvx_acquire_device_by_id: could not take a device lock");
+  *index = dev;
   if (sharers) *sharers = sh;
   return CVX_OK;
 }

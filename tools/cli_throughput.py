@@ -43,7 +43,7 @@ with open(ark, "wb") as f, open(scp, "w") as s, open(os.path.join(d, "utt2num_fr
         f.write(rng.standard_normal((int(T), 23), dtype=np.float32).tobytes())
 frames = int(lengths.sum())
 exe = os.path.join(cvx.BIN_DIR, "nnet3-xvector-compute")
-common = ["--use-gpu=yes", "--min-chunk-size=25", "--chunk-size=10000", "--output-node=tdnn6_xvec.affine"]
+common = ["--use-gpu=yes", "--verbose=1", "--min-chunk-size=25", "--chunk-size=10000", "--output-node=tdnn6_xvec.affine"]
 
 
 def report(label, dt, stderr):
@@ -59,6 +59,9 @@ def run(label, out, extra, feat):
     dt = time.perf_counter() - t0
     assert r.returncode == 0, r.stderr[-2000:]
     report(label, dt, r.stderr)
+    for ln in r.stderr.splitlines():
+        if "lane timing" in ln or "Selected GPU" in ln:
+            print("     " + ln.split(") ", 1)[-1], flush=True)
 
 
 def same(a, b):
@@ -69,6 +72,8 @@ def same(a, b):
 run("ark file", "x_ark", ["--gpu-id=0"], f"ark:{ark}")
 run("scp (same file)", "x_scp", ["--gpu-id=0"], f"scp:{scp}")
 run("ark through a pipe (cat)", "x_pipe", ["--gpu-id=0"], f"ark:cat {ark} |")
+run("scp, --readers-per-gpu=2", "x_scp2", ["--gpu-id=0", "--readers-per-gpu=2"], f"scp:{scp}")
+run("scp, automatic GPU selection", "x_auto", [], f"scp:{scp}")
 run("scp, sliding CMN on the GPU (raw mode)", "x_raw", ["--gpu-id=0", "--cmn-window=300"], f"scp:{scp}")
 print("scp == ark:", same("x_scp", "x_ark"), flush=True)
 if num_gpus > 1:
