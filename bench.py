@@ -219,7 +219,7 @@ def cli_leg(wl: Workload, host_feats, out_ref: np.ndarray, local_rank: int, mods
             for r in range(CLI_REPLICAS):
                 sf.writelines(lines[r])
         exe = os.path.join(cvx.BIN_DIR, "nnet3-xvector-compute")
-        cmd = [exe, "--use-gpu=yes", f"--gpu-id={local_rank}", "--readers-per-gpu=2", f"--min-chunk-size={MIN_CHUNK_SIZE}",
+        cmd = [exe, "--use-gpu=yes", f"--gpu-id={local_rank}", f"--min-chunk-size={MIN_CHUNK_SIZE}",
                f"--chunk-size={wl.chunk_size}", f"--output-node={wl.node}", wl.model_path, f"scp:{scp}",
                f"ark,scp:{d}/xvector.ark,{d}/xvector.scp"]
         barrier()
@@ -400,7 +400,7 @@ def main() -> None:
                    "in_loop_value": (cli_audio / cli_loop) if cli_loop > 0 else None, "in_loop_s": cli_loop,
                    "utts_per_gpu": wl.n_utts * CLI_REPLICAS, "frames_per_gpu": total_rows * CLI_REPLICAS,
                    "startup_s": cli_wall - cli_loop,
-                   "what": "bin/nnet3-xvector-compute --use-gpu=yes --gpu-id=<rank> --readers-per-gpu=2 --chunk-size=.. model scp:<table over an archive in page cache> "
+                   "what": "bin/nnet3-xvector-compute --use-gpu=yes --gpu-id=<rank> --chunk-size=.. model scp:<table over an archive in page cache> "
                            "ark,scp:..; one process per GPU on its shard listed 4 times (the recipe's nj jobs), wall clock of the slowest process "
                            "incl. CUDA context + model load + engine build (startup_s); in_loop = the program's own 'Time taken' line",
                    "ark_bytes_per_gpu": c["ark_bytes"], "matches_c_abi_output": all_same}

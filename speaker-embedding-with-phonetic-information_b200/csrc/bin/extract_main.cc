@@ -161,7 +161,7 @@ struct LaneResult {
   int64_t num_success = 0, num_fail = 0, frame_count = 0;
   std::string error;
   // where the lane's wall time went (logged with --verbose=1)
-  double setup_s = 0, gpu_wait_s = 0, extract_s = 0, total_s = 0;
+  double setup_s = 0, gpu_wait_s = 0, extract_s = 0, device_s = 0, total_s = 0, first_call_s = 0, max_call_s = 0;
   int64_t calls = 0;
 };
 
@@ -224,7 +224,7 @@ int ExtractMain(int argc, const char* const* argv, bool multiple_input) {
     std::string mean_vec, transform_mat;
     bool normalize_length = false, scaleup = true;
     int32_t chunk_size = -1, min_chunk_size = 100, gpu_id = -1, cmn_window = 0, min_cmn_window = 100, num_gpus = 1;
-    int32_t readers_per_gpu = 1;
+
     bool cmn_center = true, cmn_norm_vars = false;
     int64_t batch_rows = 1 << 20, max_batch_rows = 0;
     bool pad_input = false, profile = false, check_saturation = false;
@@ -253,10 +253,6 @@ int ExtractMain(int argc, const char* const* argv, bool multiple_input) {
                 "Use this many GPUs (devices gpu-id .. gpu-id + num-gpus - 1) from ONE process, one engine per GPU. "
                 "scp inputs: one reader thread per GPU over a length-balanced share of the table; archive / pipe "
                 "inputs: row batches go to the GPUs in turn.  Output order is the table's either way");
-    po.Register("readers-per-gpu", &readers_per_gpu,
-                "scp inputs: reader lanes (reader thread + pinned batches + engine) per GPU.  One reader copies ~4-6 GB/s "
-                "out of the page cache, about what ONE B200 consumes on the c-vector net; 2 keeps the GPU busy on the "
-                "x-vector nets and on compressed archives");
     po.Register("shard", &shard_spec,
                 "J/N: process only the J-th (1-based, like JOB) of N length-balanced shards of the feature table "
                 "(greedy LPT over frame counts; replaces utils/split_data.sh)");
@@ -334,7 +330,6 @@ int ExtractMain(int argc, const char* const* argv, bool multiple_input) {
       CVX_WARN("--chunk-size=" << chunk_size << " is below --min-chunk-size=" << min_chunk_size
                                << ": with --pad-input=true every chunk is padded to the minimum size");
     if (num_gpus < 1) throw KaldiError("--num-gpus must be >= 1");
-    if (readers_per_gpu < 1 || readers_per_gpu > 8) throw KaldiError("--readers-per-gpu must be in 1..8");
     const std::pair<int32_t, int32_t> shard = ParseShard(shard_spec);
     gpu_id = ChooseDevice(gpu_id, use_gpu, num_gpus);
 
@@ -393,9 +388,10 @@ int ExtractMain(int argc, const char* const* argv, bool multiple_input) {
       scp_input = scp_input && feat_specs.back().is_scp;
     }
     if (!vad_rspecifier.empty()) scp_input = scp_input && ParseRspecifier(vad_rspecifier).is_scp;
-    const int num_lanes = (scp_input && num_gpus * readers_per_gpu > 1) ? num_gpus * readers_per_gpu : 1;
-    const int lanes_per_gpu = num_lanes > 1 ? readers_per_gpu : 1;
-    const int num_engines = num_lanes > 1 ? num_lanes : num_gpus;
+    // (More than one lane per GPU was tried and dropped: a second engine's pinned-buffer allocations and
+    // device-wide frees stall the first one's CUDA calls for hundreds of ms.)
+    const int num_lanes = (scp_input && num_gpus > 1) ? num_gpus : 1;
+    const int num_engines = num_gpus;
     const int32_t num_bins = shard.second * num_lanes;
     std::unordered_map<std::string, int32_t> bin_of;
     if (num_bins > 1) {
@@ -418,8 +414,7 @@ int ExtractMain(int argc, const char* const* argv, bool multiple_input) {
       for (int g = 0; g < num_engines; ++g)
         th.emplace_back([&, g] {
           cvx_engine_options o = eo;
-          const int dev = gpu_id + g / lanes_per_gpu;  // lanes of one GPU are neighbours
-          o.device = wrap_devices ? dev % ndev : dev;
+          o.device = wrap_devices ? (gpu_id + g) % ndev : gpu_id + g;
           if (cvx_engine_create(model, &o, &engines[g]) != CVX_OK) errs[g] = cvx_last_error();
         });
       for (std::thread& t : th) t.join();
@@ -494,6 +489,7 @@ int ExtractMain(int argc, const char* const* argv, bool multiple_input) {
         int status = CVX_OK;
         std::string error;
         double seconds = 0;  // inside cvx_extract
+        double device_ms = 0;
       };
       std::deque<std::unique_ptr<Job>> inflight;
       struct Joiner {
@@ -514,6 +510,9 @@ int ExtractMain(int argc, const char* const* argv, bool multiple_input) {
         job->th.join();
         res->gpu_wait_s += since(tw);
         res->extract_s += job->seconds;
+        res->device_s += job->device_ms * 1e-3;
+        if (res->calls == 0) res->first_call_s = job->seconds;
+        res->max_call_s = std::max(res->max_call_s, job->seconds);
         res->calls += 1;
         if (job->status != CVX_OK) throw KaldiError("cvx_extract failed: " + job->error);
         HostBatch& b = hb[job->batch];
@@ -550,6 +549,7 @@ int ExtractMain(int argc, const char* const* argv, bool multiple_input) {
                                      static_cast<int32_t>(w.keys.size()), w.out, 0);
           if (jp->status != CVX_OK) jp->error = cvx_last_error();
           jp->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - tj).count();
+          jp->device_ms = cvx_engine_last_extract_ms(eng);
         });
         inflight.push_back(std::move(job));
         const int next = free_batches.back();
@@ -721,7 +721,8 @@ int ExtractMain(int argc, const char* const* argv, bool multiple_input) {
       if (po.verbose >= 1)
         CVX_LOG("lane timing: " << res->total_s << " s = " << res->setup_s << " s waiting for pinned buffers + readers, "
                                 << res->gpu_wait_s << " s blocked on the GPU, the rest reading / packing; " << res->calls
-                                << " cvx_extract calls took " << res->extract_s << " s");
+                                << " cvx_extract calls took " << res->extract_s << " s (first " << res->first_call_s << " s, longest "
+                                << res->max_call_s << " s), of which " << res->device_s << " s between the engine's CUDA events");
     };
 
     VectorWriter writer(vector_wspecifier);
@@ -791,7 +792,7 @@ int ExtractMain(int argc, const char* const* argv, bool multiple_input) {
       int32_t n = 0;
       cvx_engine_get_profile(engines[g], recs, 16, &n);
       for (int32_t i = 0; i < n; ++i)
-        CVX_LOG("profile engine" << g << " (gpu " << (gpu_id + g / lanes_per_gpu) << ") " << recs[i].name << ": launches=" << recs[i].launches
+        CVX_LOG("profile gpu" << (gpu_id + g) << " " << recs[i].name << ": launches=" << recs[i].launches
                               << " ms=" << recs[i].total_ms
                               << (recs[i].flops > 0 ? " TFLOP/s=" + std::to_string(recs[i].flops / recs[i].total_ms * 1e-9) : "")
                               << (recs[i].bytes > 0 ? " GB/s=" + std::to_string(recs[i].bytes / recs[i].total_ms * 1e-6) : ""));

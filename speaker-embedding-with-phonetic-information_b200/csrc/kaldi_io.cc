@@ -5,6 +5,7 @@
 #include "kaldi_io.h"
 
 #include <sys/wait.h>
+#include <unistd.h>
 
 #include <cctype>
 #include <cerrno>
@@ -12,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <future>
 #include <iostream>
 
 namespace cvx {
@@ -114,6 +116,31 @@ int Input::Get() {
 void Input::Read(void* dst, size_t n) {
   unsigned char* d = static_cast<unsigned char*>(dst);
   while (n) {
+    if (pos_ >= end_ && n >= (size_t{1} << 20) && fp_ && !is_pipe_ && !is_stdin_) {
+      // large body from a file: two threads pread() one half each -- one thread copies ~4.5 GB/s out of
+      // the page cache, less than one B200 consumes on the c-vector net
+      const long off = std::ftell(fp_);
+      const int fd = fileno(fp_);
+      if (off >= 0 && fd >= 0) {
+        const size_t half = (n / 2) & ~size_t{4095};
+        auto pread_all = [fd](unsigned char* dst, size_t len, off_t at) -> bool {
+          while (len) {
+            ssize_t k = ::pread(fd, dst, len, at);
+            if (k <= 0) return false;
+            dst += k;
+            at += k;
+            len -= static_cast<size_t>(k);
+          }
+          return true;
+        };
+        std::future<bool> second = std::async(std::launch::async, pread_all, d + half, n - half, static_cast<off_t>(off) + static_cast<off_t>(half));
+        const bool ok1 = pread_all(d, half, off);
+        const bool ok2 = second.get();
+        if (!ok1 || !ok2) throw KaldiError("unexpected end of input in " + name_);
+        if (std::fseek(fp_, off + static_cast<long>(n), SEEK_SET) != 0) throw KaldiError("cannot seek in " + name_);
+        return;
+      }
+    }
     if (pos_ >= end_ && n >= buf_.size() && fp_) {
       // large body: read straight into the destination, bypassing the buffer
       size_t got = std::fread(d, 1, n, fp_);

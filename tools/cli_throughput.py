@@ -72,7 +72,6 @@ def same(a, b):
 run("ark file", "x_ark", ["--gpu-id=0"], f"ark:{ark}")
 run("scp (same file)", "x_scp", ["--gpu-id=0"], f"scp:{scp}")
 run("ark through a pipe (cat)", "x_pipe", ["--gpu-id=0"], f"ark:cat {ark} |")
-run("scp, --readers-per-gpu=2", "x_scp2", ["--gpu-id=0", "--readers-per-gpu=2"], f"scp:{scp}")
 run("scp, automatic GPU selection", "x_auto", [], f"scp:{scp}")
 run("scp, sliding CMN on the GPU (raw mode)", "x_raw", ["--gpu-id=0", "--cmn-window=300"], f"scp:{scp}")
 print("scp == ark:", same("x_scp", "x_ark"), flush=True)
