@@ -619,14 +619,6 @@ void Engine::RunFrames(const float* const* dev_feats, int64_t rows, int64_t src_
         a.tile_stream = s.taps[0].stream;
         a.off_min = lo;
         a.off_max = hi;
-        // every offset lo..hi, in order: the spliced row is one contiguous window of the feature array
-        bool window = static_cast<int32_t>(s.taps.size()) == hi - lo + 1;
-        for (size_t i = 0; window && i < s.taps.size(); ++i)
-          window = s.taps[i].offset == lo + static_cast<int32_t>(i) && s.taps[i].dim == plan_.input_dims[a.tile_stream] &&
-                   s.taps[i].col0 == static_cast<int32_t>(i) * s.taps[i].dim;
-        static const bool window_off = std::getenv("CVX_STAGE_WINDOW") && std::getenv("CVX_STAGE_WINDOW")[0] == '0';
-        a.window = window && !window_off ? 1 : 0;
-        a.window_width = (hi - lo + 1) * plan_.input_dims[a.tile_stream];
       }
     }
     a.out = buffers_[s.buffer].ptr;

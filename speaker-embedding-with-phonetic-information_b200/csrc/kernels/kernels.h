@@ -143,10 +143,6 @@ struct StageArgs {
   // tiled fast path: every mapped column reads stream `tile_stream` at offsets in [off_min, off_max]
   int32_t tile_stream;               // -1: generic gather
   int32_t off_min, off_max;
-  // window fast path: the taps are ALL offsets off_min..off_max of stream tile_stream in ascending order,
-  // so (rows being contiguous) output row r is just the contiguous window flat[(r + off_min) * dim, + width)
-  int32_t window;                    // 0: off
-  int32_t window_width;              // (off_max - off_min + 1) * dim
 };
 cudaError_t LaunchStageInput(const StageArgs& args, cudaStream_t stream);
 

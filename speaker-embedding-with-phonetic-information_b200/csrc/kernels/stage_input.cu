@@ -134,53 +134,10 @@ __global__ void __launch_bounds__(256) stage_input_tiled_kernel(const __grid_con
   }
 }
 
-// Window variant for the recipes' first-layer splice Append(input@-2 .. input@2): with contiguous feature
-// rows the spliced operand row r IS the contiguous window [(r + off_min) * dim, + taps * dim) of the flat
-// feature array, so staging is a sliding-window copy + conversion: no shared memory, no barrier; a thread
-// converts 8 consecutive columns (one 16-byte store), neighbouring rows overlap in L1.
-template <typename T>
-__global__ void __launch_bounds__(256) stage_input_window_kernel(const __grid_constant__ StageArgs args) {
-  constexpr int kVec = 16 / sizeof(T);
-  const int groups = args.ld_out / kVec;
-  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const int64_t row = idx / groups;
-  if (row >= args.rows) return;
-  const int c0 = static_cast<int>(idx - row * groups) * kVec;
-  const int dim = args.feat_dim[args.tile_stream];
-  const float* __restrict__ src = args.feats[args.tile_stream];
-  const int64_t base = (row + args.off_min) * dim + c0;
-  const int64_t lo = args.src_row_min * dim, hi = args.src_row_max * dim;
-  float v[kVec];
-#pragma unroll
-  for (int e = 0; e < kVec; ++e) {
-    const int64_t g = base + e;
-    v[e] = (c0 + e < args.window_width && g >= lo && g < hi) ? __ldg(src + g) : 0.f;
-  }
-  uint4 packed;
-  if constexpr (sizeof(T) == 4) {
-    packed = make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
-  } else {
-    uint32_t w[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) w[e] = pack_pair<T>(v[2 * e], v[2 * e + 1]);
-    packed = make_uint4(w[0], w[1], w[2], w[3]);
-  }
-  *reinterpret_cast<uint4*>(static_cast<T*>(args.out) + row * args.ld_out + c0) = packed;
-}
-
 }  // namespace
 
 cudaError_t LaunchStageInput(const StageArgs& args, cudaStream_t stream) {
   if (args.rows <= 0) return cudaSuccess;
-  if (args.tile_stream >= 0 && args.window) {
-    const int vec = 16 / static_cast<int>(ElemSize(args.elem));
-    const int64_t total = args.rows * (args.ld_out / vec);
-    const unsigned grid = static_cast<unsigned>((total + 255) / 256);
-    if (args.elem == kF16) stage_input_window_kernel<__half><<<grid, 256, 0, stream>>>(args);
-    else if (args.elem == kBF16) stage_input_window_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(args);
-    else stage_input_window_kernel<float><<<grid, 256, 0, stream>>>(args);
-    return cudaGetLastError();
-  }
   if (args.tile_stream >= 0) {
     const unsigned tgrid = static_cast<unsigned>((args.rows + kStageTileRows - 1) / kStageTileRows);
     const size_t tsmem = static_cast<size_t>(args.ld_out) * 4 +
