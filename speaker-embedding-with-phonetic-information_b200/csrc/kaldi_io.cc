@@ -12,8 +12,10 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
 #include <fstream>
-#include <future>
+#include <mutex>
+#include <thread>
 #include <iostream>
 
 namespace cvx {
@@ -34,6 +36,82 @@ void LogMessage(const char* severity, const char* func, const char* file, int li
 }
 
 // ---------------------------------------------------------------- Input ----
+
+namespace {
+
+bool PreadAll(int fd, unsigned char* dst, size_t len, off_t at) {
+  while (len) {
+    ssize_t k = ::pread(fd, dst, len, at);
+    if (k <= 0) return false;
+    dst += k;
+    at += k;
+    len -= static_cast<size_t>(k);
+  }
+  return true;
+}
+
+// One helper thread per reader thread (thread_local): reads the second half of a large matrix body
+// while its owner reads the first.  A persistent thread, because a table has thousands of entries and
+// starting a thread per entry costs a fifth of the read itself.
+class PreadHelper {
+ public:
+  ~PreadHelper() {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      stop_ = true;
+    }
+    cv_.notify_all();
+    if (th_.joinable()) th_.join();
+  }
+  void Start(int fd, unsigned char* dst, size_t len, off_t at) {
+    if (!th_.joinable()) th_ = std::thread([this] { Run(); });
+    std::lock_guard<std::mutex> lk(mu_);
+    fd_ = fd, dst_ = dst, len_ = len, at_ = at;
+    pending_ = true;
+    done_ = false;
+    cv_.notify_all();
+  }
+  bool Wait() {
+    std::unique_lock<std::mutex> lk(mu_);
+    cv_.wait(lk, [&] { return done_; });
+    return ok_;
+  }
+
+ private:
+  void Run() {
+    std::unique_lock<std::mutex> lk(mu_);
+    while (true) {
+      cv_.wait(lk, [&] { return pending_ || stop_; });
+      if (stop_) return;
+      pending_ = false;
+      const int fd = fd_;
+      unsigned char* dst = dst_;
+      const size_t len = len_;
+      const off_t at = at_;
+      lk.unlock();
+      const bool ok = PreadAll(fd, dst, len, at);
+      lk.lock();
+      ok_ = ok;
+      done_ = true;
+      cv_.notify_all();
+    }
+  }
+  std::thread th_;
+  std::mutex mu_;
+  std::condition_variable cv_;
+  bool pending_ = false, done_ = false, ok_ = false, stop_ = false;
+  int fd_ = -1;
+  unsigned char* dst_ = nullptr;
+  size_t len_ = 0;
+  off_t at_ = 0;
+};
+
+PreadHelper& ThreadPreadHelper() {
+  thread_local PreadHelper helper;
+  return helper;
+}
+
+}  // namespace
 
 static std::string Trim(const std::string& s) {
   size_t a = 0, b = s.size();
@@ -123,19 +201,10 @@ void Input::Read(void* dst, size_t n) {
       const int fd = fileno(fp_);
       if (off >= 0 && fd >= 0) {
         const size_t half = (n / 2) & ~size_t{4095};
-        auto pread_all = [fd](unsigned char* dst, size_t len, off_t at) -> bool {
-          while (len) {
-            ssize_t k = ::pread(fd, dst, len, at);
-            if (k <= 0) return false;
-            dst += k;
-            at += k;
-            len -= static_cast<size_t>(k);
-          }
-          return true;
-        };
-        std::future<bool> second = std::async(std::launch::async, pread_all, d + half, n - half, static_cast<off_t>(off) + static_cast<off_t>(half));
-        const bool ok1 = pread_all(d, half, off);
-        const bool ok2 = second.get();
+        PreadHelper& helper = ThreadPreadHelper();  // this reader thread's persistent second reader
+        helper.Start(fd, d + half, n - half, static_cast<off_t>(off) + static_cast<off_t>(half));
+        const bool ok1 = PreadAll(fd, d, half, off);
+        const bool ok2 = helper.Wait();
         if (!ok1 || !ok2) throw KaldiError("unexpected end of input in " + name_);
         if (std::fseek(fp_, off + static_cast<long>(n), SEEK_SET) != 0) throw KaldiError("cannot seek in " + name_);
         return;
