@@ -431,6 +431,8 @@ void Engine::EncodeMaps() {
     // first layers (K <= 128): weight half-tiles stay in shared memory for the whole launch
     a.resident_b = a.num_kb <= 2 ? 1 : 0;
     if (const char* env = std::getenv("CVX_RESIDENT_W")) a.resident_b = a.resident_b && env[0] != '0';
+    a.wide_epilogue = 1;
+    if (const char* env = std::getenv("CVX_WIDE_EPILOGUE")) a.wide_epilogue = env[0] != '0';
     BuildHaloArgs(op);
   }
 }

@@ -67,6 +67,7 @@ struct TdnnGemmArgs {
   // keeps ONE tile column for the whole launch and loads its weight half-tiles once instead of with
   // every tile -- a quarter of the bytes such a tile moves through the SM
   int32_t resident_b;
+  int32_t wide_epilogue;  // with resident_b: run the 16-epilogue-warp variant (tuning aid: CVX_WIDE_EPILOGUE=0 turns it off)
 };
 
 size_t TdnnGemmSmemBytes();

@@ -25,31 +25,39 @@
 namespace cvx {
 namespace {
 
-constexpr int kStages = 6;
 constexpr int kABytes = kGemmBlockM * kGemmBlockK * 2;        // 16 KB: 128 rows of this CTA
 constexpr int kBBytes = (kGemmBlockN / 2) * kGemmBlockK * 2;  // 16 KB: this CTA's half of W
 constexpr int kCWarpBytes = 32 * 128;
-constexpr int kSmemA = 0;
-constexpr int kSmemB = kSmemA + kStages * kABytes;      // 98304
-constexpr int kSmemC = kSmemB + kStages * kBBytes;      // 196608
-constexpr int kSmemPost = kSmemC + 8 * kCWarpBytes;     // 229376
-constexpr int kSmemBars = kSmemPost + kGemmBlockN * 8;  // 231424
-constexpr int kNumBars = 2 * kStages + 5;
-constexpr int kSmemTmemPtr = kSmemBars + kNumBars * 8;  // 231552
-constexpr int kSmemTotal = kSmemTmemPtr + 32;           // 231584 <= 232448
 constexpr int kTmemCols = 512;
-// Epilogue warps: 8 (two per TMEM lane quarter, 64-column chunks) for the storing variants.  The
-// fused-pooling epilogue is latency-bound (tcgen05.ld -> convert -> smem transpose -> dependent
-// FHADD/FHFMA chains; ncu r2: ~5 600 cycles per 128 x 256 tile with two warps per scheduler, issue
-// slots 40 % used), so it runs 16 warps (four per quarter) on 32-column units with half the
-// per-warp staging buffer each.
-template <bool kPool>
+// Epilogue warps: 8 (two per TMEM lane quarter, 64-column chunks) for the ordinary storing variant.
+// kPool: the fused-pooling epilogue is latency-bound (tcgen05.ld -> convert -> smem transpose ->
+// dependent FHADD/FHFMA chains; ncu r2: ~5 600 cycles per 128 x 256 tile with two warps per
+// scheduler, issue slots 40 % used), so it runs 16 warps (four per quarter) on 32-column units with
+// half the per-warp staging buffer each.
+// kWide: the first TDNN layers (K <= 128: two K blocks, weights resident) are all epilogue -- 1 024
+// MMA cycles per tile against ~2 900 cycles of TMEM -> convert -> staging -> TMA store, again
+// latency-bound with two warps per scheduler (issue slots 32 % used, and slower in the sustained
+// bench than under ncu exactly by the SM clock ratio).  They run 16 epilogue warps, one 64-column chunk
+// each, with 4 KB staging buffers paid for by a 4-stage ring (they only ever have 2 K blocks in flight).
+template <bool kPool, bool kWide>
 struct PairCfg {
-  static constexpr int kEpiWarps = kPool ? 16 : 8;
+  static_assert(!(kPool && kWide), "one or the other");
+  static constexpr int kStages = kWide ? 4 : 6;
+  static constexpr int kEpiWarps = (kPool || kWide) ? 16 : 8;
   static constexpr int kEpiThreads = 32 * kEpiWarps;
   static constexpr int kThreads = 64 + kEpiThreads;
-  static constexpr int kParts = kEpiWarps / 4;       // warps sharing one TMEM lane quarter
-  static constexpr int kWarpBuf = 8 * kCWarpBytes / kEpiWarps;  // bytes of smem_c per warp
+  static constexpr int kParts = kEpiWarps / 4;                  // warps sharing one TMEM lane quarter
+  static constexpr int kWarpBuf = kPool ? kCWarpBytes / 2 : kCWarpBytes;  // bytes of smem_c per warp
+  static constexpr int kSmemA = 0;
+  static constexpr int kSmemB = kSmemA + kStages * kABytes;
+  static constexpr int kSmemC = kSmemB + kStages * kBBytes;
+  static constexpr int kSmemPost = kSmemC + kEpiWarps * kWarpBuf;
+  static constexpr int kSmemBars = kSmemPost + kGemmBlockN * 8;
+  static constexpr int kNumBars = 2 * kStages + 5;
+  static constexpr int kSmemTmemPtr = kSmemBars + kNumBars * 8;
+  static constexpr int kSmemTotal = kSmemTmemPtr + 32;
+  static_assert(kSmemB % 1024 == 0 && kSmemC % 1024 == 0, "swizzle alignment");
+  static_assert(kSmemTotal <= 232448, "shared memory budget");
 };
 
 template <bool kBF16>
@@ -80,12 +88,14 @@ __device__ __forceinline__ void accum16(uint16_t x, float& sx, float& sxx) {
 // operand type (as if stored) and reduces sum x / sum x^2 over the valid rows of each 32-row
 // group (PoolGroupMeta) into per-slot partials through a swizzled smem transpose; the
 // [rows, 1500] activation is never written.
-template <bool kBF16, bool kOutF32, bool kPool>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairCfg<kPool>::kThreads, 1)
+template <bool kBF16, bool kOutF32, bool kPool, bool kWide = false>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairCfg<kPool, kWide>::kThreads, 1)
     tdnn_gemm_pair_kernel(const __grid_constant__ TdnnGemmArgs args) {
-  using Cfg = PairCfg<kPool>;
+  using Cfg = PairCfg<kPool, kWide>;
   constexpr int kEpilogueThreads = Cfg::kEpiThreads;
   constexpr int kEpilogueWarps = Cfg::kEpiWarps;
+  constexpr int kStages = Cfg::kStages, kSmemA = Cfg::kSmemA, kSmemB = Cfg::kSmemB, kSmemC = Cfg::kSmemC,
+                kSmemPost = Cfg::kSmemPost, kSmemBars = Cfg::kSmemBars, kSmemTmemPtr = Cfg::kSmemTmemPtr;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* smem_a = smem + kSmemA;
   uint8_t* smem_b = smem + kSmemB;
@@ -343,26 +353,43 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairCfg<kPool>::kThr
 
 }  // namespace
 
-cudaError_t LaunchTdnnGemmPair(const TdnnGemmArgs& args, int num_sms, cudaStream_t stream) {
-  const bool bf16 = args.ab_format == 1;
-  auto kern = args.pool_meta ? (bf16 ? tdnn_gemm_pair_kernel<true, false, true> : tdnn_gemm_pair_kernel<false, false, true>)
-              : args.out_f32 ? (bf16 ? tdnn_gemm_pair_kernel<true, true, false> : tdnn_gemm_pair_kernel<false, true, false>)
-                             : (bf16 ? tdnn_gemm_pair_kernel<true, false, false> : tdnn_gemm_pair_kernel<false, false, false>);
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
+namespace {
+template <typename Kern>
+cudaError_t LaunchPair(Kern kern, int threads, int smem, int stages, const TdnnGemmArgs& args, int num_sms, cudaStream_t stream) {
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
   const int tiles = ((args.num_m_tiles + 1) / 2) * args.num_n_tiles;
   if (tiles <= 0) return cudaSuccess;
   int clusters = tiles < num_sms / 2 ? tiles : num_sms / 2;
   if (args.resident_b) {
-    if (args.num_kb > kStages) return cudaErrorInvalidValue;
+    if (args.num_kb > stages) return cudaErrorInvalidValue;
     // a pair must keep its tile column: the stride over tiles is a multiple of the column count
     // (tiles itself is one, so at least num_n_tiles pairs remain)
     clusters = clusters / args.num_n_tiles * args.num_n_tiles;
     if (clusters == 0) clusters = args.num_n_tiles;
   }
-  const int threads = args.pool_meta ? PairCfg<true>::kThreads : PairCfg<false>::kThreads;
-  kern<<<2 * clusters, threads, kSmemTotal, stream>>>(args);
+  kern<<<2 * clusters, threads, smem, stream>>>(args);
   return cudaGetLastError();
+}
+}  // namespace
+
+cudaError_t LaunchTdnnGemmPair(const TdnnGemmArgs& args, int num_sms, cudaStream_t stream) {
+  const bool bf16 = args.ab_format == 1;
+  using Pool = PairCfg<true, false>;
+  using Wide = PairCfg<false, true>;
+  using Plain = PairCfg<false, false>;
+  if (args.pool_meta)
+    return bf16 ? LaunchPair(tdnn_gemm_pair_kernel<true, false, true>, Pool::kThreads, Pool::kSmemTotal, Pool::kStages, args, num_sms, stream)
+                : LaunchPair(tdnn_gemm_pair_kernel<false, false, true>, Pool::kThreads, Pool::kSmemTotal, Pool::kStages, args, num_sms, stream);
+  if (args.out_f32)
+    return bf16 ? LaunchPair(tdnn_gemm_pair_kernel<true, true, false>, Plain::kThreads, Plain::kSmemTotal, Plain::kStages, args, num_sms, stream)
+                : LaunchPair(tdnn_gemm_pair_kernel<false, true, false>, Plain::kThreads, Plain::kSmemTotal, Plain::kStages, args, num_sms, stream);
+  // first layers (resident weights, at most two K blocks): the 16-warp epilogue variant
+  if (args.resident_b && args.wide_epilogue && args.num_kb <= Wide::kStages)
+    return bf16 ? LaunchPair(tdnn_gemm_pair_kernel<true, false, false, true>, Wide::kThreads, Wide::kSmemTotal, Wide::kStages, args, num_sms, stream)
+                : LaunchPair(tdnn_gemm_pair_kernel<false, false, false, true>, Wide::kThreads, Wide::kSmemTotal, Wide::kStages, args, num_sms, stream);
+  return bf16 ? LaunchPair(tdnn_gemm_pair_kernel<true, false, false>, Plain::kThreads, Plain::kSmemTotal, Plain::kStages, args, num_sms, stream)
+              : LaunchPair(tdnn_gemm_pair_kernel<false, false, false>, Plain::kThreads, Plain::kSmemTotal, Plain::kStages, args, num_sms, stream);
 }
 
 }  // namespace cvx
