@@ -76,6 +76,40 @@ def test_device_locks_spread_concurrent_jobs(cvx, tmp_path):
                 p.wait(timeout=30)
 
 
+_HOLDER_BY_ID = r"""
+import ctypes as C, importlib, os, sys
+sys.path.insert(0, {root!r})
+os.environ["CVX_LOCK_DIR"] = {dir!r}
+cvx = importlib.import_module({pkg!r})
+lib = cvx.load_library()
+ids = {ids!r}
+arr = (C.c_char_p * len(ids))(*[i.encode() for i in ids])
+lib.cvx_acquire_device_by_id.argtypes = [C.POINTER(C.c_char_p), C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+d, s = C.c_int32(-1), C.c_int32(-1)
+rc = lib.cvx_acquire_device_by_id(arr, len(ids), 0, C.byref(d), C.byref(s))
+print(rc, d.value, s.value, flush=True)
+sys.stdin.readline()
+"""
+
+
+def test_pre_cuda_selection_shares_lock_names_with_cuda_enumeration(cvx, tmp_path):
+    """a job that picks its GPU from /proc's PCI ids before initialising CUDA (lower-case hex) and one that
+    enumerates through CUDA (upper-case hex) must exclude each other on the same device."""
+    procs, got = [], []
+    try:
+        for ids in (["0000:1b:00.0", "0000:2c:00.0"], ["0000:1B:00.0", "0000:2C:00.0"], ["0000:1b:00.0", "0000:2c:00.0"]):
+            code = _HOLDER_BY_ID.format(root=ROOT, pkg=cvx.__name__, dir=str(tmp_path), ids=ids)
+            p = subprocess.Popen([sys.executable, "-c", code], stdin=subprocess.PIPE, stdout=subprocess.PIPE, text=True)
+            procs.append(p)
+            got.append(tuple(map(int, p.stdout.readline().split())))
+        assert got == [(0, 0, 0), (0, 1, 0), (0, 0, 1)]
+    finally:
+        for p in procs:
+            if p.poll() is None:
+                p.stdin.write("\n"); p.stdin.flush()
+                p.wait(timeout=30)
+
+
 def test_ivector_mean_writes_text_by_default(cvx, kf, tmp_path):
     """upstream's option is --binary-write with default false; --binary stays as an alias."""
     vecs = [(f"u{i}", np.arange(4, dtype=np.float32) + i) for i in range(3)]
