@@ -9,9 +9,6 @@
 
 namespace cvx {
 
-struct UnsupportedError : public std::runtime_error {
-  using std::runtime_error::runtime_error;
-};
 struct FormatError : public std::runtime_error {
   using std::runtime_error::runtime_error;
 };

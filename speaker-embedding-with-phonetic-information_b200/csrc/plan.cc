@@ -1,6 +1,8 @@
 #include "plan.h"
 
 #include <algorithm>
+#include <climits>
+#include <cstdint>
 #include <sstream>
 #include <stdexcept>
 
@@ -25,10 +27,13 @@ void Plan::Finalize() {
     if (d <= 0) fail("input dim <= 0");
   if (frame.empty()) fail("no frame layers");
   const int32_t n_in = static_cast<int32_t>(input_dims.size());
+  // nnet3's own contexts (a layer all of whose taps look forward is computable BEFORE t = 0, one that
+  // only looks back AFTER t = T-1, and upstream computes such frames when a consumer asks for them)
+  std::vector<int32_t> true_left(frame.size(), 0), true_right(frame.size(), 0);
   for (size_t i = 0; i < frame.size(); ++i) {
     Layer& l = frame[i];
     if (l.taps.empty()) fail("frame layer " + l.name + " has no taps");
-    int32_t k = 0, left = 0, right = 0;
+    int32_t k = 0, left = 0, right = 0, tl = INT32_MIN, tr = INT32_MIN;
     for (const Tap& t : l.taps) {
       if (t.src >= static_cast<int32_t>(i) || t.src < -n_in) fail("frame layer " + l.name + ": bad tap source");
       k += SrcDim(t.src);
@@ -36,7 +41,11 @@ void Plan::Finalize() {
       // output t needs the source at t+offset: sl <= t+offset <= T-1-sr
       left = std::max(left, sl - t.offset);
       right = std::max(right, sr + t.offset);
+      tl = std::max(tl, (t.src >= 0 ? true_left[t.src] : 0) - t.offset);
+      tr = std::max(tr, (t.src >= 0 ? true_right[t.src] : 0) + t.offset);
     }
+    true_left[i] = tl;
+    true_right[i] = tr;
     // rows exist only for 0 <= t < T, so contexts never go negative
     l.left = std::max(left, 0);
     l.right = std::max(right, 0);
@@ -53,6 +62,19 @@ void Plan::Finalize() {
   } else {
     if (pool_src < 0 || pool_src >= static_cast<int32_t>(frame.size())) fail("pool_src out of range");
     if (pool_left_context < 0 || pool_right_context < 0) fail("negative pooling context");
+    // The packed layout holds rows 0 <= t < T of every layer, so a layer's context is clamped at 0.  Nothing is
+    // lost as long as the frames that reach the pooling are the ones upstream pools: the clamped chain must give
+    // the pooled layer the context nnet3 itself computes (window [0, right-context]: a negative LEFT context is
+    // harmless).  It does for every network of the recipes; it does not when a source whose taps all look
+    // forward (computable before t = 0) is tapped again backwards, or when the pooled layer only looks back
+    // (computable after the last input frame: upstream would pool those frames too).
+    const Layer& pl = frame[pool_src];
+    if (pl.left != std::max(true_left[pool_src], 0) || pl.right != true_right[pool_src])
+      throw UnsupportedError("the pooled layer " + pl.name + " is computable on frames [" + std::to_string(true_left[pool_src]) +
+                             ", T-1-(" + std::to_string(true_right[pool_src]) + ")] under nnet3's rules but only on [" +
+                             std::to_string(pl.left) + ", T-1-" + std::to_string(pl.right) +
+                             "] in a layout that holds frames 0..T-1 of every layer (some layer is needed before the first or "
+                             "after the last input frame); the recipes' networks have no such taps");
   }
   int32_t d = PooledDim();
   for (Layer& l : segment) {

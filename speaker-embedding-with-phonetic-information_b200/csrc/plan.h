@@ -5,10 +5,16 @@
 #define CVX_PLAN_H_
 
 #include <cstdint>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
 namespace cvx {
+
+// The graph uses something the packed-row execution model cannot represent (-> CVX_ERR_UNSUPPORTED).
+struct UnsupportedError : public std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
 
 struct Tap {
   int32_t src;     // >= 0: frame layer index; < 0: input stream (-1 - src)
@@ -51,7 +57,8 @@ struct Plan {
   }
   int64_t MacPerFrame() const;
   int64_t MacPerChunk() const;
-  // Validates indices/dims, fills Layer::left/right and `description`; throws std::runtime_error.
+  // Validates indices/dims, fills Layer::left/right and `description`; throws std::runtime_error, or
+  // UnsupportedError for a graph with frames outside the input's time range (see plan.cc).
   void Finalize();
 };
 

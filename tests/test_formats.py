@@ -146,3 +146,33 @@ def test_cpp_loader_tolerates_unknown_trailing_fields(cvx, kf, synth, tmp_path):
         p = str(tmp_path / f"x{int(binary)}.raw")
         kf.write_nnet3(p, m, binary)
         assert cvx.Model(p, "tdnn6.affine").info.embedding_dim == 8
+
+
+def test_forward_only_taps_are_refused_not_clamped(cvx, kf, synth, tmp_path):
+    """a layer whose taps all look forward is computable before t = 0 under nnet3's rules; tapped again
+    backwards, upstream uses those frames.  The packed layout cannot hold them: the loader refuses the
+    net (CVX_ERR_UNSUPPORTED) instead of silently pooling fewer frames (found by tests/test_gpu_fuzz.py)."""
+    rng = np.random.default_rng(1)
+    b = synth._Builder(rng)
+    b.input("input", 7)
+    b.relu_batchnorm_layer("a", 16, "input@1")                       # valid t in [-1, T-2]
+    b.relu_batchnorm_layer("b", 16, "Append(a@-1,a@1)")              # needs a(-1) at t = 0: computable upstream
+    b.stats_layer("stats", 0, 10000, "b")
+    b.relu_batchnorm_layer("seg", 8)
+    b.output_layer("output", 4)
+    kf.write_nnet3(str(tmp_path / "fwd.raw"), b.model(), True)
+    with pytest.raises(cvx.CvxError) as e:
+        cvx.Model(str(tmp_path / "fwd.raw"), "seg.affine")
+    assert e.value.code == -4 and "computable on frames [0, T-1-(2)]" in str(e.value), str(e.value)
+    # with a tap at 0 the first layer is computable exactly on the input's frames and all is well:
+    # a: left 1, right 0; b taps a@-1, a@1 -> left 2, right 1
+    b = synth._Builder(np.random.default_rng(1))
+    b.input("input", 7)
+    b.relu_batchnorm_layer("a", 16, "Append(input@-1,input@0)")
+    b.relu_batchnorm_layer("b", 16, "Append(a@-1,a@1)")
+    b.stats_layer("stats", 0, 10000, "b")
+    b.relu_batchnorm_layer("seg", 8)
+    b.output_layer("output", 4)
+    kf.write_nnet3(str(tmp_path / "bwd.raw"), b.model(), True)
+    m = cvx.Model(str(tmp_path / "bwd.raw"), "seg.affine")
+    assert (m.info.left_context, m.info.right_context) == (2, 1)
