@@ -223,7 +223,7 @@ def cli_leg(wl: Workload, host_feats, out_ref: np.ndarray, local_rank: int, mods
         # a free GPU through the lock files and makes it the only device its CUDA context sees
         # (a CUDA_VISIBLE_DEVICES restriction of this process is inherited and respected)
         env = {k: v for k, v in os.environ.items() if k != "CVX_DEVICE"}
-        cmd = [exe, "--use-gpu=yes", f"--min-chunk-size={MIN_CHUNK_SIZE}",
+        cmd = [exe, "--use-gpu=yes", "--verbose=1", f"--min-chunk-size={MIN_CHUNK_SIZE}",
                f"--chunk-size={wl.chunk_size}", f"--output-node={wl.node}", wl.model_path, f"scp:{scp}",
                f"ark,scp:{d}/xvector.ark,{d}/xvector.scp"]
         barrier()
@@ -232,18 +232,20 @@ def cli_leg(wl: Workload, host_feats, out_ref: np.ndarray, local_rank: int, mods
         wall = time.perf_counter() - t0
         if r.returncode != 0:
             raise RuntimeError("drop-in program failed: " + r.stderr[-2000:])
-        in_loop, picked = None, None
+        in_loop, picked, phases = None, None, []
         for ln in r.stderr.splitlines():
             if "Time taken" in ln:
                 in_loop = float(ln.split("Time taken")[1].split("s:")[0])
             if "Selected GPU" in ln or "sharing GPU" in ln:
                 picked = ln.split(") ", 1)[-1]
+            if "start-up:" in ln or "tear-down" in ln or "lane timing" in ln:
+                phases.append(ln.split(") ", 1)[-1])
         got = np.stack([v for _, v in kf.read_ark(f"{d}/xvector.ark")])
         same = bool(got.shape == (CLI_REPLICAS * out_ref.shape[0], out_ref.shape[1]) and
                     all(np.allclose(got[r * len(out_ref):(r + 1) * len(out_ref)], out_ref, rtol=1e-4, atol=1e-4)
                         for r in range(CLI_REPLICAS)))
         return {"wall_s": wall, "in_loop_s": in_loop, "matches_c_abi_output": same, "ark_bytes": os.path.getsize(ark),
-                "device": picked}
+                "device": picked, "phases": phases}
     finally:
         shutil.rmtree(d, ignore_errors=True)
 
@@ -411,7 +413,8 @@ def main() -> None:
                            "ark,scp:..; one process per GPU on its shard listed 4 times (the recipe's nj jobs), wall clock of the slowest process "
                            "incl. CUDA context + model load + engine build (startup_s); in_loop = the program's own 'Time taken' line",
                    "ark_bytes_per_gpu": c["ark_bytes"], "matches_c_abi_output": all_same,
-                   "device_selection": [g["device"] for g in gather({"device": c["device"]})]}
+                   "device_selection": [g["device"] for g in gather({"device": c["device"]})],
+                   "rank0_phases": c["phases"]}
 
     # ---- the other BASELINE configs, device-resident leg only ----------------------------
     other = None

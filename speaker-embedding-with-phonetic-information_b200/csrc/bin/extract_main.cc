@@ -331,11 +331,15 @@ int ExtractMain(int argc, const char* const* argv, bool multiple_input) {
                                << ": with --pad-input=true every chunk is padded to the minimum size");
     if (num_gpus < 1) throw KaldiError("--num-gpus must be >= 1");
     const std::pair<int32_t, int32_t> shard = ParseShard(shard_spec);
+    const auto t_proc = std::chrono::steady_clock::now();
+    auto since_start = [&]() { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t_proc).count(); };
     gpu_id = ChooseDevice(gpu_id, use_gpu, num_gpus);
+    const double t_device = since_start();
 
     cvx_model* model = nullptr;
     if (cvx_model_load(nnet_rxfilename.c_str(), output_node.empty() ? nullptr : output_node.c_str(), &model) != CVX_OK)
       throw KaldiError(std::string("reading ") + nnet_rxfilename + ": " + cvx_last_error());
+    const double t_model = since_start();
     cvx_model_info info;
     cvx_model_get_info(model, &info);
     if (po.verbose >= 1) CVX_LOG("extraction plan:\n" << cvx_model_describe(model));
@@ -422,6 +426,9 @@ int ExtractMain(int argc, const char* const* argv, bool multiple_input) {
         if (!e.empty()) throw KaldiError("creating the GPU engine: " + e);
     }
     cvx_engine* engine = engines[0];
+    if (po.verbose >= 1)
+      CVX_LOG("start-up: device selection " << t_device << " s, model load " << (t_model - t_device) << " s, CUDA context + "
+                                             << num_engines << " engine(s) " << (since_start() - t_model) << " s");
 
     if (!mean_vec.empty() || !transform_mat.empty() || normalize_length) {
       // the back-end's per-vector chain, applied before the embeddings leave the device
@@ -823,8 +830,10 @@ int ExtractMain(int argc, const char* const* argv, bool multiple_input) {
       }
       if (total == 0) CVX_LOG("range check: no activation reached the fp16 range limit");
     }
+    const double t_done = since_start();
     for (cvx_engine* e : engines) cvx_engine_destroy(e);
     cvx_model_free(model);
+    if (po.verbose >= 1) CVX_LOG("tear-down (engines, device memory): " << (since_start() - t_done) << " s; " << since_start() << " s since main()");
     return num_success != 0 ? 0 : 1;
   } catch (const std::exception& e) {
     LogMessage("ERROR", "main", __FILE__, __LINE__, e.what());
