@@ -242,8 +242,8 @@ def cli_leg(wl: Workload, host_feats, out_ref: np.ndarray, local_rank: int, mods
                 phases.append(ln.split(") ", 1)[-1])
         got = np.stack([v for _, v in kf.read_ark(f"{d}/xvector.ark")])
         same = bool(got.shape == (CLI_REPLICAS * out_ref.shape[0], out_ref.shape[1]) and
-                    all(np.allclose(got[r * len(out_ref):(r + 1) * len(out_ref)], out_ref, rtol=1e-4, atol=1e-4)
-                        for r in range(CLI_REPLICAS)))
+                    all(float(np.max(np.abs(got[r * len(out_ref):(r + 1) * len(out_ref)] - out_ref))) <= 5e-4 * float(np.max(np.abs(out_ref)))
+                        for r in range(CLI_REPLICAS)))   # other device batches: other summation order / activation form
         return {"wall_s": wall, "in_loop_s": in_loop, "matches_c_abi_output": same, "ark_bytes": os.path.getsize(ark),
                 "device": picked, "phases": phases}
     finally:

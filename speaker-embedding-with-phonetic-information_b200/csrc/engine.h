@@ -125,7 +125,8 @@ class Engine {
     std::vector<KBlockDesc> kb;
     int32_t n_pad = 0, k_pad = 0;
     void* d_w = nullptr;        // [n_pad, k_pad] of elem
-    float2* d_post = nullptr;   // [n_pad]
+    float2* d_post = nullptr;        // [n_pad] {b', o}: dense form, outputs are r + o
+    float2* d_post_sparse = nullptr; // [n_pad] offset-forwarding form (engine.cu): outputs are r, sources' offsets in b'
     TdnnGemmArgs targs;
     TdnnGemmHaloArgs hargs;
     bool halo_ok = false;  // the layer fits the tap-halo kernel's limits
@@ -145,9 +146,10 @@ class Engine {
   void EncodeMaps();
   void BuildHaloArgs(FrameOp& op);
   // pool_meta != NULL: the pooled layer runs with the fused-pooling epilogue (partials -> d_partials_)
+  // sparse: run the offset-forwarding form (hidden activations stored without their BatchNorm offset)
   void RunFrames(const float* const* dev_feats, int64_t rows, int64_t src_row_min, int64_t src_row_max,
                  const PoolGroupMeta* pool_meta = nullptr, float* f32_out = nullptr, int32_t f32_ld = 0,
-                 int32_t pool_slots = 0);
+                 int32_t pool_slots = 0, bool sparse = false);
   void ProfBegin(int cls, double flops, double bytes, int layer = -1);
   void ProfEnd();
   void ProfResolve();
@@ -184,6 +186,7 @@ class Engine {
   int64_t seg_split_rows_ = 0;
   int64_t last_num_chunks_ = 0;
   bool fused_pool_ = false;  // pooled layer's activations are reduced in its GEMM epilogue
+  bool forward_offsets_ = false;  // the sparse form exists (extraction plans; CVX_FORWARD_OFFSETS=0 turns it off)
   void *d_pool_meta_ = nullptr, *d_slot_n_ = nullptr, *d_slot_begin_ = nullptr, *d_chunk_rng_ = nullptr;
   size_t pool_meta_cap_ = 0, slot_n_cap_ = 0, slot_begin_cap_ = 0, chunk_rng_cap_ = 0;
   void RunPrestep(int32_t s, int32_t dim, const cvx_prestep& pre, int32_t u0, int32_t u1, int64_t run0, int64_t num_runs,

@@ -15,6 +15,10 @@ using detail::ElemToFloat;
 using detail::Encode2D;
 using detail::RoundUp;
 
+// A device batch runs the sparse (offset-forwarding) form only if every chunk in it pools at least this many
+// frames: the form's slightly larger activation rounding error needs the pooling average (engine.cu).
+constexpr int32_t kSparseMinPooledFrames = 32;
+
 // -------------------------------------------------------------- extract ----
 void Engine::Extract(const float* const* feats, int32_t num_streams, int64_t total_rows, const int64_t* chunk_start,
                      const int32_t* chunk_len, const int32_t* chunk_utt, const float* chunk_weight,
@@ -291,8 +295,11 @@ void Engine::Extract(const float* const* feats, int32_t num_streams, int64_t tot
       ProfEnd();
     }
     const int32_t batch_slots = fused ? slot_begin_packed[slot_begin_pos[bi] + (b.c1 - b.c0)] : 0;
+    // sparse form (engine.cu, "offset forwarding") unless a chunk of this batch pools only a handful of frames
+    bool sparse = true;
+    for (int64_t c = b.c0; c < b.c1 && sparse; ++c) sparse = chunk_hi[c] - chunk_lo[c] + 1 >= kSparseMinPooledFrames;
     RunFrames(dev, rows, src_min, src_max, fused ? static_cast<const PoolGroupMeta*>(d_pool_meta_) + meta_pos[bi] : nullptr,
-              nullptr, 0, batch_slots);
+              nullptr, 0, batch_slots, sparse);
     if (!dev_in) CVX_CUDA_CHECK(cudaEventRecord(feat_free_[fb], compute_));
 
     const int32_t nslabs = static_cast<int32_t>(b.slab1 - b.slab0);

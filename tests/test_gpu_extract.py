@@ -56,14 +56,24 @@ def test_chunking_semantics(cvx, synth, model_dir, require_gpu):
         assert np.all(got[~ok] == 0)
 
 
-@pytest.mark.parametrize("fused", [False, True])
-def test_ragged_batch_is_bit_identical_to_single(cvx, synth, model_dir, require_gpu, monkeypatch, fused):
+@pytest.mark.parametrize("mode", ["dense-standalone", "dense-fused", "default"])
+def test_ragged_batch_is_bit_identical_to_single(cvx, synth, model_dir, require_gpu, monkeypatch, mode):
     """per-chunk results must not depend on what else is in the packed batch, nor on
     how the engine cuts device batches (guards the edge handling of the packed layout).
     With the stand-alone pooling kernels (CVX_FUSED_POOL=0) this holds bit for bit; the fused
-    pooling epilogue sums in 32-row groups aligned to the batch, so there it holds to ~1e-6."""
-    monkeypatch.setenv("CVX_FUSED_POOL", "1" if fused else "0")
-    same = (lambda x, y: np.allclose(x, y, rtol=2e-5, atol=2e-5)) if fused else np.array_equal
+    pooling epilogue sums in 32-row groups aligned to the batch, so there it holds to ~1e-6.  Both with
+    the dense form pinned (CVX_FORWARD_OFFSETS=0): by default a device batch runs the sparse
+    (offset-forwarding) form unless it holds a chunk that pools < 32 frames -- the 45-frame utterance
+    here -- so a chunk's rounding depends on its batch; the two forms agree to ~1e-4 of the 1e-3 tolerance."""
+    if mode != "default":
+        monkeypatch.setenv("CVX_FORWARD_OFFSETS", "0")
+        monkeypatch.setenv("CVX_FUSED_POOL", "1" if mode == "dense-fused" else "0")
+    if mode == "dense-standalone":
+        same = np.array_equal
+    elif mode == "dense-fused":
+        same = lambda x, y: np.allclose(x, y, rtol=2e-5, atol=2e-5)
+    else:
+        same = lambda x, y: np.max(np.abs(x - y)) <= 5e-4 * np.max(np.abs(y))
     path, model = model_dir("v5_cvector")
     mod = cvx.Model(path, "tdnn6_xvec.affine")
     lengths = [300, 45, 1000, 77, 512, 128]
@@ -78,6 +88,29 @@ def test_ragged_batch_is_bit_identical_to_single(cvx, synth, model_dir, require_
         one, _ = big.extract({k: v[base:base + T] for k, v in feats.items()}, [T], chunk_size=400, min_chunk_size=25)
         assert same(one[0], a[u]), u
         base += T
+
+
+def test_sparse_and_dense_forms_agree(cvx, synth, model_dir, require_gpu, monkeypatch):
+    """offset forwarding (hidden activations stored as relu(.) without the BatchNorm offset, the offset folded
+    into the consumers' biases) is an exact algebraic rewrite: in fp32 the two forms agree to rounding, in fp16
+    to a fraction of the tolerance; utterances that pool < 32 frames keep the dense form either way."""
+    from oracle.nnet3_oracle import Oracle, extract_all, parity_metrics
+    path, model = model_dir("v5_cvector")
+    mod = cvx.Model(path, "tdnn6_xvec.affine")
+    lengths = [300, 1000, 640, 2000]
+    feats = _inputs(synth, mod, lengths, 5)
+    ref, _ = extract_all(Oracle(model, "tdnn6_xvec.affine", np.float64), feats, lengths, chunk_size=500, min_chunk_size=25)
+    out = {}
+    for prec in ("fp32", "fp16"):
+        for fwd in ("0", "1"):
+            monkeypatch.setenv("CVX_FORWARD_OFFSETS", fwd)
+            out[prec, fwd], _ = cvx.Extractor(mod, precision=prec).extract(feats, lengths, chunk_size=500, min_chunk_size=25)
+    assert np.max(np.abs(out["fp32", "0"] - out["fp32", "1"])) <= 2e-5 * np.max(np.abs(ref))
+    assert not np.array_equal(out["fp16", "0"], out["fp16", "1"])          # the sparse form really ran
+    for fwd in ("0", "1"):
+        r, c = parity_metrics(out["fp16", fwd], ref)
+        print(f"forward_offsets={fwd}: rel {r:.3e} cos {c:.8f}")
+        assert r <= TOL_REL and c >= TOL_COS, (fwd, r, c)
 
 
 @pytest.mark.parametrize("name", ["v2_small", "v5_small"])

@@ -11,6 +11,12 @@ pytestmark = pytest.mark.gpu
 TOL_REL, TOL_COS = 1e-3, 0.9999
 
 
+def _same(x, y):
+    """the same utterance computed in two runs whose device batches differ: the fused pooling sums in another
+    order (~1e-6) and the batch may run the other activation form (dense / sparse, DESIGN.md section 6: ~1e-4)."""
+    return np.max(np.abs(np.asarray(x) - np.asarray(y))) <= 5e-4 * np.max(np.abs(y))
+
+
 @pytest.fixture(scope="module")
 def data_dir(tmp_path_factory, cvx, kf, synth, model_dir):
     """A small Kaldi-style data dir: feats.ark/scp (23-dim), utt2num_frames, vad, the v2 net."""
@@ -57,8 +63,8 @@ def test_shards_partition_the_table(cvx, kf, data_dir):
                 assert k not in seen
                 seen[k] = v
         assert set(seen) == set(whole)
-        for k in whole:                                      # batch positions differ: fused pooling sums in another order
-            assert np.allclose(seen[k], whole[k], rtol=2e-5, atol=2e-5)
+        for k in whole:
+            assert _same(seen[k], whole[k]), k
     # an archive cannot be balanced without frame counts
     r = _run(cvx, ["--shard=1/2", data_dir["model"], f"ark:{d}/feats.ark", f"ark:{d}/none.ark"])
     assert r.returncode != 0 and "--utt2num-frames" in r.stderr
@@ -75,7 +81,7 @@ def test_reader_lanes_keep_table_order(cvx, kf, data_dir, monkeypatch):
     assert "3 reader lane(s)" in r3.stderr and "Done 40 utterances, failed for 0" in r3.stderr
     a, b = list(kf.read_ark(f"{d}/one.ark")), list(kf.read_ark(f"{d}/three.ark"))
     assert [k for k, _ in a] == [k for k, _ in b] == data_dir["keys"]
-    assert all(np.allclose(x, y, rtol=2e-5, atol=2e-5) for (_, x), (_, y) in zip(a, b))
+    assert all(_same(x, y) for (_, x), (_, y) in zip(a, b))
     # lanes inside a shard, and an archive input (one sequential stream: batches go to the engines in turn)
     r = _run(cvx, ["--num-gpus=2", "--shard=2/2", data_dir["model"], f"scp:{d}/feats.scp", f"ark:{d}/s22.ark"])
     assert r.returncode == 0, r.stderr
