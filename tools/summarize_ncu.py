@@ -181,7 +181,35 @@ def sass_summary():
     print("sass summary:", len(per), "kernels")
 
 
+def sparse_vs_dense():
+    """same batch, same box, back to back: offset forwarding on (default) vs CVX_FORWARD_OFFSETS=0"""
+    ra, rb = os.path.join(G, f"{tag}_prof_gemm.ncu-rep"), os.path.join(G, f"{tag}dense_prof_gemm.ncu-rep")
+    plan_path = os.path.join(G, f"{tag}_plan.json")
+    if not (os.path.exists(ra) and os.path.exists(rb) and os.path.exists(plan_path)):
+        return
+    layers = json.load(open(plan_path))["layers"]
+    rows = []
+    for rep in (ra, rb):
+        hdr, units, data = raw_table(rep)
+        idx = {h: i for i, h in enumerate(hdr)}
+        rows.append([(to_us(r[idx["gpu__time_duration.sum"]], units[idx["gpu__time_duration.sum"]]),
+                      num(r[idx["sm__cycles_elapsed.avg.per_second"]]),
+                      num(r[idx["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]])) for r in data])
+    lines = [f"# {tag}: offset forwarding (sparse hidden activations) vs the dense form, same batch, same box (ncu --set full --clock-control none)\n",
+             "Commands: `ncu … -k regex:tdnn_gemm -s 33 -c 10 python tools/profile_step.py` and the same with `CVX_FORWARD_OFFSETS=0` "
+             "(tools/profile_r2.sh + one extra capture).  The kernels, tiles and tensor-pipe utilisation are identical; what differs is the "
+             "SM clock the 1 kW cap allows, because about half of the activation operand is exact zeros in the sparse form.", "",
+             "| # | layer | K -> N | sparse: time us | SM clock GHz | tensor pipe % | dense: time us | SM clock GHz | tensor pipe % | time ratio |",
+             "|---|---|---|---|---|---|---|---|---|---|"]
+    for i, (L, a, b) in enumerate(zip(layers, rows[0], rows[1])):
+        lines.append(f"| {i} | {L['name']} | {L['K']} -> {L['N']} | {a[0]:.1f} | {a[1]:.3f} | {a[2]:.1f} | {b[0]:.1f} | {b[1]:.3f} | {b[2]:.1f} | {a[0] / b[0]:.3f} |")
+    ta, tb = sum(a[0] for a in rows[0]), sum(b[0] for b in rows[1])
+    lines += ["", f"Sum over the 10 frame layers: {ta:.0f} us vs {tb:.0f} us = **{ta / tb:.3f}** (the first layers read raw features and do not change)."]
+    open(os.path.join(P, f"{tag}_sparse_vs_dense.md"), "w").write("\n".join(lines) + "\n")
+
+
 os.makedirs(P, exist_ok=True)
+sparse_vs_dense()
 launch_list()
 s = gemm_report(tag, "the 10 frame layers of one 500 000-row batch of the headline net (v5 c-vector), incl. the pooled layer's kPool launch",
                 "Command (tools/profile_r2.sh): `ncu --set full --clock-control none --import-source on -k regex:tdnn_gemm -s 33 -c 10 "
