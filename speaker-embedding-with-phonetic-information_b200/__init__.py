@@ -19,7 +19,8 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libcvx.so")
+# CVX_LIB: another build of the library (A/B runs of kernel variants); the default is the in-tree build
+LIB_PATH = os.environ.get("CVX_LIB") or os.path.join(_HERE, "lib", "libcvx.so")
 BIN_DIR = os.path.join(_HERE, "bin")
 
 PRECISION = {"fp16": 0, "bf16": 1, "fp32": 2}

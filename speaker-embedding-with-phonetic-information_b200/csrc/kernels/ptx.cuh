@@ -43,8 +43,28 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// try_wait blocks in hardware until the phase completes or a time limit passes.  With the default
+// (implementation-defined, short) limit a waiting warp re-issues the instruction every ~50 cycles: a
+// third of all instructions the tap-halo kernel executes were such polls (ncu r2).  A suspend-time hint
+// lets the warp sleep until it is woken by the completion itself (ptxas: NANOSLEEP.SYNCS).  Measured
+// neutral on the step time (same-box A/B, 2 x 2 runs: 842-849 k vs 839-846 k audio-s/s) -- the polls were
+// cheap -- and kept because an idle warp that sleeps is the better citizen.
+#ifndef CVX_MBAR_SUSPEND_NS
+#define CVX_MBAR_SUSPEND_NS 20000
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
+#if CVX_MBAR_SUSPEND_NS > 0
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(static_cast<uint32_t>(CVX_MBAR_SUSPEND_NS))
+      : "memory");
+#else
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
@@ -54,6 +74,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "=r"(ok)
       : "r"(smem_u32(bar)), "r"(parity)
       : "memory");
+#endif
   return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
