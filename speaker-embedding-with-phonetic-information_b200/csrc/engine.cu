@@ -169,7 +169,7 @@ void Engine::Build() {
   // the form is chosen per device batch.  r is larger in magnitude than r + o (o < 0 for a positive BatchNorm
   // mean), so its 16-bit rounding error is ~25 % larger: pooling averages that away at the bench's shapes
   // (2.0e-4 -> 2.5e-4 of the 1e-3 tolerance) but not for a chunk that pools a handful of frames, so a batch
-  // holding a chunk with fewer than kSparseMinPooledFrames pooled frames runs the dense form, as do
+  // holding a chunk of an utterance that pools fewer than kSparseMinPooledFrames frames in total runs the dense form, as do
   // frame-level outputs (nnet3-compute: no average at all).  Never for the pooled / output layer itself.
   forward_offsets_ = !plan_.FrameOutput();
   if (const char* env = std::getenv("CVX_FORWARD_OFFSETS")) forward_offsets_ = forward_offsets_ && env[0] != '0';

@@ -15,8 +15,8 @@ using detail::ElemToFloat;
 using detail::Encode2D;
 using detail::RoundUp;
 
-// A device batch runs the sparse (offset-forwarding) form only if every chunk in it pools at least this many
-// frames: the form's slightly larger activation rounding error needs the pooling average (engine.cu).
+// A device batch runs the sparse (offset-forwarding) form only if every utterance with a chunk in it pools at
+// least this many frames: the form's slightly larger activation rounding error needs the pooling average (engine.cu).
 constexpr int32_t kSparseMinPooledFrames = 32;
 
 // -------------------------------------------------------------- extract ----
@@ -96,6 +96,9 @@ void Engine::Extract(const float* const* feats, int32_t num_streams, int64_t tot
       batches.push_back(b);
     }
   }
+  // pooled frames per utterance (all of its chunks): decides the activation form of its batches
+  std::vector<int64_t> utt_pooled(static_cast<size_t>(num_utts), 0);
+  for (int64_t c = 0; c < num_chunks; ++c) utt_pooled[chunk_utt[c]] += chunk_hi[c] - chunk_lo[c] + 1;
   // ---- fused pooling: per batch, every 32-row group holds at most two runs of valid rows (tail of
   // one chunk, head of the next); slot = one run.  The host only numbers the slots per chunk, the
   // per-group table itself is built on the device (pool_meta_kernel), so this is O(chunks). ----
@@ -295,9 +298,10 @@ void Engine::Extract(const float* const* feats, int32_t num_streams, int64_t tot
       ProfEnd();
     }
     const int32_t batch_slots = fused ? slot_begin_packed[slot_begin_pos[bi] + (b.c1 - b.c0)] : 0;
-    // sparse form (engine.cu, "offset forwarding") unless a chunk of this batch pools only a handful of frames
+    // sparse form (engine.cu, "offset forwarding") unless an utterance with chunks in this batch pools only a
+    // handful of frames in total (a short tail chunk of a long utterance carries a tiny weight in its average)
     bool sparse = true;
-    for (int64_t c = b.c0; c < b.c1 && sparse; ++c) sparse = chunk_hi[c] - chunk_lo[c] + 1 >= kSparseMinPooledFrames;
+    for (int64_t c = b.c0; c < b.c1 && sparse; ++c) sparse = utt_pooled[chunk_utt[c]] >= kSparseMinPooledFrames;
     RunFrames(dev, rows, src_min, src_max, fused ? static_cast<const PoolGroupMeta*>(d_pool_meta_) + meta_pos[bi] : nullptr,
               nullptr, 0, batch_slots, sparse);
     if (!dev_in) CVX_CUDA_CHECK(cudaEventRecord(feat_free_[fb], compute_));
