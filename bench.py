@@ -447,6 +447,8 @@ def main() -> None:
             gm = p2["tdnn_gemm"]
             other[wid] = {"value": w2.audio_sec / (ms_plain / 1e3), "ms_per_step": ms_plain, "ms_per_step_profiled": ms_prof,
                           "gemm_ms_per_step": gm["total_ms"] / 3, "gemm_frac": gm["flops"] / (gm["total_ms"] * 1e-3) / 1e12 / peaks()["tflops"],
+                          # of the SUSTAINED measured peak: millisecond steps run at burst clocks and can exceed 1
+                          "gemm_frac_of": "sustained bf16 GEMM peak (MEASURED_PEAKS.json)",
                           "topology": w2.topology, "frames": w2.total_rows, "utts": w2.n_utts,
                           "outputs_finite": bool(np.isfinite(o2).all() and np.abs(o2).sum() > 0)}
             ex2.close()
