@@ -46,7 +46,7 @@ struct TdnnGemmArgs {
   KBlockDesc kb[kMaxKBlocks];
   int32_t num_kb;
   int32_t n_pad;          // output row pitch, multiple of 64
-  int32_t n_mma;          // roundup(out_dim, 32): columns the MMAs produce
+  int32_t n_mma;          // roundup(out_dim, 16 or 32): columns the MMAs produce; the store maps end here
   int32_t tile_n;         // N tile width: n_mma split into equal tiles, multiple of 32, <= 256
   int32_t num_m_tiles;    // ceil(rows / 128)
   int32_t num_n_tiles;    // ceil(n_pad / 256)

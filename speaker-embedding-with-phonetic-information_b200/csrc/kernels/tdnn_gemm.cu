@@ -178,7 +178,8 @@ __global__ void __launch_bounds__(kThreads, 1) tdnn_gemm_kernel(const __grid_con
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m0 = (tile / num_n_tiles) * kGemmBlockM;
       const int n0 = (tile % num_n_tiles) * args.tile_n;
-      const int n_cols = min(args.tile_n, args.n_mma - n0);  // multiple of 32
+      // whole 32-column units; columns beyond n_mma (a 16-column tail no MMA wrote) are clipped by the store maps
+      const int n_cols = (min(args.tile_n, args.n_mma - n0) + 31) & ~31;
       const int n_chunks = (n_cols + 63) >> 6;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;

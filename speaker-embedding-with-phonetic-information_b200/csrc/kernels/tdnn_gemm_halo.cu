@@ -220,7 +220,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       const int m0 = (tile / num_n_tiles) * (2 * kGemmBlockM) + static_cast<int>(rank) * kGemmBlockM;
       const int n0 = (tile % num_n_tiles) * args.tile_n;
       constexpr int kChunkCols = kOutF32 ? 32 : 64;  // 128 bytes of output per row and chunk
-      const int n_cols = min(args.tile_n, args.n_mma - n0);  // multiple of 32
+      // whole 32-column units; columns beyond n_mma (a 16-column tail no MMA wrote) are clipped by the store maps
+      const int n_cols = (min(args.tile_n, args.n_mma - n0) + 31) & ~31;
       const int n_chunks = (n_cols + kChunkCols - 1) / kChunkCols;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;

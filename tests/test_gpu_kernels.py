@@ -30,6 +30,11 @@ CASES = [
     (515, 650, [-1, 0, 1], 650),             # AM layers: K and N need padding
     (129, 650, [-6, -3, 0], 128),            # AM bottleneck
     (64, 40, [0], 64),                       # tiny
+    # widths that end in a 16-column tail (the MMAs produce roundup(out_dim, 16) columns, the store maps clip there)
+    (300, 64, [0], 40),                      # one tile of 48 columns: full-chunk store clipped at 48
+    (260, 96, [-1, 0, 1], 272),              # tiles 160 + 112: the second ends in a 48-column chunk
+    (300, 128, [-2, 0, 2], 330),             # tiles 192 + 144: the second ends in a clipped half chunk
+    (200, 64, [0], 10),                      # N = 16, the narrowest instruction
 ]
 
 
