@@ -422,6 +422,11 @@ int32_t Engine::StagingFor(const std::vector<Tap>& taps) {
 void Engine::EnsureRows(int64_t rows) {
   int64_t need = (rows + kGemmBlockM - 1) / kGemmBlockM * kGemmBlockM;
   if (need <= rows_cap_) return;
+  // A job of many calls cuts device batches of slightly different sizes just below max_batch_rows_: growing to
+  // exactly `need` re-allocated every activation buffer (GBs: free + malloc + clear + new tensor maps) whenever
+  // a batch beat the previous record.  Anything beyond a small job gets the full batch size at once.
+  static const bool grow_exact = std::getenv("CVX_GROW_EXACT") != nullptr;  // A/B aid: the old policy
+  if (need * 4 > max_batch_rows_ && !grow_exact) need = std::max(need, max_batch_rows_);
   CVX_CUDA_CHECK(cudaStreamSynchronize(compute_));
   CVX_CUDA_CHECK(cudaStreamSynchronize(copy_));
   for (Buffer& b : buffers_) {

@@ -1,6 +1,8 @@
 // Engine::Extract -- the hot path: packed ragged batches of chunks -> per-utterance embeddings.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <climits>
 #include <cstdlib>
 #include <cstring>
@@ -23,6 +25,12 @@ constexpr int32_t kSparseMinPooledFrames = 32;
 void Engine::Extract(const float* const* feats, int32_t num_streams, int64_t total_rows, const int64_t* chunk_start,
                      const int32_t* chunk_len, const int32_t* chunk_utt, const float* chunk_weight,
                      int64_t num_chunks, int32_t num_utts, float* out, uint32_t flags) {
+  // CVX_TRACE=1: host-side phases of every call on stderr (where a call's wall time goes beyond its device time)
+  static const bool trace = std::getenv("CVX_TRACE") != nullptr;
+  const auto t_enter = std::chrono::steady_clock::now();
+  auto ms_since = [](std::chrono::steady_clock::time_point t) {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count();
+  };
   CVX_CUDA_CHECK(cudaSetDevice(opts_.device));
   if (num_streams != static_cast<int32_t>(plan_.input_dims.size()))
     throw InvalidArgument("model has " + std::to_string(plan_.input_dims.size()) + " input stream(s), got " +
@@ -152,6 +160,7 @@ void Engine::Extract(const float* const* feats, int32_t num_streams, int64_t tot
   }
 
   // ---- device scratch ----
+  const double ms_tables = ms_since(t_enter);
   int64_t max_rows = 0, max_chunks = 0, max_slabs = 0;
   for (const Batch& b : batches) {
     max_rows = std::max(max_rows, b.row1 - b.row0);
@@ -196,6 +205,7 @@ void Engine::Extract(const float* const* feats, int32_t num_streams, int64_t tot
       for (int32_t s = 0; s < num_streams; ++s)
         Grow(&d_feat_[i][s], &d_feat_cap_[i][s], static_cast<size_t>(max_rows) * plan_.input_dims[s] * 4);
 
+  const double ms_scratch = ms_since(t_enter);
   if (fused) {
     int32_t* rng = static_cast<int32_t*>(d_chunk_rng_);
     CVX_CUDA_CHECK(cudaMemcpyAsync(rng, chunk_lo.data(), static_cast<size_t>(num_chunks) * 4, cudaMemcpyHostToDevice, compute_));
@@ -260,6 +270,7 @@ void Engine::Extract(const float* const* feats, int32_t num_streams, int64_t tot
   };
 
   // ---- batches ----
+  const double ms_meta = ms_since(t_enter);
   CVX_CUDA_CHECK(cudaEventRecord(call_begin_, compute_));
   int64_t pending = 0, pending_c0 = 0;  // chunks whose statistics wait for the segment layers
   for (size_t bi = 0; bi < batches.size(); ++bi) {
@@ -369,10 +380,18 @@ void Engine::Extract(const float* const* feats, int32_t num_streams, int64_t tot
     CVX_CUDA_CHECK(cudaStreamWaitEvent(compute_, out_free_[0], 0));
   }
   CVX_CUDA_CHECK(cudaEventRecord(call_end_, compute_));
+  const double ms_enqueued = ms_since(t_enter);
   CVX_CUDA_CHECK(cudaStreamSynchronize(compute_));
   CVX_CUDA_CHECK(cudaEventElapsedTime(&last_call_ms_, call_begin_, call_end_));
   ProfResolve();
   last_num_chunks_ = num_chunks;
+  if (trace)
+    std::fprintf(stderr,
+                 "cvx trace: extract rows=%lld chunks=%lld batches=%zu | tables %.2f ms, device scratch %.2f, table upload + sync %.2f, "
+                 "enqueue %.2f, wait %.2f | device %.2f ms, rows_cap %lld\n",
+                 static_cast<long long>(total_rows), static_cast<long long>(num_chunks), batches.size(), ms_tables,
+                 ms_scratch - ms_tables, ms_meta - ms_scratch, ms_enqueued - ms_meta, ms_since(t_enter) - ms_enqueued,
+                 static_cast<double>(last_call_ms_), static_cast<long long>(rows_cap_));
 }
 
 void Engine::LastChunkEmbeddings(float* out, int64_t num_chunks) {

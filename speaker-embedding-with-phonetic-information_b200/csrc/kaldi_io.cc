@@ -195,7 +195,7 @@ int Input::Get() {
 void Input::Read(void* dst, size_t n) {
   unsigned char* d = static_cast<unsigned char*>(dst);
   while (n) {
-    if (pos_ >= end_ && n >= (size_t{1} << 20) && fp_ && !is_pipe_ && !is_stdin_) {
+    if (pos_ >= end_ && n >= (size_t{1} << 18) && fp_ && !is_pipe_ && !is_stdin_) {
       // large body from a file: two to four threads pread() a part each -- one thread copies ~4.5 GB/s out of
       // the page cache, one B200 consumes 7.5 GB/s of features on the c-vector net
       const long off = std::ftell(fp_);
@@ -203,7 +203,8 @@ void Input::Read(void* dst, size_t n) {
       if (off >= 0 && fd >= 0) {
         // this reader thread's persistent helpers take the later parts, the thread itself the first
         PreadHelper* helpers = ThreadPreadHelpers();
-        const int parts = n >= (size_t{4} << 20) ? kPreadHelpers + 1 : 2;
+        // (a part of >= 128 KB is >= 30 us of copying against ~10 us to wake a helper)
+        const int parts = n >= (size_t{1} << 20) ? kPreadHelpers + 1 : 2;
         const size_t step = (n / parts) & ~size_t{4095};
         for (int p = 1; p < parts; ++p) {
           const size_t begin = step * p, end = p + 1 == parts ? n : step * (p + 1);

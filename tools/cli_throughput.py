@@ -60,7 +60,7 @@ def run(label, out, extra, feat):
     assert r.returncode == 0, r.stderr[-2000:]
     report(label, dt, r.stderr)
     for ln in r.stderr.splitlines():
-        if "lane timing" in ln or "Selected GPU" in ln or "start-up:" in ln or "tear-down" in ln:
+        if "lane timing" in ln or "Selected GPU" in ln or "start-up:" in ln or "tear-down" in ln or "cvx trace" in ln:
             print("     " + ln.split(") ", 1)[-1], flush=True)
 
 
