@@ -64,6 +64,34 @@ int32_t ChooseDevice(int32_t gpu_id, const std::string& use_gpu, int32_t num_gpu
       }
     }
   }
+  // CUDA_VISIBLE_DEVICES already set (a container runtime, a scheduler): the choice is among its entries, and
+  // it can still be made before CUDA starts -- the lock is named after the entry, the winner becomes the only
+  // visible device.  (All jobs of a stage inherit the same list; a job that names the same GPU differently, or
+  // selects through CUDA, does not see these locks.)
+  if (const char* cvd_env = std::getenv("CUDA_VISIBLE_DEVICES")) {
+    const std::string cvd = cvd_env;  // setenv below may free the old value
+    std::vector<std::string> entries;
+    bool usable = !std::getenv("CVX_SELECT_WITH_CUDA");
+    std::istringstream list(cvd);
+    for (std::string e; usable && std::getline(list, e, ',');) {
+      const size_t a = e.find_first_not_of(" \t"), b = e.find_last_not_of(" \t");
+      if (a == std::string::npos || e[a] == '-') usable = false;  // CUDA stops at an empty or negative entry
+      else entries.push_back(e.substr(a, b - a + 1));
+    }
+    if (usable && !entries.empty()) {
+      std::vector<std::string> names;
+      for (const std::string& e : entries) names.push_back("cvd-" + e);
+      std::vector<const char*> c;
+      for (const std::string& n : names) c.push_back(n.c_str());
+      if (cvx_acquire_device_by_id(c.data(), static_cast<int32_t>(c.size()), use_gpu == "wait" ? 1 : 0, &dev, &sharers) == CVX_OK) {
+        setenv("CUDA_VISIBLE_DEVICES", entries[dev].c_str(), 1);
+        if (sharers == 0) CVX_LOG("Selected GPU " << entries[dev] << " (entry " << dev << " of CUDA_VISIBLE_DEVICES=" << cvd << ": free; held for this job)");
+        else CVX_LOG("All " << entries.size() << " GPUs of CUDA_VISIBLE_DEVICES=" << cvd << " are in use by other jobs; sharing GPU "
+                            << entries[dev] << " with " << sharers << " other job(s)");
+        return 0;  // the only device CUDA will see
+      }
+    }
+  }
   if (cvx_acquire_device(use_gpu == "wait" ? 1 : 0, &dev, &sharers) != CVX_OK)
     throw KaldiError(std::string("selecting a GPU: ") + cvx_last_error());
   if (sharers == 0) CVX_LOG("Selected GPU " << dev << " (free; held for this job)");

@@ -130,3 +130,39 @@ def test_shard_option_is_validated(cvx):
     for bad in ("3", "0/4", "5/4", "a/b", "1/0"):
         r = subprocess.run([exe, f"--shard={bad}", "final.raw", "ark:/dev/null", "ark:/dev/null"], capture_output=True, text=True)
         assert r.returncode != 0 and "--shard expects J/N" in r.stderr, (bad, r.stderr)
+
+
+def test_selection_among_cuda_visible_devices_entries_happens_before_cuda(cvx, tmp_path):
+    """With CUDA_VISIBLE_DEVICES set (container runtimes do), a job picks one ENTRY of the list through the lock
+    files and makes it the only visible device -- no CUDA call is needed for the choice (it is logged before
+    the model is even opened, so this runs without a GPU)."""
+    import fcntl
+    exe = os.path.join(cvx.BIN_DIR, "nnet3-xvector-compute")
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="3, GPU-AbC", CVX_LOCK_DIR=str(tmp_path))
+    env.pop("CVX_DEVICE", None)
+    env.pop("CVX_SELECT_WITH_CUDA", None)
+
+    def run():
+        r = subprocess.run([exe, "--use-gpu=yes", str(tmp_path / "missing.raw"), "ark:/dev/null", "ark:/dev/null"],
+                           capture_output=True, text=True, env=env)
+        assert r.returncode != 0  # no model (and here no GPU): the job fails AFTER the selection
+        return [ln for ln in r.stderr.splitlines() if "GPU" in ln and ("Selected" in ln or "sharing" in ln)]
+
+    assert "Selected GPU 3 (entry 0 of CUDA_VISIBLE_DEVICES=3, GPU-AbC" in run()[0]
+    held = []
+    try:
+        for name in ("cvd-3.0", "cvd-gpu-abc.0"):  # lock names are lower-cased ids; round 0 = exclusive use
+            f = open(tmp_path / f"cvx-gpu-{os.getuid()}-{name}", "a+")
+            fcntl.flock(f, fcntl.LOCK_EX | fcntl.LOCK_NB)
+            held.append(f)
+            line = run()[0]
+            if len(held) == 1:
+                assert "Selected GPU GPU-AbC (entry 1 of" in line, line
+            else:
+                assert "sharing GPU 3 with 1 other job(s)" in line, line
+    finally:
+        for f in held:
+            f.close()
+    # a list CUDA itself would cut short is left to the CUDA path
+    env["CUDA_VISIBLE_DEVICES"] = "-1"
+    assert run() == []
