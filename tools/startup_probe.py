@@ -2,7 +2,8 @@
 extract_xvectors_new.sh:83-89), device picked (a) through CUDA enumeration (CVX_SELECT_WITH_CUDA=1: every job
 initialises every visible GPU first) and (b) before CUDA starts (default: among the CUDA_VISIBLE_DEVICES entries /
 /proc bus ids; the job then sees one device).  Prints every job's start-up and lane-timing lines.
-  python tools/startup_probe.py [gpus=8] [n_utts=600]"""
+  python tools/startup_probe.py [gpus=8] [n_utts=600] [all|short]
+(c) the same work from ONE process with --num-gpus=G."""
 import importlib
 import os
 import subprocess
@@ -52,8 +53,30 @@ def run_many(label, extra_env):
         print("   " + " | ".join(k[:150] for k in keep), flush=True)
 
 
+def run_one_process(label):
+    """the same G shares from ONE process: --num-gpus=G (reader lanes), CUDA initialised once"""
+    env = dict(os.environ, CVX_LOCK_DIR=d)
+    env.pop("CVX_DEVICE", None)
+    big = os.path.join(d, "all.scp")  # G copies of the table under distinct keys = the G jobs' total work
+    with open(big, "w") as f:
+        for g in range(gpus):
+            for ln in open(scp):
+                f.write(f"g{g}_{ln}")
+    t0 = time.perf_counter()
+    r = subprocess.run(base + [f"--num-gpus={gpus}", model, f"scp:{big}", f"ark:{d}/all.ark"], stderr=subprocess.PIPE, text=True, env=env)
+    dt = time.perf_counter() - t0
+    assert r.returncode == 0, r.stderr[-2000:]
+    print(f"== {label}: 1 process, --num-gpus={gpus}, {gpus} x {frames} frames, {dt:.2f} s wall", flush=True)
+    for ln in r.stderr.splitlines():
+        if "start-up:" in ln or "since main" in ln or "Time taken" in ln:
+            print("   " + ln.split(") ", 1)[-1][:200], flush=True)
+
+
+mode = sys.argv[3] if len(sys.argv) > 3 else "all"
 for rep in range(2):
-    run_many(f"selection through CUDA (run {rep})", {"CVX_SELECT_WITH_CUDA": "1"})
+    if mode == "all":
+        run_many(f"selection through CUDA (run {rep})", {"CVX_SELECT_WITH_CUDA": "1"})
     run_many(f"selection before CUDA (run {rep})", {})
+    run_one_process(f"one process (run {rep})")
 import shutil
 shutil.rmtree(d, ignore_errors=True)
